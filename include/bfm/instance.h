@@ -1,0 +1,3 @@
+#pragma once
+// forwarder: the declarations the reference keeps in bfm/instance.h live in bfm/libbfm.h
+#include <bfm/libbfm.h>
