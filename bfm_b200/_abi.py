@@ -291,7 +291,7 @@ assert len(PROTOTYPES) == 67
 def bind(path: str, extra: dict | None = None) -> C.CDLL:
 	"""dlopen ``path`` and attach prototypes; raises if any of the 67 symbols is missing."""
 
-	lib = C.CDLL(os.path.abspath(path), mode=C.RTLD_GLOBAL if extra else C.RTLD_LOCAL)
+	lib = C.CDLL(os.path.abspath(path), mode=C.RTLD_LOCAL)  # never global: ours and the reference export the same names
 
 	for name, (restype, argtypes) in {**PROTOTYPES, **(extra or {})}.items():
 		fn = getattr(lib, name)  # AttributeError = missing export

@@ -1,0 +1,277 @@
+/*
+ * context.cu - device context of libbfm (B200 build): one device, one non-blocking stream, a
+ * stream-ordered memory pool, an event stopwatch and the kernel-launch counter.
+ *
+ * Part of the thin C ABI declared in gpu.h.  If no CUDA device can be initialised every entry point
+ * fails with -1 and a message - the library has no CPU path.
+ */
+#include "gpu_internal.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+
+namespace {
+
+struct Context {
+	bool tried = false;
+	bool ok = false;
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	size_t launches = 0;
+	char err[512] = "";
+
+	static constexpr int kEvents = 64;
+	cudaEvent_t events[kEvents];
+	int next_event = 0;
+
+	void* pinned = nullptr;      /* 4 KiB of page-locked host memory for status polls */
+	cudaEvent_t poll[2] = {};    /* untimed events marking those polls */
+};
+
+Context G;
+
+void set_error(char const* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(G.err, sizeof G.err, fmt, ap);
+	va_end(ap);
+}
+
+bool init() {
+	if (G.tried) {
+		return G.ok;
+	}
+
+	G.tried = true;
+
+	int count = 0;
+	cudaError_t rc = cudaGetDeviceCount(&count);
+
+	if (rc != cudaSuccess || count == 0) {
+		set_error("no usable CUDA device (%s); libbfm's hot path is GPU-only and has no CPU fallback", rc != cudaSuccess ? cudaGetErrorString(rc) : "device count is 0");
+		cudaGetLastError();
+		return false;
+	}
+
+	/* one process per GPU: honour BFM_DEVICE, else LOCAL_RANK (torchrun), else the current device */
+
+	char const* env = getenv("BFM_DEVICE");
+
+	if (env == nullptr) {
+		env = getenv("LOCAL_RANK");
+	}
+
+	if (env != nullptr) {
+		G.device = atoi(env) % count;
+	}
+
+	else if (cudaGetDevice(&G.device) != cudaSuccess) {
+		G.device = 0;
+	}
+
+	if ((rc = cudaSetDevice(G.device)) != cudaSuccess) {
+		set_error("cudaSetDevice(%d): %s", G.device, cudaGetErrorString(rc));
+		return false;
+	}
+
+	cudaDeviceProp prop;
+
+	if ((rc = cudaGetDeviceProperties(&prop, G.device)) != cudaSuccess) {
+		set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(rc));
+		return false;
+	}
+
+	G.sm_count = prop.multiProcessorCount;
+
+	if ((rc = cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking)) != cudaSuccess) {
+		set_error("cudaStreamCreate: %s", cudaGetErrorString(rc));
+		return false;
+	}
+
+	/* keep freed blocks in the pool: repeated bfm_sim_run calls reuse them without going to the driver */
+
+	cudaMemPool_t pool;
+
+	if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) {
+		uint64_t keep = UINT64_MAX;
+		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+	}
+
+	for (auto& ev : G.events) {
+		if ((rc = cudaEventCreate(&ev)) != cudaSuccess) {
+			set_error("cudaEventCreate: %s", cudaGetErrorString(rc));
+			return false;
+		}
+	}
+
+	for (auto& ev : G.poll) {
+		if ((rc = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) {
+			set_error("cudaEventCreate: %s", cudaGetErrorString(rc));
+			return false;
+		}
+	}
+
+	if ((rc = cudaMallocHost(&G.pinned, 4096)) != cudaSuccess) {
+		set_error("cudaMallocHost: %s", cudaGetErrorString(rc));
+		return false;
+	}
+
+	G.ok = true;
+	return true;
+}
+
+} // namespace
+
+/* ---- internal accessors (gpu_internal.cuh) ----------------------------------------------------- */
+
+bool bfmg_ready() {
+	if (!init()) {
+		return false;
+	}
+
+	cudaSetDevice(G.device); /* cheap; keeps us correct if the host program switched devices */
+	return true;
+}
+
+cudaStream_t bfmg_stream() {
+	return G.stream;
+}
+
+void* bfmg_pinned() {
+	return G.pinned;
+}
+
+cudaEvent_t bfmg_poll_event(int i) {
+	return G.poll[i & 1];
+}
+
+void bfmg_count_launch(size_t n) {
+	G.launches += n;
+}
+
+int bfmg_check(cudaError_t rc, char const* what, char const* file, int line) {
+	if (rc == cudaSuccess) {
+		return 0;
+	}
+
+	set_error("%s: %s (%s:%d)", what, cudaGetErrorString(rc), file, line);
+	cudaGetLastError();
+	return -1;
+}
+
+/* ---- gpu.h --------------------------------------------------------------------------------------- */
+
+extern "C" {
+
+int bfmg_available(void) {
+	return bfmg_ready() ? 1 : 0;
+}
+
+char const* bfmg_last_error(void) {
+	return G.err;
+}
+
+int bfmg_sm_count(void) {
+	return bfmg_ready() ? G.sm_count : 0;
+}
+
+size_t bfmg_launch_count(void) {
+	return G.launches;
+}
+
+int bfmg_alloc(void** d_ptr, size_t bytes) {
+	*d_ptr = nullptr;
+
+	if (!bfmg_ready()) {
+		return -1;
+	}
+
+	return BFMG_CHECK(cudaMallocAsync(d_ptr, bytes ? bytes : 16, G.stream));
+}
+
+void bfmg_free(void* d_ptr) {
+	if (d_ptr != nullptr && G.ok) {
+		cudaSetDevice(G.device);
+		cudaFreeAsync(d_ptr, G.stream);
+	}
+}
+
+int bfmg_upload(void* d_dst, void const* src, size_t bytes) {
+	if (!bfmg_ready()) {
+		return -1;
+	}
+
+	if (bytes == 0) {
+		return 0;
+	}
+
+	/* the source is pageable host memory owned by the caller: the copy is staged by the driver and has
+	 * returned from the host buffer's point of view when the call returns */
+	return BFMG_CHECK(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, G.stream));
+}
+
+int bfmg_download(void* dst, void const* d_src, size_t bytes) {
+	if (!bfmg_ready()) {
+		return -1;
+	}
+
+	if (bytes != 0 && BFMG_CHECK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, G.stream)) < 0) {
+		return -1;
+	}
+
+	return BFMG_CHECK(cudaStreamSynchronize(G.stream));
+}
+
+int bfmg_copy(void* d_dst, void const* d_src, size_t bytes) {
+	if (!bfmg_ready()) {
+		return -1;
+	}
+
+	return bytes ? BFMG_CHECK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, G.stream)) : 0;
+}
+
+int bfmg_zero(void* d_dst, size_t bytes) {
+	if (!bfmg_ready()) {
+		return -1;
+	}
+
+	return bytes ? BFMG_CHECK(cudaMemsetAsync(d_dst, 0, bytes, G.stream)) : 0;
+}
+
+int bfmg_sync(void) {
+	if (!bfmg_ready()) {
+		return -1;
+	}
+
+	return BFMG_CHECK(cudaStreamSynchronize(G.stream));
+}
+
+int bfmg_tick(void) {
+	if (!bfmg_ready()) {
+		return -1;
+	}
+
+	int const slot = G.next_event;
+	G.next_event = (G.next_event + 1) % Context::kEvents;
+
+	return BFMG_CHECK(cudaEventRecord(G.events[slot], G.stream)) < 0 ? -1 : slot;
+}
+
+float bfmg_lap(int from, int to) {
+	if (from < 0 || to < 0 || !G.ok) {
+		return -1;
+	}
+
+	float ms = -1;
+
+	if (cudaEventSynchronize(G.events[to]) != cudaSuccess || cudaEventElapsedTime(&ms, G.events[from], G.events[to]) != cudaSuccess) {
+		cudaGetLastError();
+		return -1;
+	}
+
+	return ms;
+}
+
+} // extern "C"

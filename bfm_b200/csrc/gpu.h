@@ -1,0 +1,125 @@
+/*
+ * gpu.h - the thin C ABI between libbfm's host code (C) and its sm_100a CUDA kernels (.cu).
+ *
+ * Plain pointers and sizes only.  Every pointer named d_* is device memory obtained from
+ * bfmg_alloc; everything runs on the library's own stream.  All functions return 0 on success and
+ * -1 on failure (bfmg_last_error() says why).  There is no CPU fallback behind any of them.
+ */
+#ifndef BFM_GPU_H
+#define BFM_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- context --------------------------------------------------------------------------------- */
+
+int bfmg_available(void);              /* 1 when a CUDA device is usable (initialises lazily) */
+char const* bfmg_last_error(void);
+int bfmg_sm_count(void);
+size_t bfmg_launch_count(void);        /* kernels launched by this library so far */
+
+int bfmg_alloc(void** d_ptr, size_t bytes);
+void bfmg_free(void* d_ptr);
+int bfmg_upload(void* d_dst, void const* src, size_t bytes);
+int bfmg_download(void* dst, void const* d_src, size_t bytes); /* synchronises */
+int bfmg_copy(void* d_dst, void const* d_src, size_t bytes);
+int bfmg_zero(void* d_dst, size_t bytes);
+int bfmg_sync(void);
+
+/* CUDA-event stopwatch on the library stream: tick returns a handle, lap gives ms between two */
+int bfmg_tick(void);
+float bfmg_lap(int from, int to);      /* synchronises on `to` */
+
+/* ---- sparsity pattern on the device (mirror of bfmi_plan_t, see internal.h) ------------------- */
+
+typedef struct {
+	int32_t nb;
+	int32_t n_slices;
+	int64_t n_slots;
+	int32_t kind;
+
+	int32_t* slice_off;
+	int32_t* row_len;
+	int32_t* scol;
+	int32_t* diag_pos;
+	int32_t* ctr_ptr;
+	uint32_t* ctr;
+	int32_t* elems;
+} bfmg_pattern_t;
+
+/* ---- assembly -------------------------------------------------------------------------------- */
+
+#define BFMG_MAX_POINTS 8
+#define BFMG_MAX_FORCES 8
+
+/* shape-function tables at the integration points, material constants, constant body forces */
+typedef struct {
+	int32_t kind;       /* nodes per element: 3 or 4 */
+	int32_t n_points;
+	int32_t axisym;     /* 0 planar, 1 axisymmetric */
+	int32_t grad_const; /* 1 when dxsi/deta do not depend on the point (P1): geometry computed once */
+
+	double a, b, c;     /* elasticity constants (reference system.c:454-458 / :242-244) */
+	double rho;
+
+	double weight[BFMG_MAX_POINTS];
+	double phi[BFMG_MAX_POINTS][4];
+	double dxsi[BFMG_MAX_POINTS][4];
+	double deta[BFMG_MAX_POINTS][4];
+
+	int32_t n_forces;
+	int32_t forces_per_node; /* 0: const_force[k] applies everywhere; 1: d_nforce[k][node] tables */
+	double const_force[BFMG_MAX_FORCES][2];
+} bfmg_asm_tables_t;
+
+/* one launch: stiffness blocks + load vector.  d_val: 4 * n_slots doubles, d_b: 2 * nb doubles */
+int bfmg_assemble(bfmg_pattern_t const* pat, bfmg_asm_tables_t const* tab, double const* d_coords, double const* d_nforce, double* d_val, double* d_b);
+
+/* ---- boundary conditions --------------------------------------------------------------------- */
+
+/* one Dirichlet-type condition (reference apply_constraint, system.c:358-374, for every listed DOF
+ * in ascending order): d_dofs/d_vals list the constrained DOFs, d_rows the block rows whose entries
+ * or right-hand side can change; d_stamp/d_cval are 2*nb scratch arrays owned by the caller, epoch
+ * must be unique per call and non-zero */
+int bfmg_bc_dirichlet(bfmg_pattern_t const* pat, double* d_val, double* d_b, int32_t* d_stamp, double* d_cval, int32_t epoch, int32_t const* d_dofs, double const* d_vals, int32_t n_dofs, int32_t const* d_rows, int32_t n_rows);
+
+/* right-hand-side additions (Neumann edge loads), grouped by DOF, applied in list order */
+int bfmg_bc_add(double* d_b, int32_t const* d_group_dof, int32_t const* d_group_ptr, double const* d_add, int32_t n_groups);
+
+/* ---- FP64 conjugate gradient ----------------------------------------------------------------- */
+
+typedef struct {
+	double tol;          /* stop at ||r|| <= tol * ||b|| in the Jacobi-scaled norm */
+	int32_t max_iter;
+	int32_t chunk;       /* iterations enqueued between two convergence polls */
+	int32_t verify;      /* recompute the true residual at the end (and restart if it drifted) */
+} bfmg_pcg_opts_t;
+
+typedef struct {
+	int32_t iterations;
+	int32_t converged;   /* 1 converged, 0 hit max_iter, -1 breakdown */
+	int32_t restarts;
+	double rel_residual;      /* recursive residual, scaled norm */
+	double true_rel_residual; /* ||b - A x|| / ||b||, scaled norm (NaN if not verified) */
+	float ms;
+	size_t launches;
+} bfmg_pcg_result_t;
+
+/* solves A x = b; d_val is left untouched (a scaled copy is made) */
+int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res);
+
+/* times `reps` back-to-back launches of the CG SpMV kernel (q = A p with the fused dot) on d_val */
+int bfmg_spmv_time(bfmg_pattern_t const* pat, double const* d_val, int reps, float* ms_per_launch);
+
+/* y = A x, plain (tests) */
+int bfmg_spmv(bfmg_pattern_t const* pat, double const* d_val, double const* d_x, double* d_y);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

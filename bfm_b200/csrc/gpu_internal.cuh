@@ -1,0 +1,61 @@
+/*
+ * gpu_internal.cuh - helpers shared by the .cu translation units (not part of any ABI).
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "gpu.h"
+
+#define BFMG_HIDDEN __attribute__((visibility("hidden")))
+
+BFMG_HIDDEN bool bfmg_ready();                 /* context initialised and current */
+BFMG_HIDDEN cudaStream_t bfmg_stream();
+BFMG_HIDDEN void bfmg_count_launch(size_t n);
+BFMG_HIDDEN void* bfmg_pinned();               /* 4 KiB page-locked scratch */
+BFMG_HIDDEN cudaEvent_t bfmg_poll_event(int i); /* two untimed events */
+BFMG_HIDDEN int bfmg_check(cudaError_t rc, char const* what, char const* file, int line);
+
+#define BFMG_CHECK(call) bfmg_check((call), #call, __FILE__, __LINE__)
+
+/* launch on the library stream, count it, report configuration errors */
+#define BFMG_LAUNCH(kernel, grid, block, smem, ...)                       \
+	(bfmg_count_launch(1), (kernel)<<<(grid), (block), (smem), bfmg_stream()>>>(__VA_ARGS__), \
+	 bfmg_check(cudaGetLastError(), #kernel, __FILE__, __LINE__))
+
+constexpr int kWarp = 32;
+constexpr int kBlock = 256;                  /* 8 warps per CTA for every kernel in this library */
+constexpr int kWarpsPerBlock = kBlock / kWarp;
+
+/* persistent-style grids: a multiple of the SM count, capped by the amount of work */
+static inline int bfmg_grid(int64_t work_items_per_block_units, int ctas_per_sm) {
+	int64_t const cap = (int64_t) bfmg_sm_count() * ctas_per_sm;
+	int64_t g = work_items_per_block_units < cap ? work_items_per_block_units : cap;
+	return (int) (g < 1 ? 1 : g);
+}
+
+/* streaming 16-byte loads that do not pollute L1 (matrix values and column indices are read once per
+ * SpMV; L1 is kept for the gathered vector) */
+__device__ __forceinline__ double2 ld_stream(double2 const* p) {
+	double2 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+	return v;
+}
+
+__device__ __forceinline__ int ld_stream(int const* p) {
+	int v;
+	asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+	for (int off = kWarp / 2; off > 0; off >>= 1) {
+		v += __shfl_down_sync(0xffffffffu, v, off);
+	}
+
+	return v;
+}

@@ -1,0 +1,108 @@
+/*
+ * internal.h - declarations shared by the host-side C sources of libbfm (B200 build).
+ * Nothing here is exported; the public surface is include/bfm/libbfm.h + include/bfm_b200.h.
+ */
+#ifndef BFM_INTERNAL_H
+#define BFM_INTERNAL_H
+
+#include <stdarg.h>
+#include <stdint.h>
+
+#include <bfm/libbfm.h>
+#include <bfm_b200.h>
+
+#include "gpu.h"
+
+#define BFMI_HIDDEN __attribute__((visibility("hidden")))
+
+/* fill state->err, print it on stderr (unless BFM_QUIET is set) and return -1 */
+BFMI_HIDDEN int bfmi_fail(bfm_state_t* state, char const* file, char const* func, size_t line, char const* fmt, ...);
+#define BFMI_FAIL(state, ...) bfmi_fail((state), __FILE__, __func__, __LINE__, __VA_ARGS__)
+
+/* ---------------------------------------------------------------------------------------------
+ * symbolic plan: everything that depends only on the mesh connectivity (built once per mesh)
+ *
+ * The global matrix is stored by NODE blocks (2x2 doubles per pair of coupled nodes) in a
+ * sliced-ELL layout of 32-row slices ("SELL-32"): slice s holds block rows 32s..32s+31, padded to
+ * the longest of them; slot (row a, position t) lives at  slice_off[a / 32] + 32 t + a % 32.  Both
+ * the assembly and the SpMV kernels walk a slice with one warp, lane = row, so every access to the
+ * value/column arrays is a contiguous 32-wide segment.
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct bfmi_plan {
+	int refs;
+
+	/* cache key (plans built from a mesh only) */
+	bfm_mesh_t const* mesh;
+	size_t n_nodes, n_elems;
+	int kind;
+	uint64_t elems_hash;
+
+	/* host copies */
+	int32_t nb;         /* block rows = nodes */
+	int32_t n_slices;   /* ceil(nb / 32) */
+	int64_t n_slots;    /* padded block count (multiple of 32) */
+	int64_t n_blocks;   /* real blocks */
+	int64_t n_ctr;      /* element contributions over all blocks */
+
+	int32_t* slice_off; /* [n_slices + 1] first slot of each slice */
+	int32_t* row_len;   /* [nb] real blocks per row */
+	int32_t* scol;      /* [n_slots] block column; padding slots point at their own row */
+	int32_t* diag_pos;  /* [nb] slot of the diagonal block */
+	int32_t* ctr_ptr;   /* [n_slots + 1] contributor list bounds (NULL without a mesh) */
+	uint32_t* ctr;      /* [n_ctr] element << 4 | local row node << 2 | local column node */
+	int32_t* elems32;   /* [n_elems * kind] connectivity narrowed to 32 bits */
+
+	bfmg_pattern_t dev; /* device mirror, filled by bfmi_plan_upload */
+	bool on_device;
+} bfmi_plan_t;
+
+BFMI_HIDDEN bfmi_plan_t* bfmi_plan_for_mesh(bfm_state_t* state, bfm_mesh_t const* mesh); /* cached, retained */
+BFMI_HIDDEN bfmi_plan_t* bfmi_plan_from_csr(bfm_state_t* state, size_t n, size_t const* rowptr, size_t const* col);
+BFMI_HIDDEN void bfmi_plan_retain(bfmi_plan_t* plan);
+BFMI_HIDDEN void bfmi_plan_release(bfmi_plan_t* plan);
+BFMI_HIDDEN void bfmi_plan_forget(bfm_mesh_t const* mesh); /* mesh is going away */
+BFMI_HIDDEN int bfmi_plan_upload(bfm_state_t* state, bfmi_plan_t* plan);
+
+/* slot of block (a, b), or -1 */
+BFMI_HIDDEN int64_t bfmi_plan_find(bfmi_plan_t const* plan, int32_t a, int32_t b);
+
+/* ---------------------------------------------------------------------------------------------
+ * BFM_MATRIX_KIND_CSR implementation object (matrix->csr.impl)
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct bfmi_csr {
+	bfm_state_t* state;
+	bfmi_plan_t* plan;
+
+	double* d_val;      /* device, 4 * n_slots doubles: plane of (a00,a01) pairs, then plane of (a10,a11) */
+	bool d_valid;       /* device copy is current */
+	double* h_val;      /* host mirror, same layout (lazy) */
+	bool h_valid;
+
+	size_t* perm;       /* logical renumbering applied by bfm_perm_perm_matrix, or NULL */
+	size_t* inv_perm;
+
+	bfmx_stats_t stats; /* of the last solve */
+} bfmi_csr_t;
+
+BFMI_HIDDEN int bfmi_csr_wrap(bfm_matrix_t* matrix, bfm_state_t* state, bfmi_plan_t* plan, double* d_val);
+BFMI_HIDDEN int bfmi_csr_destroy(bfm_matrix_t* matrix);
+BFMI_HIDDEN int bfmi_csr_mirror(bfmi_csr_t* csr); /* make h_val valid */
+BFMI_HIDDEN double bfmi_csr_get(bfm_matrix_t* matrix, size_t i, size_t j);
+BFMI_HIDDEN int bfmi_csr_put(bfm_matrix_t* matrix, size_t i, size_t j, double val, bool add);
+BFMI_HIDDEN size_t bfmi_csr_bandwidth(bfm_matrix_t* matrix);
+BFMI_HIDDEN int bfmi_csr_solve(bfm_matrix_t* matrix, bfm_vec_t* y);
+BFMI_HIDDEN int bfmi_csr_copy(bfm_matrix_t* dst, bfm_matrix_t* src);
+BFMI_HIDDEN int bfmi_csr_rcm(bfm_perm_t* perm, bfm_matrix_t* matrix);
+BFMI_HIDDEN int bfmi_csr_set_perm(bfm_matrix_t* matrix, size_t const* perm, size_t n);
+
+/* RCM driver shared by the dense and the sparse front ends (perm.c): row_nnz(i, out, ctx) writes
+ * the ascending column indices of the numerically non-zero entries of row i and returns their count */
+typedef size_t (*bfmi_row_fn_t)(size_t i, size_t* out, void* ctx);
+BFMI_HIDDEN int bfmi_rcm(bfm_perm_t* perm, size_t n, size_t max_row, bfmi_row_fn_t row_nnz, void* ctx);
+
+/* solver options resolved from the environment (BFM_CG_TOL, BFM_CG_MAXIT, ...) */
+BFMI_HIDDEN void bfmi_pcg_options(size_t n, bfmg_pcg_opts_t* opts);
+
+#endif

@@ -1,0 +1,1011 @@
+/*
+ * job.c - the hot path's driver: what the reference's run_elasticity (sim.c:103-135) and
+ * create_planar / bfm_system_create_axisymmetric_strain (system.c:427-529, :539-622) do for one
+ * instance, re-staged for the GPU:
+ *
+ *   create    host: plan (cached per mesh), shape tables, material constants, BC work lists
+ *   upload    H2D:  coordinates, per-node force tables (FUNKY forces only), BC lists
+ *   assemble  GPU:  k_assemble, then one k_bc_dirichlet / k_bc_add per boundary condition, in
+ *                   instance condition order (system.c:470-526)
+ *   solve     GPU:  FP64 PCG
+ *   download  D2H:  displacements -> instance->effects (sim.c:127-131)
+ *
+ * bfm_sim_run chains the five; bfm_system_create_planar_* stop after `assemble` and hand the matrix
+ * back as a CSR-kind bfm_matrix_t.
+ */
+#include "internal.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ---- BC work lists ----------------------------------------------------------------------------- */
+
+typedef enum {
+	OP_DIRICHLET, /* apply_constraint on an ascending DOF list */
+	OP_ADD,       /* ordered additions to the right-hand side */
+} op_kind_t;
+
+typedef struct {
+	op_kind_t kind;
+
+	/* OP_DIRICHLET: constrained DOFs + values, block rows to revisit */
+	int32_t n_dofs;
+	int32_t* dofs;
+	double* vals;
+	int32_t n_rows;
+	int32_t* rows;
+
+	/* OP_ADD: groups of additions per DOF, in application order inside a group */
+	int32_t n_groups;
+	int32_t* group_dof;
+	int32_t* group_ptr;
+	double* add;
+
+	/* device mirrors */
+	int32_t *d_dofs, *d_rows, *d_group_dof, *d_group_ptr;
+	double *d_vals, *d_add;
+} bc_op_t;
+
+struct bfmx_job {
+	bfm_state_t* state;
+	bfm_sim_kind_t kind;
+	bfm_instance_t* instance;
+	bfm_mesh_t* mesh;
+
+	bfmi_plan_t* plan;
+	bfmg_asm_tables_t tab;
+
+	double* h_nforce; /* [n_forces][nb][2], FUNKY forces sampled at the nodes */
+
+	size_t n_ops;
+	bc_op_t* ops;
+
+	double* d_coords;
+	double* d_nforce;
+	double* d_val;
+	double* d_b;
+	double* d_x;
+	int32_t* d_stamp;
+	double* d_cval;
+
+	bool uploaded, assembled, solved;
+	bfmx_stats_t stats;
+};
+
+static bfmx_stats_t last_stats;
+
+void bfmx_publish_stats(bfmx_stats_t const* stats) {
+	last_stats = *stats;
+}
+
+int bfmx_last_stats(bfmx_stats_t* out) {
+	*out = last_stats;
+	return 0;
+}
+
+int bfmx_device_available(void) {
+	return bfmg_available();
+}
+
+char const* bfmx_device_error(void) {
+	return bfmg_last_error();
+}
+
+static double now_ms(void) {
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+/* ---- shape tables, material constants, forces --------------------------------------------------- */
+
+static int fill_tables(bfmx_job_t* job, size_t n_forces, bfm_force_t** forces) {
+	bfm_state_t* const state = job->state;
+	bfm_obj_t* const obj = job->instance->obj;
+	bfm_material_t const* const material = obj->material;
+	bfm_rule_t* const rule = obj->rule;
+	bfm_shape_t* const shape = &rule->shape;
+	bfmg_asm_tables_t* const T = &job->tab;
+	size_t const kind = job->mesh->kind;
+
+	memset(T, 0, sizeof *T);
+
+	if (rule->n_points > BFMG_MAX_POINTS) {
+		return BFMI_FAIL(state, "integration rules with more than %d points are not supported on the GPU path", BFMG_MAX_POINTS);
+	}
+
+	if (n_forces > BFMG_MAX_FORCES) {
+		return BFMI_FAIL(state, "more than %d body forces are not supported on the GPU path", BFMG_MAX_FORCES);
+	}
+
+	T->kind = (int32_t) kind;
+	T->n_points = (int32_t) rule->n_points;
+	T->axisym = job->kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN;
+	T->rho = material->rho;
+
+	/* the rule's own shape functions, evaluated on the host exactly as the reference does per element
+	 * and integration point (system.c:151-158); the kernel only reads the table */
+
+	T->grad_const = 1;
+
+	for (size_t g = 0; g < rule->n_points; g++) {
+		double phi[6] = {0}, dxsi[6] = {0}, deta[6] = {0};
+
+		shape->phi(shape, rule->points[g], phi);
+		shape->dphi(shape, 0, rule->points[g], dxsi);
+		shape->dphi(shape, 1, rule->points[g], deta);
+
+		T->weight[g] = rule->weights[g];
+
+		for (size_t j = 0; j < kind; j++) {
+			T->phi[g][j] = phi[j];
+			T->dxsi[g][j] = dxsi[j];
+			T->deta[g][j] = deta[j];
+
+			if (memcmp(&T->dxsi[g][j], &T->dxsi[0][j], sizeof(double)) != 0 || memcmp(&T->deta[g][j], &T->deta[0][j], sizeof(double)) != 0) {
+				T->grad_const = 0;
+			}
+		}
+	}
+
+	/* elasticity constants, association as written in the reference */
+
+	double const E = material->E;
+	double const nu = material->nu;
+
+	if (job->kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN) { /* system.c:242-244 (note '* (1 - 2 nu)') */
+		T->a = E * (1 - nu) / (1 + nu) * (1 - 2 * nu);
+		T->b = E * nu / (1 + nu) / (1 - 2 * nu);
+	}
+
+	else if (job->kind == BFM_SIM_KIND_PLANAR_STRAIN) { /* system.c:454-456 */
+		T->a = E * (1 - nu) / (1 + nu) / (1 - 2 * nu);
+		T->b = E * nu / (1 + nu) / (1 - 2 * nu);
+	}
+
+	else {
+		T->a = E / (1 - nu * nu);
+		T->b = E * nu / (1 - nu * nu);
+	}
+
+	T->c = E / (2 * (1 + nu));
+
+	/* forces: constants when none is FUNKY, otherwise every force becomes a per-node table */
+
+	T->n_forces = (int32_t) n_forces;
+
+	for (size_t k = 0; k < n_forces; k++) {
+		if (forces[k]->dim != 2) {
+			return BFMI_FAIL(state, "force %zu has dimension %zu, the mesh has 2 (the reference would use stale values here)", k, forces[k]->dim);
+		}
+
+		if (forces[k]->kind == BFM_FORCE_KIND_FUNKY) {
+			T->forces_per_node = 1;
+		}
+	}
+
+	if (!T->forces_per_node) {
+		for (size_t k = 0; k < n_forces; k++) {
+			if (forces[k]->kind == BFM_FORCE_KIND_LINEAR) {
+				T->const_force[k][0] = forces[k]->linear.force.data[0];
+				T->const_force[k][1] = forces[k]->linear.force.data[1];
+			}
+		}
+
+		return 0;
+	}
+
+	size_t const nb = job->mesh->n_nodes;
+
+	job->h_nforce = malloc(n_forces * nb * 2 * sizeof *job->h_nforce + 8);
+
+	if (job->h_nforce == NULL) {
+		return -1;
+	}
+
+	bfm_vec_t pos, out;
+
+	if (bfm_vec_create(&pos, state, 2) < 0 || bfm_vec_create(&out, state, 2) < 0) {
+		return -1;
+	}
+
+	for (size_t k = 0; k < n_forces; k++) {
+		for (size_t a = 0; a < nb; a++) {
+			pos.data[0] = job->mesh->coords[2 * a + 0];
+			pos.data[1] = job->mesh->coords[2 * a + 1];
+
+			bfm_force_eval(forces[k], &pos, &out); /* status ignored, as in system.c:198 */
+
+			job->h_nforce[(k * nb + a) * 2 + 0] = out.data[0];
+			job->h_nforce[(k * nb + a) * 2 + 1] = out.data[1];
+		}
+	}
+
+	bfm_vec_destroy(&pos);
+	bfm_vec_destroy(&out);
+
+	return 0;
+}
+
+/* ---- boundary conditions -> ordered work lists ---------------------------------------------------- */
+
+static int cmp_i32(void const* a, void const* b) {
+	int32_t const x = *(int32_t const*) a;
+	int32_t const y = *(int32_t const*) b;
+	return x < y ? -1 : x > y;
+}
+
+/* block rows holding a column of one of the constrained nodes = their graph neighbours */
+static int affected_rows(bfmi_plan_t const* plan, bc_op_t* op) {
+	size_t cap = 0;
+
+	for (int32_t i = 0; i < op->n_dofs; i++) {
+		if (i == 0 || op->dofs[i] / 2 != op->dofs[i - 1] / 2) {
+			cap += (size_t) plan->row_len[op->dofs[i] / 2];
+		}
+	}
+
+	op->rows = malloc((cap + 1) * sizeof *op->rows);
+
+	if (op->rows == NULL) {
+		return -1;
+	}
+
+	size_t cnt = 0;
+
+	for (int32_t i = 0; i < op->n_dofs; i++) {
+		int32_t const a = op->dofs[i] / 2;
+
+		if (i != 0 && a == op->dofs[i - 1] / 2) {
+			continue;
+		}
+
+		for (int32_t t = 0; t < plan->row_len[a]; t++) {
+			op->rows[cnt++] = plan->scol[(int64_t) plan->slice_off[a / 32] + (int64_t) t * 32 + a % 32];
+		}
+	}
+
+	qsort(op->rows, cnt, sizeof *op->rows, cmp_i32);
+
+	size_t uniq = 0;
+
+	for (size_t i = 0; i < cnt; i++) {
+		if (i == 0 || op->rows[i] != op->rows[i - 1]) {
+			op->rows[uniq++] = op->rows[i];
+		}
+	}
+
+	op->n_rows = (int32_t) uniq;
+	return 0;
+}
+
+/* apply_dirichlet (system.c:376-386) */
+static int op_dirichlet_xy(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t* op) {
+	size_t const nn = job->mesh->n_nodes;
+	int32_t const shift = cond->kind == BFM_CONDITION_KIND_DIRICHLET_X ? 0 : 1;
+	size_t count = 0;
+
+	for (size_t j = 0; j < nn; j++) {
+		count += cond->nodes[j];
+	}
+
+	op->kind = OP_DIRICHLET;
+	op->dofs = malloc((count + 1) * sizeof *op->dofs);
+	op->vals = malloc((count + 1) * sizeof *op->vals);
+
+	if (op->dofs == NULL || op->vals == NULL) {
+		return -1;
+	}
+
+	for (size_t j = 0; j < nn; j++) {
+		if (cond->nodes[j]) {
+			op->dofs[op->n_dofs] = (int32_t) (2 * j) + shift;
+			op->vals[op->n_dofs++] = cond->value;
+		}
+	}
+
+	return affected_rows(job->plan, op);
+}
+
+/* apply_dirichlet_normal_tangent (system.c:388-425): tangent = sum over the node's boundary edges, in
+ * edge order, of (x_i - x_other) / length / 2; pow(d, 2) is d * d, as gcc -O2 compiles it */
+static int op_dirichlet_nt(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t* op) {
+	bfm_mesh_t const* const mesh = job->mesh;
+	size_t const nn = mesh->n_nodes;
+	bool const tangent = cond->kind == BFM_CONDITION_KIND_DIRICHLET_TANGENT;
+
+	double* const tx = calloc(nn + 1, sizeof *tx);
+	double* const ty = calloc(nn + 1, sizeof *ty);
+	size_t count = 0;
+
+	for (size_t j = 0; j < nn; j++) {
+		count += cond->nodes[j];
+	}
+
+	op->kind = OP_DIRICHLET;
+	op->dofs = malloc((2 * count + 1) * sizeof *op->dofs);
+	op->vals = malloc((2 * count + 1) * sizeof *op->vals);
+
+	if (tx == NULL || ty == NULL || op->dofs == NULL || op->vals == NULL) {
+		free(tx);
+		free(ty);
+		return -1;
+	}
+
+	/* one pass over the edges in ascending order feeds every node's sum in the reference's order */
+
+	for (size_t j = 0; j < mesh->n_edges; j++) {
+		bfm_edge_t const* const edge = &mesh->edges[j];
+
+		if (edge->elems[1] != -1) {
+			continue;
+		}
+
+		for (int side = 0; side < 2; side++) {
+			size_t const i = edge->nodes[side];
+			size_t const other = edge->nodes[1 - side];
+
+			if (side == 1 && edge->nodes[0] == edge->nodes[1]) {
+				break; /* degenerate edge: the reference's else-if takes the first branch only */
+			}
+
+			if (i >= nn || other >= nn || !cond->nodes[i]) {
+				continue;
+			}
+
+			double const dx = mesh->coords[i * 2 + 0] - mesh->coords[other * 2 + 0];
+			double const dy = mesh->coords[i * 2 + 1] - mesh->coords[other * 2 + 1];
+			double const length = sqrt(dx * dx + dy * dy);
+
+			tx[i] += dx / length / 2;
+			ty[i] += dy / length / 2;
+		}
+	}
+
+	for (size_t i = 0; i < nn; i++) {
+		if (!cond->nodes[i]) {
+			continue;
+		}
+
+		op->dofs[op->n_dofs] = (int32_t) (2 * i);
+		op->vals[op->n_dofs++] = cond->value * (tangent ? tx[i] : -ty[i]);
+
+		op->dofs[op->n_dofs] = (int32_t) (2 * i + 1);
+		op->vals[op->n_dofs++] = cond->value * (tangent ? ty[i] : tx[i]);
+	}
+
+	free(tx);
+	free(ty);
+
+	return affected_rows(job->plan, op);
+}
+
+typedef struct {
+	int32_t dof;
+	int32_t seq;
+	double val;
+} pending_add_t;
+
+static int cmp_pending(void const* a, void const* b) {
+	pending_add_t const* const x = a;
+	pending_add_t const* const y = b;
+
+	if (x->dof != y->dof) {
+		return x->dof < y->dof ? -1 : 1;
+	}
+
+	return x->seq < y->seq ? -1 : x->seq > y->seq;
+}
+
+/* Neumann loads (system.c:477-522; axisymmetric weighting :586-617): every mesh edge with both end
+ * nodes in the mask adds to the right-hand side, in edge order */
+static int op_neumann(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t* op) {
+	bfm_mesh_t const* const mesh = job->mesh;
+	bool const axisym = job->kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN;
+	bool const xy = cond->kind == BFM_CONDITION_KIND_NEUMANN_X || cond->kind == BFM_CONDITION_KIND_NEUMANN_Y;
+
+	op->kind = OP_ADD;
+
+	if (!xy && axisym) {
+		return 0; /* the axisymmetric BC loop has no normal/tangent Neumann branch */
+	}
+
+	pending_add_t* const pend = malloc((4 * mesh->n_edges + 1) * sizeof *pend);
+
+	if (pend == NULL) {
+		return -1;
+	}
+
+	int32_t n = 0;
+
+	for (size_t j = 0; j < mesh->n_edges; j++) {
+		size_t const n1 = mesh->edges[j].nodes[0];
+		size_t const n2 = mesh->edges[j].nodes[1];
+
+		if (n1 >= mesh->n_nodes || n2 >= mesh->n_nodes || !cond->nodes[n1] || !cond->nodes[n2]) {
+			continue;
+		}
+
+		double const dx = mesh->coords[n1 * 2 + 0] - mesh->coords[n2 * 2 + 0];
+		double const dy = mesh->coords[n1 * 2 + 1] - mesh->coords[n2 * 2 + 1];
+
+		if (xy) {
+			int32_t const shift = cond->kind == BFM_CONDITION_KIND_NEUMANN_X ? 0 : 1;
+			double const jacobian = sqrt(dx * dx + dy * dy) / 2;
+			double load = jacobian * cond->value;
+
+			if (axisym) {
+				double const r1 = mesh->coords[n1 * 2 + 0] * (1 - 1 / sqrt(3)) / 2 + mesh->coords[n1 * 2 + 1] * (1 + 1 / sqrt(3)) / 2;
+				double const r2 = mesh->coords[n2 * 2 + 0] * (1 - 1 / sqrt(3)) / 2 + mesh->coords[n2 * 2 + 1] * (1 + 1 / sqrt(3)) / 2;
+				double const fac = r1 + r2;
+
+				load = fac * jacobian * cond->value;
+			}
+
+			pend[n] = (pending_add_t) {(int32_t) (n1 * 2) + shift, n, load}, n++;
+			pend[n] = (pending_add_t) {(int32_t) (n2 * 2) + shift, n, load}, n++;
+		}
+
+		else {
+			bool const tangent = cond->kind == BFM_CONDITION_KIND_NEUMANN_TANGENT;
+			double const lx = 0.5 * cond->value * (tangent ? dx : -dy);
+			double const ly = 0.5 * cond->value * (tangent ? dy : dx);
+
+			pend[n] = (pending_add_t) {(int32_t) (n1 * 2 + 0), n, lx}, n++;
+			pend[n] = (pending_add_t) {(int32_t) (n1 * 2 + 1), n, ly}, n++;
+			pend[n] = (pending_add_t) {(int32_t) (n2 * 2 + 0), n, lx}, n++;
+			pend[n] = (pending_add_t) {(int32_t) (n2 * 2 + 1), n, ly}, n++;
+		}
+	}
+
+	qsort(pend, (size_t) n, sizeof *pend, cmp_pending);
+
+	op->group_dof = malloc(((size_t) n + 1) * sizeof *op->group_dof);
+	op->group_ptr = malloc(((size_t) n + 2) * sizeof *op->group_ptr);
+	op->add = malloc(((size_t) n + 1) * sizeof *op->add);
+
+	if (op->group_dof == NULL || op->group_ptr == NULL || op->add == NULL) {
+		free(pend);
+		return -1;
+	}
+
+	for (int32_t i = 0; i < n; i++) {
+		if (i == 0 || pend[i].dof != pend[i - 1].dof) {
+			op->group_dof[op->n_groups] = pend[i].dof;
+			op->group_ptr[op->n_groups++] = i;
+		}
+
+		op->add[i] = pend[i].val;
+	}
+
+	op->group_ptr[op->n_groups] = n;
+
+	free(pend);
+	return 0;
+}
+
+static int build_ops(bfmx_job_t* job) {
+	bfm_instance_t const* const instance = job->instance;
+	bool const axisym = job->kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN;
+
+	job->ops = calloc(instance->n_conditions + 1, sizeof *job->ops);
+
+	if (job->ops == NULL) {
+		return -1;
+	}
+
+	for (size_t i = 0; i < instance->n_conditions; i++) {
+		bfm_condition_t const* const cond = instance->conditions[i];
+		bc_op_t* const op = &job->ops[job->n_ops];
+		int rv = 0;
+
+		switch (cond->kind) {
+		case BFM_CONDITION_KIND_DIRICHLET_X:
+		case BFM_CONDITION_KIND_DIRICHLET_Y:
+			rv = op_dirichlet_xy(job, cond, op);
+			break;
+
+		case BFM_CONDITION_KIND_DIRICHLET_NORMAL:
+		case BFM_CONDITION_KIND_DIRICHLET_TANGENT:
+			rv = op_dirichlet_nt(job, cond, op);
+			break;
+
+		case BFM_CONDITION_KIND_NEUMANN_X:
+		case BFM_CONDITION_KIND_NEUMANN_Y:
+			rv = op_neumann(job, cond, op);
+			break;
+
+		case BFM_CONDITION_KIND_NEUMANN_NORMAL:
+		case BFM_CONDITION_KIND_NEUMANN_TANGENT:
+			if (axisym) {
+				continue;
+			}
+
+			rv = op_neumann(job, cond, op);
+			break;
+
+		default:
+			continue; /* unknown kinds fall through every branch of the reference's BC loop */
+		}
+
+		if (rv < 0) {
+			return -1;
+		}
+
+		job->n_ops++;
+	}
+
+	return 0;
+}
+
+/* ---- job life cycle -------------------------------------------------------------------------------- */
+
+static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind, bfm_instance_t* instance, size_t n_forces, bfm_force_t** forces) {
+	bfm_mesh_t* const mesh = instance->obj->mesh;
+
+	*out = NULL;
+
+	if (mesh->dim != 2 || (mesh->kind != BFM_ELEM_KIND_SIMPLEX && mesh->kind != BFM_ELEM_KIND_QUAD)) {
+		return -1; /* system.c:436-442, :547-553 */
+	}
+
+	if (kind != BFM_SIM_KIND_PLANAR_STRAIN && kind != BFM_SIM_KIND_PLANAR_STRESS && kind != BFM_SIM_KIND_AXISYMMETRIC_STRAIN) {
+		return -1;
+	}
+
+	if (!bfmg_available()) {
+		return BFMI_FAIL(state, "%s", bfmg_last_error());
+	}
+
+	bfmx_job_t* const job = calloc(1, sizeof *job);
+
+	if (job == NULL) {
+		return -1;
+	}
+
+	job->state = state;
+	job->kind = kind;
+	job->instance = instance;
+	job->mesh = mesh;
+
+	double const t0 = now_ms();
+
+	job->plan = bfmi_plan_for_mesh(state, mesh);
+
+	if (job->plan == NULL) {
+		goto fail;
+	}
+
+	bool const fresh = !job->plan->on_device;
+
+	if (bfmi_plan_upload(state, job->plan) < 0) {
+		goto fail;
+	}
+
+	if (fresh) {
+		job->stats.ms_plan = (float) (now_ms() - t0);
+
+		job->stats.h2d_bytes += ((size_t) job->plan->n_slices + 1 + 2 * (size_t) job->plan->nb + 2 * (size_t) job->plan->n_slots + 1 + (size_t) job->plan->n_ctr + job->plan->n_elems * (size_t) job->plan->kind) * 4;
+	}
+
+	if (fill_tables(job, n_forces, forces) < 0 || build_ops(job) < 0) {
+		goto fail;
+	}
+
+	size_t const nb = (size_t) job->plan->nb;
+
+	if (
+		bfmg_alloc((void**) &job->d_coords, nb * 2 * sizeof(double)) < 0 ||
+		bfmg_alloc((void**) &job->d_val, (size_t) job->plan->n_slots * 4 * sizeof(double)) < 0 ||
+		bfmg_alloc((void**) &job->d_b, nb * 2 * sizeof(double)) < 0 ||
+		bfmg_alloc((void**) &job->d_x, nb * 2 * sizeof(double)) < 0 ||
+		(job->h_nforce != NULL && bfmg_alloc((void**) &job->d_nforce, n_forces * nb * 2 * sizeof(double)) < 0)
+	) {
+		BFMI_FAIL(state, "device allocation failed: %s", bfmg_last_error());
+		goto fail;
+	}
+
+	bool any_dirichlet = false;
+
+	for (size_t i = 0; i < job->n_ops; i++) {
+		bc_op_t* const op = &job->ops[i];
+		int rv = 0;
+
+		if (op->kind == OP_DIRICHLET) {
+			any_dirichlet = true;
+
+			rv |= bfmg_alloc((void**) &op->d_dofs, ((size_t) op->n_dofs + 1) * sizeof(int32_t));
+			rv |= bfmg_alloc((void**) &op->d_vals, ((size_t) op->n_dofs + 1) * sizeof(double));
+			rv |= bfmg_alloc((void**) &op->d_rows, ((size_t) op->n_rows + 1) * sizeof(int32_t));
+		}
+
+		else if (op->n_groups > 0) {
+			rv |= bfmg_alloc((void**) &op->d_group_dof, ((size_t) op->n_groups + 1) * sizeof(int32_t));
+			rv |= bfmg_alloc((void**) &op->d_group_ptr, ((size_t) op->n_groups + 2) * sizeof(int32_t));
+			rv |= bfmg_alloc((void**) &op->d_add, ((size_t) op->group_ptr[op->n_groups] + 1) * sizeof(double));
+		}
+
+		if (rv < 0) {
+			BFMI_FAIL(state, "device allocation failed: %s", bfmg_last_error());
+			goto fail;
+		}
+	}
+
+	if (any_dirichlet && (bfmg_alloc((void**) &job->d_stamp, nb * 2 * sizeof(int32_t)) < 0 || bfmg_alloc((void**) &job->d_cval, nb * 2 * sizeof(double)) < 0)) {
+		BFMI_FAIL(state, "device allocation failed: %s", bfmg_last_error());
+		goto fail;
+	}
+
+	job->stats.n_dofs = 2 * nb;
+	job->stats.n_blocks = (size_t) job->plan->n_blocks;
+	job->stats.n_slots = (size_t) job->plan->n_slots;
+
+	*out = job;
+	return 0;
+
+fail:
+
+	bfmx_job_destroy(job);
+	return -1;
+}
+
+int bfmx_job_create(bfmx_job_t** job, bfm_sim_t* sim, size_t instance_index) {
+	if (instance_index >= sim->n_instances) {
+		return -1;
+	}
+
+	return job_create(job, sim->state, sim->kind, sim->instances[instance_index], sim->n_forces, sim->forces);
+}
+
+int bfmx_job_destroy(bfmx_job_t* job) {
+	if (job == NULL) {
+		return 0;
+	}
+
+	for (size_t i = 0; i < job->n_ops; i++) {
+		bc_op_t* const op = &job->ops[i];
+
+		free(op->dofs), free(op->vals), free(op->rows);
+		free(op->group_dof), free(op->group_ptr), free(op->add);
+
+		bfmg_free(op->d_dofs), bfmg_free(op->d_vals), bfmg_free(op->d_rows);
+		bfmg_free(op->d_group_dof), bfmg_free(op->d_group_ptr), bfmg_free(op->d_add);
+	}
+
+	free(job->ops);
+	free(job->h_nforce);
+
+	bfmg_free(job->d_coords);
+	bfmg_free(job->d_nforce);
+	bfmg_free(job->d_val);
+	bfmg_free(job->d_b);
+	bfmg_free(job->d_x);
+	bfmg_free(job->d_stamp);
+	bfmg_free(job->d_cval);
+
+	bfmi_plan_release(job->plan);
+	free(job);
+
+	return 0;
+}
+
+#define UP(dst, src, count, type) (bytes += (size_t) (count) * sizeof(type), bfmg_upload((dst), (src), (size_t) (count) * sizeof(type)))
+
+int bfmx_job_upload(bfmx_job_t* job) {
+	size_t const nb = (size_t) job->plan->nb;
+	size_t bytes = 0;
+	int const t0 = bfmg_tick();
+	int rv = 0;
+
+	rv |= UP(job->d_coords, job->mesh->coords, nb * 2, double);
+
+	if (job->h_nforce != NULL) {
+		rv |= UP(job->d_nforce, job->h_nforce, (size_t) job->tab.n_forces * nb * 2, double);
+	}
+
+	for (size_t i = 0; i < job->n_ops; i++) {
+		bc_op_t* const op = &job->ops[i];
+
+		if (op->kind == OP_DIRICHLET) {
+			rv |= UP(op->d_dofs, op->dofs, op->n_dofs, int32_t);
+			rv |= UP(op->d_vals, op->vals, op->n_dofs, double);
+			rv |= UP(op->d_rows, op->rows, op->n_rows, int32_t);
+		}
+
+		else if (op->n_groups > 0) {
+			rv |= UP(op->d_group_dof, op->group_dof, op->n_groups, int32_t);
+			rv |= UP(op->d_group_ptr, op->group_ptr, op->n_groups + 1, int32_t);
+			rv |= UP(op->d_add, op->add, op->group_ptr[op->n_groups], double);
+		}
+	}
+
+	if (job->d_stamp != NULL) {
+		rv |= bfmg_zero(job->d_stamp, nb * 2 * sizeof(int32_t));
+	}
+
+	int const t1 = bfmg_tick();
+
+	if (rv < 0 || bfmg_sync() < 0) {
+		return BFMI_FAIL(job->state, "upload failed: %s", bfmg_last_error());
+	}
+
+	job->stats.ms_upload = bfmg_lap(t0, t1);
+	job->stats.h2d_bytes += bytes;
+	job->uploaded = true;
+
+	return 0;
+}
+
+int bfmx_job_assemble(bfmx_job_t* job) {
+	if (!job->uploaded) {
+		return -1;
+	}
+
+	size_t const before = bfmg_launch_count();
+	int const t0 = bfmg_tick();
+
+	if (bfmg_assemble(&job->plan->dev, &job->tab, job->d_coords, job->d_nforce, job->d_val, job->d_b) < 0) {
+		return BFMI_FAIL(job->state, "assembly failed: %s", bfmg_last_error());
+	}
+
+	int const t1 = bfmg_tick();
+
+	for (size_t i = 0; i < job->n_ops; i++) {
+		bc_op_t const* const op = &job->ops[i];
+		int rv;
+
+		if (op->kind == OP_DIRICHLET) {
+			rv = bfmg_bc_dirichlet(&job->plan->dev, job->d_val, job->d_b, job->d_stamp, job->d_cval, (int32_t) i + 1, op->d_dofs, op->d_vals, op->n_dofs, op->d_rows, op->n_rows);
+		}
+
+		else {
+			rv = bfmg_bc_add(job->d_b, op->d_group_dof, op->d_group_ptr, op->d_add, op->n_groups);
+		}
+
+		if (rv < 0) {
+			return BFMI_FAIL(job->state, "boundary conditions failed: %s", bfmg_last_error());
+		}
+	}
+
+	int const t2 = bfmg_tick();
+
+	if (bfmg_sync() < 0) {
+		return BFMI_FAIL(job->state, "assembly failed: %s", bfmg_last_error());
+	}
+
+	job->stats.ms_assemble = bfmg_lap(t0, t1);
+	job->stats.ms_bc = bfmg_lap(t1, t2);
+	job->stats.kernel_launches += bfmg_launch_count() - before;
+	job->assembled = true;
+
+	return 0;
+}
+
+int bfmx_job_solve(bfmx_job_t* job) {
+	if (!job->assembled) {
+		return -1;
+	}
+
+	bfmg_pcg_opts_t opts;
+	bfmg_pcg_result_t res;
+
+	bfmi_pcg_options(job->stats.n_dofs, &opts);
+
+	if (bfmg_pcg(&job->plan->dev, job->d_val, job->d_b, job->d_x, &opts, &res) < 0) {
+		return BFMI_FAIL(job->state, "PCG failed: %s", bfmg_last_error());
+	}
+
+	job->stats.cg_iterations = res.iterations;
+	job->stats.cg_restarts = res.restarts;
+	job->stats.cg_converged = res.converged;
+	job->stats.cg_rel_residual = res.rel_residual;
+	job->stats.cg_true_rel_residual = res.true_rel_residual;
+	job->stats.ms_solve = res.ms;
+	job->stats.kernel_launches += res.launches;
+	job->solved = true;
+
+	if (res.converged != 1) {
+		return BFMI_FAIL(job->state, "PCG stopped after %d iterations without converging (relative residual %.3e, true %.3e)", res.iterations, res.rel_residual, res.true_rel_residual);
+	}
+
+	return 0;
+}
+
+int bfmx_job_download(bfmx_job_t* job) {
+	if (!job->solved) {
+		return -1;
+	}
+
+	size_t const bytes = job->stats.n_dofs * sizeof(double);
+	int const t0 = bfmg_tick();
+
+	/* effects[node * dim + k] = x[node * dim + k] (sim.c:127-131): same interleaving, one copy */
+
+	if (bfmg_download(job->instance->effects, job->d_x, bytes) < 0) {
+		return BFMI_FAIL(job->state, "download failed: %s", bfmg_last_error());
+	}
+
+	int const t1 = bfmg_tick();
+
+	job->stats.ms_download = bfmg_lap(t0, t1);
+	job->stats.d2h_bytes += bytes;
+
+	return 0;
+}
+
+int bfmx_job_stats(bfmx_job_t* job, bfmx_stats_t* out) {
+	*out = job->stats;
+	return 0;
+}
+
+int bfmx_job_spmv_time(bfmx_job_t* job, int reps, float* ms_per_launch) {
+	if (!job->assembled) {
+		return -1;
+	}
+
+	return bfmg_spmv_time(&job->plan->dev, job->d_val, reps, ms_per_launch);
+}
+
+int bfmx_job_read(bfmx_job_t* job, double* b, double* x) {
+	size_t const bytes = job->stats.n_dofs * sizeof(double);
+
+	if (b != NULL && (!job->assembled || bfmg_download(b, job->d_b, bytes) < 0)) {
+		return -1;
+	}
+
+	if (x != NULL && (!job->solved || bfmg_download(x, job->d_x, bytes) < 0)) {
+		return -1;
+	}
+
+	return 0;
+}
+
+/* ---- bfm_sim_run (reference sim.c:137-155) ---------------------------------------------------------- */
+
+int bfm_sim_run(bfm_sim_t* sim) {
+	if (sim->kind == BFM_SIM_KIND_NONE) {
+		return 0;
+	}
+
+	if (sim->kind != BFM_SIM_KIND_PLANAR_STRAIN && sim->kind != BFM_SIM_KIND_PLANAR_STRESS && sim->kind != BFM_SIM_KIND_AXISYMMETRIC_STRAIN) {
+		return -1;
+	}
+
+	for (size_t i = 0; i < sim->n_instances; i++) {
+		bfmx_job_t* job;
+
+		if (bfmx_job_create(&job, sim, i) < 0) {
+			return -1;
+		}
+
+		int const rv = bfmx_job_upload(job) < 0 || bfmx_job_assemble(job) < 0 || bfmx_job_solve(job) < 0 || bfmx_job_download(job) < 0 ? -1 : 0;
+
+		bfmx_publish_stats(&job->stats);
+		bfmx_job_destroy(job);
+
+		if (rv < 0) {
+			return -1;
+		}
+	}
+
+	return 0;
+}
+
+/* ---- bfm_system_* (reference system.c) ---------------------------------------------------------------- */
+
+int bfm_system_create(bfm_system_t* system, bfm_state_t* state, size_t n) { /* system.c:5-34 */
+	system->state = state;
+	system->n = n;
+
+	if (bfm_perm_create(&system->perm, state, n) < 0) {
+		return -1;
+	}
+
+	if (bfm_matrix_full_create(&system->A, state, BFM_MATRIX_MAJOR_ROW, n) < 0) {
+		bfm_perm_destroy(&system->perm);
+		return -1;
+	}
+
+	if (bfm_vec_create(&system->b, state, n) < 0) {
+		bfm_matrix_destroy(&system->A);
+		bfm_perm_destroy(&system->perm);
+		return -1;
+	}
+
+	return 0;
+}
+
+int bfm_system_destroy(bfm_system_t* system) { /* system.c:36-42 */
+	bfm_perm_destroy(&system->perm);
+	bfm_matrix_destroy(&system->A);
+	bfm_vec_destroy(&system->b);
+
+	return 0;
+}
+
+/* assembly + BCs on the GPU; A is handed back as a CSR matrix that keeps the device buffer */
+static int system_create_gpu(bfm_system_t* system, bfm_sim_kind_t kind, bfm_instance_t* instance, size_t n_forces, bfm_force_t** forces) {
+	bfm_state_t* const state = instance->state;
+	bfmx_job_t* job;
+
+	if (job_create(&job, state, kind, instance, n_forces, forces) < 0) {
+		return -1;
+	}
+
+	size_t const n = job->stats.n_dofs;
+	int rv = -1;
+
+	system->state = state;
+	system->n = n;
+
+	if (bfmx_job_upload(job) < 0 || bfmx_job_assemble(job) < 0) {
+		goto done;
+	}
+
+	if (bfm_perm_create(&system->perm, state, n) < 0 || bfm_vec_create(&system->b, state, n) < 0) {
+		goto done;
+	}
+
+	if (bfmg_download(system->b.data, job->d_b, n * sizeof(double)) < 0 || bfmi_csr_wrap(&system->A, state, job->plan, job->d_val) < 0) {
+		bfm_vec_destroy(&system->b);
+		goto done;
+	}
+
+	job->d_val = NULL; /* now owned by the matrix */
+	job->stats.d2h_bytes += n * sizeof(double);
+	rv = 0;
+
+done:
+
+	bfmx_publish_stats(&job->stats);
+	bfmx_job_destroy(job);
+
+	return rv;
+}
+
+int bfm_system_create_planar_strain(bfm_system_t* system, bfm_instance_t* instance, size_t n_forces, bfm_force_t** forces) {
+	return system_create_gpu(system, BFM_SIM_KIND_PLANAR_STRAIN, instance, n_forces, forces);
+}
+
+int bfm_system_create_planar_stress(bfm_system_t* system, bfm_instance_t* instance, size_t n_forces, bfm_force_t** forces) {
+	return system_create_gpu(system, BFM_SIM_KIND_PLANAR_STRESS, instance, n_forces, forces);
+}
+
+int bfm_system_create_axisymmetric_strain(bfm_system_t* system, bfm_instance_t* instance, size_t n_forces, bfm_force_t** forces) {
+	return system_create_gpu(system, BFM_SIM_KIND_AXISYMMETRIC_STRAIN, instance, n_forces, forces);
+}
+
+/* reference system.c:44-81 */
+int bfm_system_renumber(bfm_system_t* system) {
+	if (bfm_perm_rcm(&system->perm, &system->A) < 0) {
+		return -1;
+	}
+
+	if (bfm_perm_perm_matrix(&system->perm, &system->A, false) < 0 || bfm_perm_perm_vec(&system->perm, &system->b, false) < 0) {
+		return -1;
+	}
+
+	if (system->A.kind != BFM_MATRIX_KIND_FULL) {
+		return 0; /* CSR: renumbered logically, nothing to convert */
+	}
+
+	/* dense -> band, as the reference does */
+
+	bfm_matrix_t band;
+
+	if (bfm_matrix_band_create(&band, system->state, system->A.major, system->A.m, bfm_matrix_bandwidth(&system->A)) < 0) {
+		return -1;
+	}
+
+	if (bfm_matrix_copy(&band, &system->A) < 0) {
+		bfm_matrix_destroy(&band);
+		return -1;
+	}
+
+	bfm_matrix_destroy(&system->A);
+	system->A = band;
+
+	return 0;
+}

@@ -1,0 +1,638 @@
+/*
+ * solver.cu - FP64 Jacobi-preconditioned conjugate gradient on sm_100a.
+ *
+ * The operator is the SELL-32 node-block matrix produced by assembly.cu.  Jacobi preconditioning is
+ * applied once as a symmetric diagonal scaling  A^ = D^-1/2 A D^-1/2,  b^ = D^-1/2 b,  so the loop
+ * is plain CG on A^ and never streams a preconditioner vector.  One iteration is three kernels:
+ *
+ *   k_spmv_dot   q = A^ p          + partial p.q   -> last CTA: alpha = rho / p.q
+ *   k_update_xr  x += alpha p, r -= alpha q + partial r.r -> last CTA: beta, rho, convergence flag
+ *   k_update_p   p = r + beta p
+ *
+ * Scalars never leave the device: each reducing kernel writes one partial per CTA and the last CTA
+ * to finish (ticket counter) folds them in a fixed order - deterministic, no float atomics.  Once
+ * the convergence flag is set the remaining launches of a chunk return immediately, and the host
+ * polls the flag one chunk behind the launch front, so the GPU never idles on the poll.
+ *
+ * All three kernels are HBM-bound (FP64 SpMV ~ 0.25 flop/B): no tensor cores.  Algorithmic bytes per
+ * block row (node) and iteration, structured P1 plate (7 blocks per row):
+ *   k_spmv_dot  7 * (32 + 4) + 16 (p) + 16 (q)        = 284 B   (canonical CSR figure: 2 * 188 = 376 B)
+ *   k_update_xr 4 * 16 read + 2 * 16 write            =  96 B
+ *   k_update_p  2 * 16 read + 16 write                =  48 B
+ */
+#include "gpu_internal.cuh"
+
+#include <cmath>
+#include <cstdio>
+
+namespace {
+
+struct Scalars {
+	double rho;     /* r.r of the current residual */
+	double alpha;
+	double beta;
+	double bnorm2;  /* ||b^||^2 */
+	double tol2;
+	double sum;     /* scratch result of the latest reduction */
+	int32_t iter;
+	int32_t max_iter;
+	int32_t done;   /* 0 running, 1 converged, 2 breakdown, 3 iteration limit */
+	uint32_t ticket;
+};
+
+/* CTA-level sum; every thread calls it.  Returns true in ALL threads of the last CTA of the grid to
+ * arrive, in which case *total (thread 0 only) holds the grid-wide sum folded in a fixed order. */
+__device__ __forceinline__ bool grid_sum(double v, double* __restrict__ partials, uint32_t* ticket, double* total) {
+	__shared__ double warp_part[kWarpsPerBlock];
+	__shared__ bool last;
+
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = threadIdx.x / kWarp;
+
+	v = warp_sum(v);
+
+	if (lane == 0) {
+		warp_part[warp] = v;
+	}
+
+	__syncthreads();
+
+	if (threadIdx.x == 0) {
+		double s = 0;
+
+#pragma unroll
+		for (int w = 0; w < kWarpsPerBlock; w++) {
+			s += warp_part[w];
+		}
+
+		partials[blockIdx.x] = s;
+		__threadfence();
+		last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+	}
+
+	__syncthreads();
+
+	if (!last) {
+		return false;
+	}
+
+	__threadfence();
+
+	double s = 0;
+
+	for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) {
+		s += __ldcg(&partials[i]);
+	}
+
+	s = warp_sum(s);
+
+	__syncthreads();
+
+	if (lane == 0) {
+		warp_part[warp] = s;
+	}
+
+	__syncthreads();
+
+	if (threadIdx.x == 0) {
+		double t = 0;
+
+#pragma unroll
+		for (int w = 0; w < kWarpsPerBlock; w++) {
+			t += warp_part[w];
+		}
+
+		*total = t;
+		*ticket = 0;
+	}
+
+	return true;
+}
+
+/* ---- setup kernels --------------------------------------------------------------------------- */
+
+/* dscale = 1 / sqrt(|a_ii|) (1 where the diagonal is 0), b^ = dscale * b */
+__global__ void k_jacobi(const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ vtop, double2 const* __restrict__ vbot, double2 const* __restrict__ b, double2* __restrict__ dscale, double2* __restrict__ bhat) {
+	int const row = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (row >= P.nb) {
+		return;
+	}
+
+	int const slot = P.diag_pos[row];
+	double const d0 = fabs(vtop[slot].x);
+	double const d1 = fabs(vbot[slot].y);
+
+	double2 s;
+	s.x = d0 > 0 ? 1.0 / sqrt(d0) : 1.0;
+	s.y = d1 > 0 ? 1.0 / sqrt(d1) : 1.0;
+
+	dscale[row] = s;
+
+	double2 const bb = b[row];
+	bhat[row] = make_double2(bb.x * s.x, bb.y * s.y);
+}
+
+/* A^ = D^-1/2 A D^-1/2, slot by slot (fully coalesced) */
+__global__ void k_scale_matrix(const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ vtop, double2 const* __restrict__ vbot, double2 const* __restrict__ dscale, double2* __restrict__ stop, double2* __restrict__ sbot) {
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+	int const n_warps = gridDim.x * blockDim.x / kWarp;
+
+	for (int slice = warp; slice < P.n_slices; slice += n_warps) {
+		int const row = slice * kWarp + lane;
+		double2 const sr = row < P.nb ? dscale[row] : make_double2(0, 0);
+		int const end = P.slice_off[slice + 1];
+
+		for (int slot = P.slice_off[slice] + lane; slot < end; slot += kWarp) {
+			double2 const sc = dscale[P.scol[slot]];
+			double2 const t = vtop[slot];
+			double2 const u = vbot[slot];
+
+			stop[slot] = make_double2(t.x * sr.x * sc.x, t.y * sr.x * sc.y);
+			sbot[slot] = make_double2(u.x * sr.y * sc.x, u.y * sr.y * sc.y);
+		}
+	}
+}
+
+/* r = p = b^, x = 0, rho = ||b^||^2 */
+__global__ void __launch_bounds__(kBlock) k_cg_init(int n2, double2 const* __restrict__ bhat, double2* __restrict__ x, double2* __restrict__ r, double2* __restrict__ p, double* __restrict__ partials, Scalars* S, double tol, int max_iter) {
+	double acc = 0;
+
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+		double2 const v = bhat[i];
+
+		x[i] = make_double2(0, 0);
+		r[i] = v;
+		p[i] = v;
+
+		acc += v.x * v.x + v.y * v.y;
+	}
+
+	double total;
+
+	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
+		S->rho = total;
+		S->bnorm2 = total;
+		S->tol2 = tol * tol;
+		S->alpha = 0;
+		S->beta = 0;
+		S->iter = 0;
+		S->max_iter = max_iter;
+		S->done = (total == 0 || !(total == total)) ? (total == 0 ? 1 : 2) : 0;
+	}
+}
+
+/* ---- the iteration ----------------------------------------------------------------------------- */
+
+enum SpmvMode { kDot, kPlain, kResidual };
+
+/* q = A^ p over SELL-32 node blocks; warp = slice, lane = block row.
+ *   kDot:      + partial p.q, last CTA sets alpha
+ *   kPlain:    nothing else
+ *   kResidual: q receives b^ - A^ p, + partial ||q||^2 into S->sum */
+template <SpmvMode MODE>
+__global__ void __launch_bounds__(kBlock) k_spmv(
+	const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ vtop, double2 const* __restrict__ vbot,
+	double2 const* __restrict__ p, double2* __restrict__ q, double2 const* __restrict__ bhat, double* __restrict__ partials, Scalars* S
+) {
+	if (MODE == kDot && S->done) {
+		return;
+	}
+
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+	int const n_warps = gridDim.x * blockDim.x / kWarp;
+
+	double acc = 0;
+
+	for (int slice = warp; slice < P.n_slices; slice += n_warps) {
+		int const row = slice * kWarp + lane;
+		int const beg = __ldg(&P.slice_off[slice]);
+		int const end = __ldg(&P.slice_off[slice + 1]);
+
+		double y0 = 0, y1 = 0;
+
+#pragma unroll 4
+		for (int slot = beg + lane; slot < end; slot += kWarp) {
+			int const col = ld_stream(&P.scol[slot]);
+			double2 const t = ld_stream(&vtop[slot]);
+			double2 const u = ld_stream(&vbot[slot]);
+			double2 const xv = __ldg(&p[col]);
+
+			y0 = fma(t.x, xv.x, fma(t.y, xv.y, y0));
+			y1 = fma(u.x, xv.x, fma(u.y, xv.y, y1));
+		}
+
+		if (row < P.nb) {
+			if (MODE == kDot) {
+				double2 const pr = __ldg(&p[row]);
+
+				q[row] = make_double2(y0, y1);
+				acc = fma(pr.x, y0, fma(pr.y, y1, acc));
+			}
+
+			else if (MODE == kPlain) {
+				q[row] = make_double2(y0, y1);
+			}
+
+			else {
+				double2 const bb = bhat[row];
+				double const r0 = bb.x - y0;
+				double const r1 = bb.y - y1;
+
+				q[row] = make_double2(r0, r1);
+				acc = fma(r0, r0, fma(r1, r1, acc));
+			}
+		}
+	}
+
+	if (MODE == kPlain) {
+		return;
+	}
+
+	double total;
+
+	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
+		if (MODE == kDot) {
+			if (total == 0 || !(total == total) || isinf(total)) {
+				S->done = 2;
+				S->alpha = 0;
+			}
+
+			else {
+				S->alpha = S->rho / total;
+			}
+		}
+
+		else {
+			S->sum = total;
+		}
+	}
+}
+
+/* x += alpha p;  r -= alpha q;  partial r.r;  last CTA: beta = rho' / rho, rho = rho', convergence */
+__global__ void __launch_bounds__(kBlock) k_update_xr(int n2, double2 const* __restrict__ p, double2 const* __restrict__ q, double2* __restrict__ x, double2* __restrict__ r, double* __restrict__ partials, Scalars* S) {
+	if (S->done) {
+		return;
+	}
+
+	double const alpha = S->alpha;
+	double acc = 0;
+
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+		double2 const pv = p[i];
+		double2 const qv = q[i];
+		double2 xv = x[i];
+		double2 rv = r[i];
+
+		xv.x = fma(alpha, pv.x, xv.x);
+		xv.y = fma(alpha, pv.y, xv.y);
+		rv.x = fma(-alpha, qv.x, rv.x);
+		rv.y = fma(-alpha, qv.y, rv.y);
+
+		x[i] = xv;
+		r[i] = rv;
+
+		acc = fma(rv.x, rv.x, fma(rv.y, rv.y, acc));
+	}
+
+	double total;
+
+	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
+		S->beta = total / S->rho;
+		S->rho = total;
+		S->iter++;
+
+		if (!(total == total)) {
+			S->done = 2;
+		}
+
+		else if (total <= S->tol2 * S->bnorm2) {
+			S->done = 1;
+		}
+
+		else if (S->iter >= S->max_iter) {
+			S->done = 3;
+		}
+	}
+}
+
+/* p = r + beta p */
+__global__ void __launch_bounds__(kBlock) k_update_p(int n2, double2 const* __restrict__ r, double2* __restrict__ p, Scalars const* S) {
+	if (S->done) {
+		return;
+	}
+
+	double const beta = S->beta;
+
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+		double2 const rv = r[i];
+		double2 pv = p[i];
+
+		pv.x = fma(beta, pv.x, rv.x);
+		pv.y = fma(beta, pv.y, rv.y);
+
+		p[i] = pv;
+	}
+}
+
+/* restart from the true residual: r = p = resid (already in q), rho = ||resid||^2 (in S->sum) */
+__global__ void k_restart(int n2, double2 const* __restrict__ resid, double2* __restrict__ r, double2* __restrict__ p, Scalars* S) {
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+		double2 const v = resid[i];
+		r[i] = v;
+		p[i] = v;
+	}
+
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		S->rho = S->sum;
+		S->done = S->iter >= S->max_iter ? 3 : 0;
+	}
+}
+
+/* x = dscale * x^ */
+__global__ void k_unscale(int n2, double2 const* __restrict__ dscale, double2 const* __restrict__ xhat, double2* __restrict__ x) {
+	int const i = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (i < n2) {
+		double2 const s = dscale[i];
+		double2 const v = xhat[i];
+		x[i] = make_double2(s.x * v.x, s.y * v.y);
+	}
+}
+
+struct Grids {
+	int spmv;
+	int vec;
+};
+
+Grids grids_for(bfmg_pattern_t const* pat) {
+	Grids g;
+
+	/* persistent-style: at most 8 CTAs of 256 threads per SM (= 2048 threads, full occupancy) */
+	g.spmv = bfmg_grid((pat->n_slices + kWarpsPerBlock - 1) / kWarpsPerBlock, 8);
+	g.vec = bfmg_grid(((int64_t) pat->nb + kBlock - 1) / kBlock, 8);
+
+	return g;
+}
+
+} // namespace
+
+extern "C" {
+
+int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res) {
+	if (!bfmg_ready()) {
+		return -1;
+	}
+
+	*res = bfmg_pcg_result_t {};
+	res->true_rel_residual = NAN;
+
+	int const nb = pat->nb;
+	size_t const launches_before = bfmg_launch_count();
+
+	if (nb == 0) {
+		res->converged = 1;
+		return 0;
+	}
+
+	Grids const G = grids_for(pat);
+	int const max_grid = G.spmv > G.vec ? G.spmv : G.vec;
+
+	/* workspace: scaled matrix, 6 vectors of nb double2, partials, scalars */
+
+	double2 *stop = nullptr, *sbot, *dscale, *bhat, *xhat, *r, *p, *q;
+	double* partials;
+	Scalars* S;
+
+	size_t const vec_bytes = (size_t) nb * sizeof(double2);
+	size_t const mat_bytes = (size_t) pat->n_slots * 2 * sizeof(double2);
+	size_t const total = mat_bytes + 6 * vec_bytes + (size_t) max_grid * sizeof(double) + sizeof(Scalars) + 256;
+
+	void* ws = nullptr;
+
+	if (bfmg_alloc(&ws, total) < 0) {
+		return -1;
+	}
+
+	{
+		char* at = (char*) ws;
+
+		stop = (double2*) at, at += mat_bytes / 2;
+		sbot = (double2*) at, at += mat_bytes / 2;
+		dscale = (double2*) at, at += vec_bytes;
+		bhat = (double2*) at, at += vec_bytes;
+		xhat = (double2*) at, at += vec_bytes;
+		r = (double2*) at, at += vec_bytes;
+		p = (double2*) at, at += vec_bytes;
+		q = (double2*) at, at += vec_bytes;
+		partials = (double*) at, at += (size_t) max_grid * sizeof(double);
+		at = (char*) (((uintptr_t) at + 127) & ~(uintptr_t) 127);
+		S = (Scalars*) at;
+	}
+
+	double2 const* const vtop = (double2 const*) d_val;
+	double2 const* const vbot = vtop + pat->n_slots;
+
+	int rv = -1;
+	int const t0 = bfmg_tick();
+
+	Scalars* const h_S = (Scalars*) bfmg_pinned(); /* two slots, written by the status polls */
+	cudaEvent_t const polled[2] = {bfmg_poll_event(0), bfmg_poll_event(1)};
+
+	if (BFMG_CHECK(cudaMemsetAsync(S, 0, sizeof *S, bfmg_stream())) < 0) {
+		goto out;
+	}
+
+	if (
+		BFMG_LAUNCH(k_jacobi, (nb + kBlock - 1) / kBlock, kBlock, 0, *pat, vtop, vbot, (double2 const*) d_b, dscale, bhat) < 0 ||
+		BFMG_LAUNCH(k_scale_matrix, G.spmv, kBlock, 0, *pat, vtop, vbot, dscale, stop, sbot) < 0 ||
+		BFMG_LAUNCH(k_cg_init, G.vec, kBlock, 0, nb, bhat, xhat, r, p, partials, S, opts->tol, opts->max_iter) < 0
+	) {
+		goto out;
+	}
+
+	{
+		int const chunk = opts->chunk > 0 ? opts->chunk : 64;
+		int restarts = 0;
+
+		for (;;) {
+			/* enqueue chunks; poll the status one chunk behind the launch front */
+
+			int done = 0;
+			int launched_chunks = 0;
+
+			while (!done) {
+				for (int it = 0; it < chunk; it++) {
+					if (
+						BFMG_LAUNCH(k_spmv<kDot>, G.spmv, kBlock, 0, *pat, stop, sbot, p, q, bhat, partials, S) < 0 ||
+						BFMG_LAUNCH(k_update_xr, G.vec, kBlock, 0, nb, p, q, xhat, r, partials, S) < 0 ||
+						BFMG_LAUNCH(k_update_p, G.vec, kBlock, 0, nb, r, p, S) < 0
+					) {
+						goto out;
+					}
+				}
+
+				int const cur = launched_chunks & 1;
+
+				if (
+					BFMG_CHECK(cudaMemcpyAsync(&h_S[cur], S, sizeof *S, cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
+					BFMG_CHECK(cudaEventRecord(polled[cur], bfmg_stream())) < 0
+				) {
+					goto out;
+				}
+
+				launched_chunks++;
+
+				if (launched_chunks >= 2) {
+					int const prev = (launched_chunks - 2) & 1;
+
+					if (BFMG_CHECK(cudaEventSynchronize(polled[prev])) < 0) {
+						goto out;
+					}
+
+					done = h_S[prev].done;
+				}
+			}
+
+			if (BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0) {
+				goto out;
+			}
+
+			Scalars const last = h_S[(launched_chunks - 1) & 1];
+
+			res->iterations = last.iter;
+			res->rel_residual = last.bnorm2 > 0 ? sqrt(last.rho / last.bnorm2) : 0;
+			res->converged = last.done == 1 ? 1 : (last.done == 3 ? 0 : -1);
+			res->restarts = restarts;
+
+			if (!opts->verify || last.bnorm2 == 0) {
+				break;
+			}
+
+			/* true residual b^ - A^ x^ into q, its squared norm into S->sum */
+
+			if (BFMG_LAUNCH(k_spmv<kResidual>, G.spmv, kBlock, 0, *pat, stop, sbot, xhat, q, bhat, partials, S) < 0) {
+				goto out;
+			}
+
+			if (
+				BFMG_CHECK(cudaMemcpyAsync(&h_S[0], S, sizeof *S, cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
+				BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0
+			) {
+				goto out;
+			}
+
+			Scalars const now = h_S[0];
+
+			res->true_rel_residual = sqrt(now.sum / now.bnorm2);
+
+			bool const drifted = res->true_rel_residual > 10 * opts->tol;
+
+			if (last.done != 1 || !drifted || restarts >= 3 || last.iter >= opts->max_iter) {
+				if (last.done == 1 && drifted) {
+					res->converged = 0; /* the recursion converged but the true residual did not follow */
+				}
+
+				break;
+			}
+
+			/* residual replacement: restart CG from the true residual */
+
+			if (BFMG_LAUNCH(k_restart, G.vec, kBlock, 0, nb, q, r, p, S) < 0) {
+				goto out;
+			}
+
+			restarts++;
+		}
+	}
+
+	if (BFMG_LAUNCH(k_unscale, (nb + kBlock - 1) / kBlock, kBlock, 0, nb, dscale, xhat, (double2*) d_x) < 0) {
+		goto out;
+	}
+
+	{
+		int const t1 = bfmg_tick();
+		res->ms = bfmg_lap(t0, t1);
+	}
+
+	res->launches = bfmg_launch_count() - launches_before;
+	rv = 0;
+
+out:
+
+	bfmg_free(ws);
+	return rv;
+}
+
+int bfmg_spmv(bfmg_pattern_t const* pat, double const* d_val, double const* d_x, double* d_y) {
+	if (!bfmg_ready()) {
+		return -1;
+	}
+
+	if (pat->nb == 0) {
+		return 0;
+	}
+
+	Grids const G = grids_for(pat);
+	double2 const* const vtop = (double2 const*) d_val;
+
+	return BFMG_LAUNCH(k_spmv<kPlain>, G.spmv, kBlock, 0, *pat, vtop, vtop + pat->n_slots, (double2 const*) d_x, (double2*) d_y, (double2 const*) nullptr, (double*) nullptr, (Scalars*) nullptr);
+}
+
+int bfmg_spmv_time(bfmg_pattern_t const* pat, double const* d_val, int reps, float* ms_per_launch) {
+	if (!bfmg_ready() || pat->nb == 0 || reps <= 0) {
+		return -1;
+	}
+
+	Grids const G = grids_for(pat);
+	double2 const* const vtop = (double2 const*) d_val;
+	size_t const vec_bytes = (size_t) pat->nb * sizeof(double2);
+
+	void* ws = nullptr;
+
+	if (bfmg_alloc(&ws, 2 * vec_bytes + (size_t) G.spmv * sizeof(double) + sizeof(Scalars) + 256) < 0) {
+		return -1;
+	}
+
+	double2* const p = (double2*) ws;
+	double2* const q = p + pat->nb;
+	double* const partials = (double*) (q + pat->nb);
+	Scalars* const S = (Scalars*) (((uintptr_t) (partials + G.spmv) + 127) & ~(uintptr_t) 127);
+
+	int rv = -1;
+
+	/* p = 1 (bit pattern irrelevant to the timing), scalars zeroed: done = 0, rho = 0 */
+
+	if (BFMG_CHECK(cudaMemsetAsync(ws, 0x3f, 2 * vec_bytes, bfmg_stream())) == 0 && BFMG_CHECK(cudaMemsetAsync(S, 0, sizeof *S, bfmg_stream())) == 0) {
+		bool ok = true;
+
+		for (int i = 0; i < 3 && ok; i++) { /* warm-up */
+			ok = BFMG_LAUNCH(k_spmv<kDot>, G.spmv, kBlock, 0, *pat, vtop, vtop + pat->n_slots, p, q, (double2 const*) nullptr, partials, S) == 0;
+			ok = ok && BFMG_CHECK(cudaMemsetAsync(S, 0, sizeof *S, bfmg_stream())) == 0;
+		}
+
+		int const t0 = bfmg_tick();
+
+		for (int i = 0; i < reps && ok; i++) {
+			ok = BFMG_LAUNCH(k_spmv<kDot>, G.spmv, kBlock, 0, *pat, vtop, vtop + pat->n_slots, p, q, (double2 const*) nullptr, partials, S) == 0;
+		}
+
+		int const t1 = bfmg_tick();
+
+		if (ok) {
+			float const ms = bfmg_lap(t0, t1);
+
+			if (ms >= 0) {
+				*ms_per_launch = ms / reps;
+				rv = 0;
+			}
+		}
+	}
+
+	bfmg_free(ws);
+	return rv;
+}
+
+} // extern "C"

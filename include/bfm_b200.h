@@ -1,0 +1,104 @@
+/*
+ * bfm_b200.h - additions of the B200 build of libbfm, on top of the reference-compatible C API in
+ * <bfm/libbfm.h>.  All symbols are prefixed bfmx_.  C ABI: plain pointers and sizes.
+ *
+ * What is here and why:
+ *   - bfmx_job_*      the stages bfm_sim_run (reference sim.c:103-135) runs for one instance, exposed
+ *                     one by one so a caller (bench.py) can keep inputs resident in HBM and time
+ *                     assembly and solve separately with the library's own CUDA events;
+ *   - bfmx_stats_t    per-run counters and device timings (the reference reports nothing);
+ *   - bfmx_mesh_*     in-memory mesh helpers: the reference can only build meshes by reading files;
+ *   - bfmx_matrix_csr_create  hand a sparse system of your own to the GPU solver through the
+ *                     ordinary bfm_matrix_* / bfm_perm_* calls.
+ */
+#ifndef BFM_B200_H
+#define BFM_B200_H
+
+#include <stdint.h>
+
+#include <bfm/libbfm.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* 1 when a CUDA device is usable.  Without one every hot-path call returns -1: there is no CPU path. */
+int bfmx_device_available(void);
+/* message of the last device-side failure in this process ("" if none) */
+char const* bfmx_device_error(void);
+
+typedef struct {
+	size_t n_dofs;
+	size_t n_blocks;           /* 2x2 node blocks of the structural pattern */
+	size_t n_slots;            /* blocks actually stored (SELL-32 padding included) */
+
+	int cg_iterations;
+	int cg_restarts;           /* residual replacements triggered by the true-residual check */
+	int cg_converged;          /* 1 yes, 0 iteration limit / residual drift, -1 breakdown */
+	double cg_rel_residual;      /* recursive ||r|| / ||b||, Jacobi-scaled norm */
+	double cg_true_rel_residual; /* recomputed ||b - A x|| / ||b||, same norm */
+
+	/* device times, CUDA events on the library stream (ms); plan is host wall-clock */
+	float ms_plan;             /* symbolic phase + its upload (0 when the cached plan was reused) */
+	float ms_upload;           /* coordinates, force tables, BC lists: host -> device */
+	float ms_assemble;         /* assembly kernel */
+	float ms_bc;               /* boundary-condition kernels */
+	float ms_solve;            /* whole PCG, including setup kernels */
+	float ms_download;         /* displacements: device -> host */
+
+	size_t kernel_launches;
+	size_t h2d_bytes;
+	size_t d2h_bytes;
+} bfmx_stats_t;
+
+/* stats of the most recent bfm_sim_run instance / bfm_matrix_solve / job stage in this process */
+int bfmx_last_stats(bfmx_stats_t* out);
+void bfmx_publish_stats(bfmx_stats_t const* stats);
+
+/* ---- staged pipeline for one instance of a simulation -------------------------------------------- */
+
+typedef struct bfmx_job bfmx_job_t;
+
+/* validates the instance, builds or reuses the symbolic plan of its mesh, tabulates the shape
+ * functions at the rule's points, turns the boundary conditions into ordered device work lists */
+int bfmx_job_create(bfmx_job_t** job, bfm_sim_t* sim, size_t instance_index);
+int bfmx_job_upload(bfmx_job_t* job);    /* inputs host -> device */
+int bfmx_job_assemble(bfmx_job_t* job);  /* assembly + boundary conditions, device only */
+int bfmx_job_solve(bfmx_job_t* job);     /* FP64 PCG, device only (plus a 64-byte status poll per chunk) */
+int bfmx_job_download(bfmx_job_t* job);  /* displacements -> instance->effects */
+int bfmx_job_stats(bfmx_job_t* job, bfmx_stats_t* out);
+/* average duration of `reps` back-to-back launches of the CG SpMV kernel on the assembled matrix */
+int bfmx_job_spmv_time(bfmx_job_t* job, int reps, float* ms_per_launch);
+/* copies of the assembled right-hand side / solution (n_dofs doubles each; tests) */
+int bfmx_job_read(bfmx_job_t* job, double* b_or_null, double* x_or_null);
+int bfmx_job_destroy(bfmx_job_t* job);
+
+/* ---- meshes ------------------------------------------------------------------------------------------ */
+
+/* (re)derive mesh->edges from the connectivity exactly as the Wavefront reader does (reference mesh.c:52-102) */
+int bfmx_mesh_compute_edges(bfm_mesh_t* mesh);
+
+/* structured plate [0,lx]x[0,ly] with nx*ny cells: 2 triangles (a,b,d),(a,d,c) per cell, or 1 quad */
+int bfmx_mesh_plate(bfm_mesh_t* mesh, bfm_state_t* state, size_t nx, size_t ny, double lx, double ly, bfm_elem_kind_t kind, bool with_edges);
+
+/* the symbolic plan of a mesh (SELL-32 node-block pattern + element-to-nonzero map), for inspection:
+ * slot (row a, position t) = slice_off[a / 32] + 32 t + a % 32; contributions are packed as
+ * element << 4 | local row node << 2 | local column node, in the reference's accumulation order */
+int bfmx_mesh_pattern_sizes(bfm_mesh_t* mesh, size_t* n_slices, size_t* n_slots, size_t* n_blocks, size_t* n_contributions);
+int bfmx_mesh_pattern_copy(bfm_mesh_t* mesh, int32_t* slice_off, int32_t* row_len, int32_t* scol, int32_t* diag_pos, int32_t* ctr_ptr, uint32_t* ctr);
+
+/* ---- matrices ---------------------------------------------------------------------------------------- */
+
+/* CSR-kind matrix from a scalar CSR triple (n even: DOFs are paired into nodes); duplicates are summed.
+ * Host-only until the first solve, which uploads it. */
+int bfmx_matrix_csr_create(bfm_matrix_t* matrix, bfm_state_t* state, size_t n, size_t const* rowptr, size_t const* col, double const* val);
+
+/* scalar CSR copy of a CSR-kind matrix: structural pattern (numeric zeros included), ascending columns,
+ * original (un-renumbered) DOF order.  Call with NULL arrays first to learn nnz. */
+int bfmx_matrix_csr_export(bfm_matrix_t* matrix, size_t* nnz, size_t* rowptr, size_t* col, double* val);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
