@@ -297,6 +297,8 @@ void bfmi_pcg_options(size_t n, bfmg_pcg_opts_t* opts) {
 	opts->max_iter = (int32_t) (100 * sqrt((double) n) + 10000);
 	opts->chunk = 64;
 	opts->verify = 1;
+	opts->true_tol = 1e-6;
+	opts->max_restarts = 0;
 
 	if ((env = getenv("BFM_CG_TOL")) != NULL && atof(env) > 0) {
 		opts->tol = atof(env);
@@ -312,6 +314,14 @@ void bfmi_pcg_options(size_t n, bfmg_pcg_opts_t* opts) {
 
 	if ((env = getenv("BFM_CG_VERIFY")) != NULL) {
 		opts->verify = atoi(env);
+	}
+
+	if ((env = getenv("BFM_CG_TRUE_TOL")) != NULL && atof(env) > 0) {
+		opts->true_tol = atof(env);
+	}
+
+	if ((env = getenv("BFM_CG_RESTARTS")) != NULL) {
+		opts->max_restarts = atoi(env);
 	}
 }
 

@@ -96,7 +96,9 @@ typedef struct {
 	double tol;          /* stop at ||r|| <= tol * ||b|| in the Jacobi-scaled norm */
 	int32_t max_iter;
 	int32_t chunk;       /* iterations enqueued between two convergence polls */
-	int32_t verify;      /* recompute the true residual at the end (and restart if it drifted) */
+	int32_t verify;      /* recompute the true residual b - A x at the end and report it */
+	double true_tol;     /* a true residual above this fails the solve (after max_restarts residual replacements) */
+	int32_t max_restarts;
 } bfmg_pcg_opts_t;
 
 typedef struct {

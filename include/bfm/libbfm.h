@@ -30,7 +30,7 @@ extern "C" {
 // libbfm (B200 build) - library state: error slot + pluggable allocator.
 // ABI-compatible with the reference's bfm/bfm.h:6-34 (sizeof(bfm_state_t) == 64 on x86-64).
 // pybfm's binding generator (pybfm/bfm/gen_libbfm.py:11-50) takes its cdef text from the reference's
-// own header files and only COMPILES against the installed <bfm/*.h>, so the forwarders suffice.
+// own header files and only COMPILES against the installed bfm headers, so the forwarders suffice.
 
 // allocator hooks; every buffer the library hands back is obtained through these
 typedef void* (*bfm_alloc_t)(size_t size);
