@@ -26,6 +26,8 @@ struct Context {
 	cudaEvent_t events[kEvents];
 	int next_event = 0;
 
+	cudaEvent_t user[8][2] = {}; /* bfmx_timer_* slots */
+
 	void* pinned = nullptr;      /* 4 KiB of page-locked host memory for status polls */
 	cudaEvent_t poll[2] = {};    /* untimed events marking those polls */
 };
@@ -103,6 +105,15 @@ bool init() {
 		if ((rc = cudaEventCreate(&ev)) != cudaSuccess) {
 			set_error("cudaEventCreate: %s", cudaGetErrorString(rc));
 			return false;
+		}
+	}
+
+	for (auto& pair : G.user) {
+		for (auto& ev : pair) {
+			if ((rc = cudaEventCreate(&ev)) != cudaSuccess) {
+				set_error("cudaEventCreate: %s", cudaGetErrorString(rc));
+				return false;
+			}
 		}
 	}
 
@@ -257,6 +268,29 @@ int bfmg_tick(void) {
 	G.next_event = (G.next_event + 1) % Context::kEvents;
 
 	return BFMG_CHECK(cudaEventRecord(G.events[slot], G.stream)) < 0 ? -1 : slot;
+}
+
+int bfmg_timer_start(int slot) {
+	if (!bfmg_ready() || slot < 0 || slot >= 8) {
+		return -1;
+	}
+
+	return BFMG_CHECK(cudaEventRecord(G.user[slot][0], G.stream));
+}
+
+float bfmg_timer_stop(int slot) {
+	if (!bfmg_ready() || slot < 0 || slot >= 8) {
+		return -1;
+	}
+
+	float ms = -1;
+
+	if (cudaEventRecord(G.user[slot][1], G.stream) != cudaSuccess || cudaEventSynchronize(G.user[slot][1]) != cudaSuccess || cudaEventElapsedTime(&ms, G.user[slot][0], G.user[slot][1]) != cudaSuccess) {
+		cudaGetLastError();
+		return -1;
+	}
+
+	return ms;
 }
 
 float bfmg_lap(int from, int to) {

@@ -33,6 +33,8 @@ int bfmg_sync(void);
 /* CUDA-event stopwatch on the library stream: tick returns a handle, lap gives ms between two */
 int bfmg_tick(void);
 float bfmg_lap(int from, int to);      /* synchronises on `to` */
+int bfmg_timer_start(int slot);        /* 8 caller-owned stopwatch slots (same stream, CUDA events) */
+float bfmg_timer_stop(int slot);       /* ms since the matching start; synchronises */
 
 /* ---- sparsity pattern on the device (mirror of bfmi_plan_t, see internal.h) ------------------- */
 

@@ -93,6 +93,26 @@ char const* bfmx_device_error(void) {
 	return bfmg_last_error();
 }
 
+int bfmx_device_sync(void) {
+	return bfmg_sync();
+}
+
+int bfmx_timer_start(int slot) {
+	return bfmg_timer_start(slot);
+}
+
+float bfmx_timer_stop(int slot) {
+	return bfmg_timer_stop(slot);
+}
+
+size_t bfmx_kernel_launches(void) {
+	return bfmg_launch_count();
+}
+
+int bfmx_device_sm_count(void) {
+	return bfmg_sm_count();
+}
+
 static double now_ms(void) {
 	struct timespec ts;
 	clock_gettime(CLOCK_MONOTONIC, &ts);

@@ -27,6 +27,15 @@ int bfmx_device_available(void);
 /* message of the last device-side failure in this process ("" if none) */
 char const* bfmx_device_error(void);
 
+/* wait for everything the library has queued on its stream */
+int bfmx_device_sync(void);
+/* CUDA-event stopwatch on the library's stream (8 slots): stop returns the milliseconds since start */
+int bfmx_timer_start(int slot);
+float bfmx_timer_stop(int slot);
+/* kernels this library has launched so far in this process */
+size_t bfmx_kernel_launches(void);
+int bfmx_device_sm_count(void);
+
 typedef struct {
 	size_t n_dofs;
 	size_t n_blocks;           /* 2x2 node blocks of the structural pattern */
