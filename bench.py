@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py - assembly + solve throughput of the FEM hot path on the synthetic plate.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--cells NXxNY] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over the plate: element assembly + boundary conditions + the FP64
+PCG solve to a relative residual of 1e-12.  Rank 0 prints ONE JSON line:
+
+  value         DOF/s of assembly + solve with the mesh already resident in HBM (bfmx_job_assemble +
+                bfmx_job_solve), timed with CUDA events on the library's stream, max over ranks
+  e2e           the same metric through the reference-facing call, bfm_sim_run, with HOST buffers:
+                host->device copies of coordinates / BC lists and the device->host copy of the
+                displacements are inside the timed region
+  roofline      the dominant kernel (the CG SpMV, k_spmv<kDot>): algorithmic bytes of the stored SELL-32
+                2x2-block format per launch / its measured launch duration, against MEASURED_PEAKS.json
+  cpu_baseline  the unmodified reference libbfm (oracle/_ref, compiled from /root/reference by
+                oracle/Makefile) timed on one host core on a bounded sample of the same workload
+
+N > 1: the plate is row-partitioned over the ranks (strong scaling: the total mesh is fixed), with the
+interface-DOF halo exchange and the CG dot products going over NVLink (bfm_b200/csrc/dist.cu).
+
+`--impl reference` times the reference's own CPU implementation of the path (rank 0 only).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "assembly+solve throughput"
+UNIT = "DOF/s"
+
+DEFAULT_CELLS = "4000x1000"       # 4001 x 1001 nodes = 8.0 M DOF: the matrix alone (1.0 GB) is 8x the 126 MB L2
+REFERENCE_SAMPLE = "160x40"       # 13 202 DOF: the largest SURVEY.md parity size the dense reference does in ~10 s
+
+
+def parse_cells(text: str) -> tuple[int, int]:
+	nx, ny = (int(v) for v in text.lower().split("x"))
+	return nx, ny
+
+
+# ---- clocks ------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+	"""nvidia-smi clocks / throttle reasons of one GPU while the timed region runs (B200_PROFILING.md)"""
+
+	FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+	def __init__(self, index: int):
+		self.index = index
+		self.proc = None
+		self.lines: list[str] = []
+		self.thread = None
+
+	def start(self):
+		try:
+			self.proc = subprocess.Popen(
+				["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+				stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+			)
+		except OSError:
+			self.proc = None
+			return
+
+		def pump():
+			for line in self.proc.stdout:
+				self.lines.append(line)
+
+		self.thread = threading.Thread(target=pump, daemon=True)
+		self.thread.start()
+
+	def stop(self) -> dict:
+		if self.proc is None:
+			return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+
+		self.proc.terminate()
+
+		try:
+			self.proc.wait(timeout=5)
+		except subprocess.TimeoutExpired:
+			self.proc.kill()
+
+		self.thread.join(timeout=5)
+
+		sm, sm_max, power, reasons = [], [], [], set()
+		names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+		for line in self.lines:
+			parts = [p.strip() for p in line.split(",")]
+
+			if len(parts) < 7:
+				continue
+
+			try:
+				sm.append(float(parts[0]))
+				sm_max.append(float(parts[1]))
+				power.append(float(parts[2]))
+			except ValueError:
+				continue
+
+			for name, flag in zip(names, parts[3:7]):
+				if flag.lower().startswith("active"):
+					reasons.add(name)
+
+		# "under load" = samples drawing more than half of the highest power seen
+		busy = [s for s, p in zip(sm, power) if power and p >= 0.5 * max(power)] or sm
+
+		return {
+			"sm_mhz": statistics.median(busy) if busy else None,
+			"sm_max_mhz": max(sm_max) if sm_max else None,
+			"power_w_max": max(power) if power else None,
+			"samples": len(sm),
+			"reasons": sorted(reasons),
+		}
+
+
+# ---- the reference arm / CPU baseline ------------------------------------------------------------
+
+
+def time_reference(cells: str, steps: int, warmup: int) -> dict:
+	"""the UNMODIFIED reference libbfm (oracle/_ref/libbfm_ref.so), bfm_sim_run on one core"""
+
+	from bfm_b200 import workloads
+	from oracle import ref
+
+	if not ref.available():
+		raise RuntimeError("oracle/_ref/libbfm_ref.so is missing (python -c 'import __graft_entry__ as g; g.build()' builds it where /root/reference exists)")
+
+	nx, ny = parse_cells(cells)
+	case = workloads.plate_case(nx, ny, binding=ref.binding(), native_mesh=False)
+
+	for _ in range(warmup):
+		case.sim.run()
+
+	t0 = time.perf_counter()
+
+	for _ in range(steps):
+		case.sim.run()
+
+	seconds = (time.perf_counter() - t0) / steps
+
+	return {
+		"value": case.n_dofs / seconds,
+		"unit": UNIT,
+		"cores": 1,  # libbfm is single-threaded
+		"kind": "reference",
+		"sample": f"plate {nx}x{ny} cells = {case.n_dofs} DOF (dense reference caps at 46 340 DOF), bfm_sim_run x{steps}, {seconds:.3f} s each, host has {os.cpu_count()} logical cores",
+		"seconds_per_run": seconds,
+	}
+
+
+def reference_arm(args, rank: int):
+	if rank != 0:
+		return
+
+	nx, ny = parse_cells(args.cells)
+	base = time_reference(args.reference_sample, args.steps, args.warmup)
+
+	print(json.dumps({
+		"impl": "reference",
+		"metric": METRIC,
+		"value": base["value"],
+		"unit": UNIT,
+		"n_gpus": args.gpus,
+		"steps": args.steps,
+		"warmup": args.warmup,
+		"ms_per_step": base["seconds_per_run"] * 1e3,
+		"higher_is_better": True,
+		"scaling": "strong",
+		"vs_baseline": None,
+		"dtype": "f64",
+		"data": "synthetic",
+		"config": workload_config(nx, ny, args.gpus) | {"reference_sample": base["sample"]},
+		"cpu_baseline": base,
+		"e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+		"gpu_launches": 0,
+	}), flush=True)
+
+
+def workload_config(nx: int, ny: int, gpus: int) -> dict:
+	return {
+		"workload": f"synthetic structured triangulated plate {nx}x{ny} cells, {2 * (nx + 1) * (ny + 1)} DOF, plane stress, steel, gravity, left edge clamped (BASELINE.json configs[3])",
+		"cells": f"{nx}x{ny}",
+		"n_dofs": 2 * (nx + 1) * (ny + 1),
+		"element": "P1 triangle, 3-point Gauss",
+		"solver": "FP64 Jacobi-PCG, relative residual 1e-12",
+		"partition": "none" if gpus == 1 else f"{gpus} contiguous node-row blocks, halo exchange + dot-product reductions over NVLink",
+		"l2": "inputs larger than L2 (matrix ~1 GB at the default size); no flush needed",
+	}
+
+
+# ---- our arm ----------------------------------------------------------------------------------------
+
+
+def main():
+	ap = argparse.ArgumentParser()
+	ap.add_argument("--gpus", type=int, default=1)
+	ap.add_argument("--steps", type=int, default=3)
+	ap.add_argument("--warmup", type=int, default=3)
+	ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+	ap.add_argument("--cells", default=DEFAULT_CELLS, help="plate size NXxNY (cells)")
+	ap.add_argument("--reference-sample", default=REFERENCE_SAMPLE, help="plate size the CPU reference is timed on")
+	ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+	ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+	args = ap.parse_args()
+
+	rank = int(os.environ.get("RANK", "0"))
+	world = int(os.environ.get("WORLD_SIZE", "1"))
+	local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+	if args.impl == "reference":
+		reference_arm(args, rank)
+		return
+
+	if world != args.gpus:
+		raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+
+	import numpy as np
+
+	from bfm_b200 import api, ext, workloads
+
+	binding = api.default_binding()  # raises when libbfm.so is not built: there is no fallback
+
+	if not ext.device_available(binding):
+		raise SystemExit("no CUDA device: " + binding.lib.bfmx_device_error().decode())
+
+	lib = binding.lib
+	dist = None
+
+	if world > 1:
+		import torch
+		import torch.distributed as dist
+
+		torch.cuda.set_device(local_rank)
+		dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+		ext.dist_init(binding, dist, local_rank)  # hands the library its own communicator (bfmx_dist_init)
+
+	def barrier():
+		if dist is not None:
+			dist.barrier()
+
+		assert not lib.bfmx_device_sync()
+
+	def max_over_ranks(value: float) -> float:
+		if dist is None:
+			return value
+
+		import torch
+
+		t = torch.tensor([value], dtype=torch.float64, device="cuda")
+		dist.all_reduce(t, op=dist.ReduceOp.MAX)
+		return float(t.item())
+
+	nx, ny = parse_cells(args.cells)
+	case = workloads.plate_case(nx, ny, binding=binding)
+	n_dofs = case.n_dofs
+
+	job = ext.Job(case.sim)
+	job.upload()  # inputs resident in HBM from here on
+
+	def step():
+		job.assemble()
+		job.solve()
+
+	for _ in range(args.warmup):
+		step()
+
+	sampler = ClockSampler(local_rank)
+
+	if rank == 0:
+		sampler.start()
+
+	barrier()
+
+	launches0 = lib.bfmx_kernel_launches()
+	per_step = []
+
+	assert not lib.bfmx_timer_start(0)
+
+	for _ in range(args.steps):
+		step()
+		per_step.append(job.stats())
+
+	ms_total = lib.bfmx_timer_stop(0)  # synchronises
+	launches = lib.bfmx_kernel_launches() - launches0
+
+	barrier()
+
+	ms_total = max_over_ranks(ms_total)
+	clocks = sampler.stop() if rank == 0 else None
+
+	ms_per_step = ms_total / args.steps
+	value = n_dofs / (ms_per_step * 1e-3)
+
+	s = per_step[-1]
+	iters = s["cg_iterations"]
+	ms_asm = statistics.mean(p["ms_assemble"] + p["ms_bc"] for p in per_step)
+	ms_solve = statistics.mean(p["ms_solve"] for p in per_step)
+
+	# ---- roofline of the dominant kernel: the CG SpMV, timed live with CUDA events on the library stream
+
+	n_own = s["n_dofs_owned"] if "n_dofs_owned" in s else s["n_dofs"]
+	spmv_ms = max_over_ranks(job.spmv_ms(50))
+
+	stored_bytes = s["n_slots"] * 36 + (n_own // 2) * 32             # 2x2 blocks (32 B) + block column (4 B); p gathered once, q written once
+	canonical_bytes = 12 * 4 * s["n_blocks"] + 20 * n_own + 4        # scalar CSR, 12 B/nnz + 20 B/row
+	iter_bytes = stored_bytes + 72 * n_own                           # + update_xr (6 x 8 B/DOF) + update_p (3 x 8 B/DOF)
+
+	peaks = {}
+	peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+
+	if os.path.exists(peaks_path):
+		peaks = json.load(open(peaks_path))
+
+	peak = float(peaks.get("hbm_gbs", 6650.0))
+	peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+	achieved = stored_bytes / (spmv_ms * 1e-3) / 1e9
+	us_iter = ms_solve * 1e3 / max(iters, 1)
+
+	roofline = {
+		"kernel": "k_spmv<kDot> (q = A p over SELL-32 2x2 node blocks, fused p.q)",
+		"bound": "hbm",
+		"achieved": achieved,
+		"peak": peak,
+		"unit": "GB/s",
+		"frac": achieved / peak,
+		"frac_of_nominal_8TBs": achieved / 8000.0,
+		"peak_source": peak_src,
+		"traffic": None,  # dram__bytes from the ncu --set full capture: see profiles/
+		"bytes_per_launch": stored_bytes,
+		"us_per_launch": spmv_ms * 1e3,
+		"canonical_csr_bytes_per_launch": canonical_bytes,
+		"canonical_csr_gbs": canonical_bytes / (spmv_ms * 1e-3) / 1e9,
+		"cg_iteration": {
+			"us": us_iter,
+			"bytes": iter_bytes,
+			"achieved": iter_bytes / (us_iter * 1e-6) / 1e9,
+			"frac": iter_bytes / (us_iter * 1e-6) / 1e9 / peak,
+			"note": "whole PCG iteration (SpMV + 2 fused vector kernels) over the timed region: solve ms / iterations",
+		},
+	}
+
+	# ---- end to end: bfm_sim_run on host buffers (the call pybfm makes), copies inside the timed region
+
+	e2e = None
+
+	if not args.no_e2e:
+		case.sim.run()  # warm-up (the symbolic plan of the mesh is cached, as in examples/benchmark.py's loop)
+		barrier()
+
+		t0 = time.perf_counter()
+		assert not lib.bfmx_timer_start(1)
+		h2d = d2h = 0
+
+		for _ in range(args.steps):
+			case.sim.run()
+			st = ext.last_stats(binding)
+			h2d += st["h2d_bytes"]
+			d2h += st["d2h_bytes"]
+
+		# the displacements are on the host now; read them like pybfm does
+		checksum = float(np.abs(workloads.effects_view(case.instance)).max())
+
+		ms_e2e = lib.bfmx_timer_stop(1)
+		wall = (time.perf_counter() - t0) * 1e3
+		barrier()
+
+		ms_e2e = max_over_ranks(max(ms_e2e, wall)) / args.steps
+
+		e2e = {
+			"value": n_dofs / (ms_e2e * 1e-3),
+			"unit": UNIT,
+			"h2d_bytes_per_step": h2d // args.steps,
+			"d2h_bytes_per_step": d2h // args.steps,
+			"ms_per_step": ms_e2e,
+			"call": "bfm_sim_run (job create with cached plan + upload + assemble + solve + download into instance->effects)",
+			"max_abs_displacement": checksum,
+		}
+
+	cpu = None
+
+	if rank == 0 and world == 1 and not args.no_cpu_baseline:
+		cpu = time_reference(args.reference_sample, 1, 0)
+
+	if rank == 0:
+		print(json.dumps({
+			"metric": METRIC,
+			"value": value,
+			"unit": UNIT,
+			"n_gpus": world,
+			"steps": args.steps,
+			"warmup": args.warmup,
+			"ms_per_step": ms_per_step,
+			"higher_is_better": True,
+			"scaling": "strong",
+			"vs_baseline": None,  # the reference publishes no number for this metric
+			"dtype": "f64",
+			"data": "synthetic",
+			"config": workload_config(nx, ny, world),
+			"assembly_ms": ms_asm,
+			"solve_ms": ms_solve,
+			"cg_iterations": iters,
+			"cg_rel_residual": s["cg_rel_residual"],
+			"cg_true_rel_residual": s["cg_true_rel_residual"],
+			"roofline": roofline,
+			"cpu_baseline": cpu,
+			"e2e": e2e,
+			"gpu_launches": launches,
+			"clocks": clocks,
+		}), flush=True)
+
+	if dist is not None:
+		ext.dist_finalize(binding)
+		dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+	main()

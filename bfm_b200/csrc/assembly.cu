@@ -332,9 +332,8 @@ int bfmg_assemble(bfmg_pattern_t const* pat, bfmg_asm_tables_t const* tab, doubl
 	double2* const vbot = vtop + pat->n_slots;
 
 	int const blocks_needed = (pat->n_slices + kWarpsPerBlock - 1) / kWarpsPerBlock;
-	int const grid = bfmg_grid(blocks_needed, 8);
 
-#define ASM_LAUNCH(KIND, AXI) BFMG_LAUNCH((k_assemble<KIND, AXI>), grid, kBlock, 0, *tab, *pat, (double2 const*) d_coords, (double2 const*) d_nforce, vtop, vbot, (double2*) d_b)
+#define ASM_LAUNCH(KIND, AXI) BFMG_LAUNCH((k_assemble<KIND, AXI>), bfmg_grid(blocks_needed, bfmg_resident_ctas(k_assemble<KIND, AXI>)), kBlock, 0, *tab, *pat, (double2 const*) d_coords, (double2 const*) d_nforce, vtop, vbot, (double2*) d_b)
 
 	if (tab->kind == 3) {
 		return tab->axisym ? ASM_LAUNCH(3, true) : ASM_LAUNCH(3, false);

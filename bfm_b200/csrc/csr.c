@@ -297,7 +297,7 @@ void bfmi_pcg_options(size_t n, bfmg_pcg_opts_t* opts) {
 	opts->max_iter = (int32_t) (100 * sqrt((double) n) + 10000);
 	opts->chunk = 64;
 	opts->verify = 1;
-	opts->true_tol = 1e-6;
+	opts->true_tol = 1e-10; /* normwise backward error, see solver.cu */
 	opts->max_restarts = 0;
 
 	if ((env = getenv("BFM_CG_TOL")) != NULL && atof(env) > 0) {
@@ -396,6 +396,7 @@ int bfmi_csr_solve(bfm_matrix_t* matrix, bfm_vec_t* y) {
 	csr->stats.cg_converged = res.converged;
 	csr->stats.cg_rel_residual = res.rel_residual;
 	csr->stats.cg_true_rel_residual = res.true_rel_residual;
+	csr->stats.cg_backward_error = res.backward_error;
 	csr->stats.ms_solve = res.ms;
 	csr->stats.kernel_launches = res.launches;
 	csr->stats.h2d_bytes = n * sizeof(double);

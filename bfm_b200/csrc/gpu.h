@@ -99,7 +99,7 @@ typedef struct {
 	int32_t max_iter;
 	int32_t chunk;       /* iterations enqueued between two convergence polls */
 	int32_t verify;      /* recompute the true residual b - A x at the end and report it */
-	double true_tol;     /* a true residual above this fails the solve (after max_restarts residual replacements) */
+	double true_tol;     /* a normwise backward error above this fails the solve (after max_restarts residual replacements) */
 	int32_t max_restarts;
 } bfmg_pcg_opts_t;
 
@@ -109,6 +109,7 @@ typedef struct {
 	int32_t restarts;
 	double rel_residual;      /* recursive residual, scaled norm */
 	double true_rel_residual; /* ||b - A x|| / ||b||, scaled norm (NaN if not verified) */
+	double backward_error;    /* ||b - A x|| / (||x|| + ||b||), scaled norm, ||A^|| taken as 1 (NaN if not verified) */
 	float ms;
 	size_t launches;
 } bfmg_pcg_result_t;

@@ -37,6 +37,21 @@ static inline int bfmg_grid(int64_t work_items_per_block_units, int ctas_per_sm)
 	return (int) (g < 1 ? 1 : g);
 }
 
+/* resident CTAs of `kernel` per SM at kBlock threads: grids are sized to exactly one full wave
+ * (SMs x resident CTAs) so that grid-stride loops split the work evenly - 8 CTAs/SM of a kernel that
+ * fits only 6 would run as 1.33 waves with a 1/3-occupied tail (seen in the first ncu capture) */
+template <typename Kernel>
+static inline int bfmg_resident_ctas(Kernel kernel) {
+	int n = 0;
+
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kBlock, 0) != cudaSuccess || n < 1) {
+		cudaGetLastError();
+		n = 1;
+	}
+
+	return n;
+}
+
 /* streaming 16-byte loads that do not pollute L1 (matrix values and column indices are read once per
  * SpMV; L1 is kept for the gathered vector) */
 __device__ __forceinline__ double2 ld_stream(double2 const* p) {

@@ -822,12 +822,13 @@ int bfmx_job_solve(bfmx_job_t* job) {
 	job->stats.cg_converged = res.converged;
 	job->stats.cg_rel_residual = res.rel_residual;
 	job->stats.cg_true_rel_residual = res.true_rel_residual;
+	job->stats.cg_backward_error = res.backward_error;
 	job->stats.ms_solve = res.ms;
 	job->stats.kernel_launches += res.launches;
 	job->solved = true;
 
 	if (res.converged != 1) {
-		return BFMI_FAIL(job->state, "PCG stopped after %d iterations without converging (relative residual %.3e, true %.3e)", res.iterations, res.rel_residual, res.true_rel_residual);
+		return BFMI_FAIL(job->state, "PCG stopped after %d iterations without converging (relative residual %.3e, recomputed %.3e, backward error %.3e)", res.iterations, res.rel_residual, res.true_rel_residual, res.backward_error);
 	}
 
 	return 0;

@@ -34,6 +34,7 @@ struct Scalars {
 	double bnorm2;  /* ||b^||^2 */
 	double tol2;
 	double sum;     /* scratch result of the latest reduction */
+	double sum2;    /* second scratch result (||x^||^2 of the verification pass) */
 	int32_t iter;
 	int32_t max_iter;
 	int32_t done;   /* 0 running, 1 converged, 2 breakdown, 3 iteration limit */
@@ -362,6 +363,22 @@ __global__ void k_unscale(int n2, double2 const* __restrict__ dscale, double2 co
 	}
 }
 
+/* S->sum2 = ||v||^2 (verification pass only) */
+__global__ void __launch_bounds__(kBlock) k_norm2(int n2, double2 const* __restrict__ v, double* __restrict__ partials, Scalars* S) {
+	double acc = 0;
+
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+		double2 const a = v[i];
+		acc = fma(a.x, a.x, fma(a.y, a.y, acc));
+	}
+
+	double total;
+
+	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
+		S->sum2 = total;
+	}
+}
+
 struct Grids {
 	int spmv;
 	int vec;
@@ -370,9 +387,9 @@ struct Grids {
 Grids grids_for(bfmg_pattern_t const* pat) {
 	Grids g;
 
-	/* persistent-style: at most 8 CTAs of 256 threads per SM (= 2048 threads, full occupancy) */
-	g.spmv = bfmg_grid((pat->n_slices + kWarpsPerBlock - 1) / kWarpsPerBlock, 8);
-	g.vec = bfmg_grid(((int64_t) pat->nb + kBlock - 1) / kBlock, 8);
+	/* persistent-style: exactly one wave of resident CTAs, grid-stride loops inside */
+	g.spmv = bfmg_grid((pat->n_slices + kWarpsPerBlock - 1) / kWarpsPerBlock, bfmg_resident_ctas(k_spmv<kDot>));
+	g.vec = bfmg_grid(((int64_t) pat->nb + kBlock - 1) / kBlock, bfmg_resident_ctas(k_update_xr));
 
 	return g;
 }
@@ -388,6 +405,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 	*res = bfmg_pcg_result_t {};
 	res->true_rel_residual = NAN;
+	res->backward_error = NAN;
 
 	int const nb = pat->nb;
 	size_t const launches_before = bfmg_launch_count();
@@ -513,7 +531,10 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 			/* true residual b^ - A^ x^ into q, its squared norm into S->sum */
 
-			if (BFMG_LAUNCH(k_spmv<kResidual>, G.spmv, kBlock, 0, *pat, stop, sbot, xhat, q, bhat, partials, S) < 0) {
+			if (
+				BFMG_LAUNCH(k_spmv<kResidual>, G.spmv, kBlock, 0, *pat, stop, sbot, xhat, q, bhat, partials, S) < 0 ||
+				BFMG_LAUNCH(k_norm2, G.vec, kBlock, 0, nb, xhat, partials, S) < 0
+			) {
 				goto out;
 			}
 
@@ -528,10 +549,16 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 			res->true_rel_residual = sqrt(now.sum / now.bnorm2);
 
-			/* In FP64 the true residual cannot follow the recursion below ~eps * cond(A^): it is reported,
-			 * and only a drift beyond opts->true_tol - or an explicit restart budget - changes the outcome. */
+			/* In FP64 the recomputed residual cannot follow the recursion below ~eps * ||A^|| ||x^||, and on
+			 * these ill-conditioned plates ||x^|| / ||b^|| is ~cond(A^): 1e-8 at 80 k DOF, 5e-6 at 8 M DOF
+			 * (measured), for ANY backward-stable solver, the reference's LU included.  What a converged
+			 * solve must satisfy is a small normwise backward error
+			 *     eta = ||b^ - A^ x^|| / (||A^|| ||x^|| + ||b^||),   ||A^||_2 >= 1 (unit diagonal),
+			 * so eta is bounded with ||A^|| = 1; that is what opts->true_tol limits.  Both are reported. */
 
-			bool const drifted = res->true_rel_residual > opts->true_tol;
+			res->backward_error = sqrt(now.sum) / (sqrt(now.sum2) + sqrt(now.bnorm2));
+
+			bool const drifted = res->backward_error > opts->true_tol;
 
 			if (last.done != 1 || !drifted || restarts >= opts->max_restarts || last.iter >= opts->max_iter) {
 				if (last.done == 1 && drifted) {

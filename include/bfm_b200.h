@@ -58,6 +58,15 @@ typedef struct {
 	size_t kernel_launches;
 	size_t h2d_bytes;
 	size_t d2h_bytes;
+
+	/* recomputed ||b - A x|| / (||x|| + ||b||) in the Jacobi-scaled norm (||A^|| >= 1 taken as 1): the
+	 * normwise backward error, which is what FP64 can guarantee on an ill-conditioned system */
+	double cg_backward_error;
+
+	/* multi-GPU runs (bfmx_dist_init): this rank's share; n_dofs stays the global size */
+	size_t n_dofs_owned;
+	size_t n_ranks;
+	size_t halo_bytes_per_exchange;
 } bfmx_stats_t;
 
 /* stats of the most recent bfm_sim_run instance / bfm_matrix_solve / job stage in this process */
