@@ -162,6 +162,17 @@ void bfmg_count_launch(size_t n) {
 	G.launches += n;
 }
 
+void bfmg_set_error(char const* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(G.err, sizeof G.err, fmt, ap);
+	va_end(ap);
+}
+
+int bfmg_device() {
+	return G.device;
+}
+
 int bfmg_check(cudaError_t rc, char const* what, char const* file, int line) {
 	if (rc == cudaSuccess) {
 		return 0;

@@ -51,7 +51,41 @@ typedef struct {
 	int32_t* ctr_ptr;
 	uint32_t* ctr;
 	int32_t* elems;
+
+	/* block rows the solver works on: [0, nb) on one GPU, the owned range of a partition otherwise
+	 * (rows outside it are ghosts: gathered from, never computed) */
+	int32_t row_lo, row_hi;
 } bfmg_pattern_t;
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink (dist.cu) ------------------------------------ */
+
+#define BFMG_DIST_ID_BYTES 128
+#define BFMG_DIST_MAX_RANKS 16
+
+int bfmg_dist_unique_id(void* id);                       /* BFMG_DIST_ID_BYTES bytes, made on one rank */
+int bfmg_dist_init(int rank, int world, void const* id); /* collective over all ranks */
+int bfmg_dist_finalize(void);
+int bfmg_dist_world(void);                               /* 1 until bfmg_dist_init */
+int bfmg_dist_rank(void);
+size_t bfmg_dist_collectives(void);                      /* NCCL operations enqueued so far */
+
+/* halo plan of one rank (partition.c); arrays are host memory except d_send_idx */
+typedef struct {
+	int32_t n_nbr;
+	int32_t const* nbr;        /* neighbour ranks, ascending */
+	int32_t const* recv_begin; /* first ghost (local block row) owned by each neighbour */
+	int32_t const* recv_count;
+	int32_t const* send_ptr;   /* [n_nbr + 1] bounds in the packed send buffer */
+	int32_t n_send;
+	int32_t const* d_send_idx; /* device: local block rows to pack, grouped by neighbour */
+} bfmg_halo_t;
+
+/* refresh the ghost entries of d_vec (one double2 per local block row); d_sendbuf holds n_send double2 */
+int bfmg_dist_halo(bfmg_halo_t const* halo, double* d_vec, double* d_sendbuf);
+/* d_recv[world * count] = every rank's d_send[count], in rank order (a plain copy on one rank) */
+int bfmg_dist_allgather_f64(double const* d_send, double* d_recv, int count);
+/* d_global[2 * first_node[r] ...] = rank r's d_owned, for every r (first_node has world + 1 entries) */
+int bfmg_dist_gather_blocks(double const* d_owned, size_t const* first_node, double* d_global);
 
 /* ---- assembly -------------------------------------------------------------------------------- */
 
@@ -114,8 +148,10 @@ typedef struct {
 	size_t launches;
 } bfmg_pcg_result_t;
 
-/* solves A x = b; d_val is left untouched (a scaled copy is made) */
-int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res);
+/* solves A x = b over the rows [pat->row_lo, pat->row_hi); d_val is left untouched (a scaled copy is
+ * made).  halo = NULL on one GPU; otherwise the vectors are local (owned + ghost rows), every rank
+ * calls this collectively and d_x receives the owned rows (ghost rows of d_x are not meaningful) */
+int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res, bfmg_halo_t const* halo);
 
 /* times `reps` back-to-back launches of the CG SpMV kernel (q = A p with the fused dot) on d_val */
 int bfmg_spmv_time(bfmg_pattern_t const* pat, double const* d_val, int reps, float* ms_per_launch);

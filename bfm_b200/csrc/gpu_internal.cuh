@@ -18,6 +18,8 @@ BFMG_HIDDEN void bfmg_count_launch(size_t n);
 BFMG_HIDDEN void* bfmg_pinned();               /* 4 KiB page-locked scratch */
 BFMG_HIDDEN cudaEvent_t bfmg_poll_event(int i); /* two untimed events */
 BFMG_HIDDEN int bfmg_check(cudaError_t rc, char const* what, char const* file, int line);
+BFMG_HIDDEN void bfmg_set_error(char const* fmt, ...);
+BFMG_HIDDEN int bfmg_device();
 
 #define BFMG_CHECK(call) bfmg_check((call), #call, __FILE__, __LINE__)
 

@@ -68,6 +68,47 @@ BFMI_HIDDEN int bfmi_plan_upload(bfm_state_t* state, bfmi_plan_t* plan);
 BFMI_HIDDEN int64_t bfmi_plan_find(bfmi_plan_t const* plan, int32_t a, int32_t b);
 
 /* ---------------------------------------------------------------------------------------------
+ * row partition of a mesh over the ranks of a multi-GPU job (partition.c)
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct bfmi_part {
+	int refs;
+
+	bfm_mesh_t const* global;
+	size_t n_nodes, n_elems;
+	uint64_t hash;
+	int rank, world;
+
+	size_t lo, hi;        /* owned global nodes [lo, hi) */
+	int32_t n_local;      /* owned + ghost nodes */
+	int32_t own_begin;    /* local ids [own_begin, own_end) are the owned nodes, in global order */
+	int32_t own_end;
+	size_t* l2g;          /* [n_local] local -> global node, ascending */
+	size_t* elem_l2g;     /* [local.n_elems] local -> global element, ascending */
+
+	bfm_mesh_t local;     /* coordinates + connectivity in local ids (no edges, no domains) */
+
+	int32_t n_nbr;
+	int32_t* nbr;         /* neighbour ranks, ascending */
+	int32_t* recv_begin;  /* per neighbour: its ghosts are local ids [recv_begin, recv_begin + recv_count) */
+	int32_t* recv_count;
+	int32_t* send_ptr;    /* [n_nbr + 1] */
+	int32_t n_send;
+	int32_t* send_idx;    /* [n_send] owned local ids each neighbour ghosts, ascending per neighbour */
+
+	int32_t* d_send_idx;  /* device mirror (uploaded by the job) */
+} bfmi_part_t;
+
+BFMI_HIDDEN size_t bfmi_part_first_node(size_t n_nodes, int world, int rank);
+BFMI_HIDDEN int bfmi_part_owner(size_t n_nodes, int world, size_t node);
+BFMI_HIDDEN int32_t bfmi_part_local(bfmi_part_t const* part, size_t global_node); /* -1 when not local */
+BFMI_HIDDEN bfmi_part_t* bfmi_part_build(bfm_state_t* state, bfm_mesh_t const* mesh, int rank, int world);
+BFMI_HIDDEN bfmi_part_t* bfmi_part_for_mesh(bfm_state_t* state, bfm_mesh_t const* mesh, uint64_t hash, int rank, int world); /* cached, retained */
+BFMI_HIDDEN void bfmi_part_release(bfmi_part_t* part);
+BFMI_HIDDEN void bfmi_part_forget(bfm_mesh_t const* mesh);
+BFMI_HIDDEN uint64_t bfmi_mesh_hash(bfm_mesh_t const* mesh);
+
+/* ---------------------------------------------------------------------------------------------
  * BFM_MATRIX_KIND_CSR implementation object (matrix->csr.impl)
  * ------------------------------------------------------------------------------------------- */
 

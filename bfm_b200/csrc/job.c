@@ -52,9 +52,14 @@ struct bfmx_job {
 	bfm_state_t* state;
 	bfm_sim_kind_t kind;
 	bfm_instance_t* instance;
-	bfm_mesh_t* mesh;
+	bfm_mesh_t const* gmesh; /* the instance's mesh (global numbering) */
+	bfm_mesh_t const* mesh;  /* what this rank assembles: gmesh, or the local mesh of its partition */
 
-	bfmi_plan_t* plan;
+	bfmi_part_t* part;       /* NULL on one GPU */
+	bfmi_plan_t* plan;       /* of `mesh` */
+	bfmg_pattern_t pat;      /* plan->dev with the owned row range */
+	bfmg_halo_t halo;
+	double* d_xg;            /* multi-GPU: the gathered global solution */
 	bfmg_asm_tables_t tab;
 
 	double* h_nforce; /* [n_forces][nb][2], FUNKY forces sampled at the nodes */
@@ -111,6 +116,26 @@ size_t bfmx_kernel_launches(void) {
 
 int bfmx_device_sm_count(void) {
 	return bfmg_sm_count();
+}
+
+int bfmx_dist_unique_id(void* id) {
+	return bfmg_dist_unique_id(id);
+}
+
+int bfmx_dist_init(int rank, int world, void const* id) {
+	return bfmg_dist_init(rank, world, id);
+}
+
+int bfmx_dist_finalize(void) {
+	return bfmg_dist_finalize();
+}
+
+int bfmx_dist_rank(void) {
+	return bfmg_dist_rank();
+}
+
+int bfmx_dist_world(void) {
+	return bfmg_dist_world();
 }
 
 static double now_ms(void) {
@@ -303,7 +328,7 @@ static int affected_rows(bfmi_plan_t const* plan, bc_op_t* op) {
 
 /* apply_dirichlet (system.c:376-386) */
 static int op_dirichlet_xy(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t* op) {
-	size_t const nn = job->mesh->n_nodes;
+	size_t const nn = job->gmesh->n_nodes;
 	int32_t const shift = cond->kind == BFM_CONDITION_KIND_DIRICHLET_X ? 0 : 1;
 	size_t count = 0;
 
@@ -326,13 +351,13 @@ static int op_dirichlet_xy(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t
 		}
 	}
 
-	return affected_rows(job->plan, op);
+	return 0;
 }
 
 /* apply_dirichlet_normal_tangent (system.c:388-425): tangent = sum over the node's boundary edges, in
  * edge order, of (x_i - x_other) / length / 2; pow(d, 2) is d * d, as gcc -O2 compiles it */
 static int op_dirichlet_nt(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t* op) {
-	bfm_mesh_t const* const mesh = job->mesh;
+	bfm_mesh_t const* const mesh = job->gmesh;
 	size_t const nn = mesh->n_nodes;
 	bool const tangent = cond->kind == BFM_CONDITION_KIND_DIRICHLET_TANGENT;
 
@@ -399,7 +424,7 @@ static int op_dirichlet_nt(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t
 	free(tx);
 	free(ty);
 
-	return affected_rows(job->plan, op);
+	return 0;
 }
 
 typedef struct {
@@ -422,7 +447,7 @@ static int cmp_pending(void const* a, void const* b) {
 /* Neumann loads (system.c:477-522; axisymmetric weighting :586-617): every mesh edge with both end
  * nodes in the mask adds to the right-hand side, in edge order */
 static int op_neumann(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t* op) {
-	bfm_mesh_t const* const mesh = job->mesh;
+	bfm_mesh_t const* const mesh = job->gmesh;
 	bool const axisym = job->kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN;
 	bool const xy = cond->kind == BFM_CONDITION_KIND_NEUMANN_X || cond->kind == BFM_CONDITION_KIND_NEUMANN_Y;
 
@@ -506,6 +531,55 @@ static int op_neumann(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t* op)
 	return 0;
 }
 
+/* Multi-GPU: the lists above are in global DOF numbers; keep the DOFs of local nodes (owned and ghost -
+ * a ghost column's Dirichlet value feeds the owned rows' right-hand side) and renumber them.  The local
+ * numbering is monotone in the global one, so ascending order - the reference's application order - holds. */
+static void localize_op(bfmi_part_t const* part, bc_op_t* op) {
+	if (op->kind == OP_DIRICHLET) {
+		int32_t kept = 0;
+
+		for (int32_t i = 0; i < op->n_dofs; i++) {
+			int32_t const l = bfmi_part_local(part, (size_t) op->dofs[i] / 2);
+
+			if (l >= 0) {
+				op->dofs[kept] = 2 * l + op->dofs[i] % 2;
+				op->vals[kept++] = op->vals[i];
+			}
+		}
+
+		op->n_dofs = kept;
+		return;
+	}
+
+	/* right-hand-side additions: only owned rows matter */
+
+	int32_t kept_groups = 0;
+	int32_t kept_adds = 0;
+
+	for (int32_t g = 0; g < op->n_groups; g++) {
+		int32_t const l = bfmi_part_local(part, (size_t) op->group_dof[g] / 2);
+		int32_t const beg = op->group_ptr[g];
+		int32_t const end = op->group_ptr[g + 1];
+
+		if (l < part->own_begin || l >= part->own_end) {
+			continue;
+		}
+
+		op->group_dof[kept_groups] = 2 * l + op->group_dof[g] % 2;
+		op->group_ptr[kept_groups++] = kept_adds;
+
+		for (int32_t t = beg; t < end; t++) {
+			op->add[kept_adds++] = op->add[t];
+		}
+	}
+
+	if (op->n_groups > 0) {
+		op->group_ptr[kept_groups] = kept_adds;
+	}
+
+	op->n_groups = kept_groups;
+}
+
 static int build_ops(bfmx_job_t* job) {
 	bfm_instance_t const* const instance = job->instance;
 	bool const axisym = job->kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN;
@@ -554,6 +628,14 @@ static int build_ops(bfmx_job_t* job) {
 			return -1;
 		}
 
+		if (job->part != NULL) {
+			localize_op(job->part, op);
+		}
+
+		if (op->kind == OP_DIRICHLET && affected_rows(job->plan, op) < 0) {
+			return -1;
+		}
+
 		job->n_ops++;
 	}
 
@@ -562,7 +644,7 @@ static int build_ops(bfmx_job_t* job) {
 
 /* ---- job life cycle -------------------------------------------------------------------------------- */
 
-static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind, bfm_instance_t* instance, size_t n_forces, bfm_force_t** forces) {
+static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind, bfm_instance_t* instance, size_t n_forces, bfm_force_t** forces, bool partitioned) {
 	bfm_mesh_t* const mesh = instance->obj->mesh;
 
 	*out = NULL;
@@ -588,11 +670,24 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 	job->state = state;
 	job->kind = kind;
 	job->instance = instance;
+	job->gmesh = mesh;
 	job->mesh = mesh;
 
 	double const t0 = now_ms();
 
-	job->plan = bfmi_plan_for_mesh(state, mesh);
+	/* several GPUs: this rank assembles and solves the local mesh of its row block (partition.c) */
+
+	if (partitioned && bfmg_dist_world() > 1) {
+		job->part = bfmi_part_for_mesh(state, mesh, bfmi_mesh_hash(mesh), bfmg_dist_rank(), bfmg_dist_world());
+
+		if (job->part == NULL) {
+			goto fail;
+		}
+
+		job->mesh = &job->part->local;
+	}
+
+	job->plan = bfmi_plan_for_mesh(state, job->mesh);
 
 	if (job->plan == NULL) {
 		goto fail;
@@ -615,6 +710,37 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 	}
 
 	size_t const nb = (size_t) job->plan->nb;
+
+	job->pat = job->plan->dev;
+
+	if (job->part != NULL) {
+		bfmi_part_t* const part = job->part;
+
+		job->pat.row_lo = part->own_begin;
+		job->pat.row_hi = part->own_end;
+
+		if (part->d_send_idx == NULL && part->n_send > 0) {
+			if (bfmg_alloc((void**) &part->d_send_idx, (size_t) part->n_send * sizeof(int32_t)) < 0 || bfmg_upload(part->d_send_idx, part->send_idx, (size_t) part->n_send * sizeof(int32_t)) < 0) {
+				BFMI_FAIL(state, "uploading the halo plan failed: %s", bfmg_last_error());
+				goto fail;
+			}
+
+			job->stats.h2d_bytes += (size_t) part->n_send * sizeof(int32_t);
+		}
+
+		job->halo.n_nbr = part->n_nbr;
+		job->halo.nbr = part->nbr;
+		job->halo.recv_begin = part->recv_begin;
+		job->halo.recv_count = part->recv_count;
+		job->halo.send_ptr = part->send_ptr;
+		job->halo.n_send = part->n_send;
+		job->halo.d_send_idx = part->d_send_idx;
+
+		if (bfmg_alloc((void**) &job->d_xg, mesh->n_nodes * 2 * sizeof(double)) < 0) {
+			BFMI_FAIL(state, "device allocation failed: %s", bfmg_last_error());
+			goto fail;
+		}
+	}
 
 	if (
 		bfmg_alloc((void**) &job->d_coords, nb * 2 * sizeof(double)) < 0 ||
@@ -658,7 +784,10 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 		goto fail;
 	}
 
-	job->stats.n_dofs = 2 * nb;
+	job->stats.n_dofs = 2 * mesh->n_nodes;
+	job->stats.n_dofs_owned = 2 * (size_t) (job->pat.row_hi - job->pat.row_lo);
+	job->stats.n_ranks = job->part != NULL ? (size_t) job->part->world : 1;
+	job->stats.halo_bytes_per_exchange = job->part != NULL ? (size_t) job->part->n_send * 16 : 0;
 	job->stats.n_blocks = (size_t) job->plan->n_blocks;
 	job->stats.n_slots = (size_t) job->plan->n_slots;
 
@@ -676,7 +805,7 @@ int bfmx_job_create(bfmx_job_t** job, bfm_sim_t* sim, size_t instance_index) {
 		return -1;
 	}
 
-	return job_create(job, sim->state, sim->kind, sim->instances[instance_index], sim->n_forces, sim->forces);
+	return job_create(job, sim->state, sim->kind, sim->instances[instance_index], sim->n_forces, sim->forces, true);
 }
 
 int bfmx_job_destroy(bfmx_job_t* job) {
@@ -704,8 +833,10 @@ int bfmx_job_destroy(bfmx_job_t* job) {
 	bfmg_free(job->d_x);
 	bfmg_free(job->d_stamp);
 	bfmg_free(job->d_cval);
+	bfmg_free(job->d_xg);
 
 	bfmi_plan_release(job->plan);
+	bfmi_part_release(job->part);
 	free(job);
 
 	return 0;
@@ -813,7 +944,7 @@ int bfmx_job_solve(bfmx_job_t* job) {
 
 	bfmi_pcg_options(job->stats.n_dofs, &opts);
 
-	if (bfmg_pcg(&job->plan->dev, job->d_val, job->d_b, job->d_x, &opts, &res) < 0) {
+	if (bfmg_pcg(&job->pat, job->d_val, job->d_b, job->d_x, &opts, &res, job->part != NULL ? &job->halo : NULL) < 0) {
 		return BFMI_FAIL(job->state, "PCG failed: %s", bfmg_last_error());
 	}
 
@@ -841,10 +972,28 @@ int bfmx_job_download(bfmx_job_t* job) {
 
 	size_t const bytes = job->stats.n_dofs * sizeof(double);
 	int const t0 = bfmg_tick();
+	double const* d_src = job->d_x;
+
+	/* several GPUs: every rank receives every owned block, so that each process ends with the complete
+	 * field, exactly as a single-process caller of the reference does */
+
+	if (job->part != NULL) {
+		size_t first[BFMG_DIST_MAX_RANKS + 1];
+
+		for (int r = 0; r <= job->part->world; r++) {
+			first[r] = bfmi_part_first_node(job->part->n_nodes, job->part->world, r);
+		}
+
+		if (bfmg_dist_gather_blocks(job->d_x + 2 * (size_t) job->part->own_begin, first, job->d_xg) < 0) {
+			return BFMI_FAIL(job->state, "gathering the displacements failed: %s", bfmg_last_error());
+		}
+
+		d_src = job->d_xg;
+	}
 
 	/* effects[node * dim + k] = x[node * dim + k] (sim.c:127-131): same interleaving, one copy */
 
-	if (bfmg_download(job->instance->effects, job->d_x, bytes) < 0) {
+	if (bfmg_download(job->instance->effects, d_src, bytes) < 0) {
 		return BFMI_FAIL(job->state, "download failed: %s", bfmg_last_error());
 	}
 
@@ -866,11 +1015,11 @@ int bfmx_job_spmv_time(bfmx_job_t* job, int reps, float* ms_per_launch) {
 		return -1;
 	}
 
-	return bfmg_spmv_time(&job->plan->dev, job->d_val, reps, ms_per_launch);
+	return bfmg_spmv_time(&job->pat, job->d_val, reps, ms_per_launch);
 }
 
 int bfmx_job_read(bfmx_job_t* job, double* b, double* x) {
-	size_t const bytes = job->stats.n_dofs * sizeof(double);
+	size_t const bytes = (size_t) job->plan->nb * 2 * sizeof(double); /* local rows on a partitioned job */
 
 	if (b != NULL && (!job->assembled || bfmg_download(b, job->d_b, bytes) < 0)) {
 		return -1;
@@ -951,7 +1100,7 @@ static int system_create_gpu(bfm_system_t* system, bfm_sim_kind_t kind, bfm_inst
 	bfm_state_t* const state = instance->state;
 	bfmx_job_t* job;
 
-	if (job_create(&job, state, kind, instance, n_forces, forces) < 0) {
+	if (job_create(&job, state, kind, instance, n_forces, forces, false) < 0) { /* the staged API is single-GPU */
 		return -1;
 	}
 

@@ -28,6 +28,7 @@ int bfm_mesh_destroy(bfm_mesh_t* mesh) {
 	bfm_state_t* const state = mesh->state;
 
 	bfmi_plan_forget(mesh); /* drop any cached symbolic plan keyed on this mesh */
+	bfmi_part_forget(mesh); /* ... and its row partition */
 
 	state->free(mesh->coords);
 	state->free(mesh->elems);

@@ -66,6 +66,10 @@ static uint64_t hash_elems(size_t const* elems, size_t count) {
 	return total;
 }
 
+uint64_t bfmi_mesh_hash(bfm_mesh_t const* mesh) {
+	return hash_elems(mesh->elems, mesh->n_elems * mesh->kind);
+}
+
 static void plan_free(bfmi_plan_t* plan) {
 	if (plan->on_device) {
 		bfmg_free(plan->dev.slice_off);
@@ -532,6 +536,8 @@ int bfmi_plan_upload(bfm_state_t* state, bfmi_plan_t* plan) {
 	d->n_slices = plan->n_slices;
 	d->n_slots = plan->n_slots;
 	d->kind = plan->kind;
+	d->row_lo = 0;
+	d->row_hi = plan->nb;
 
 	plan->on_device = true; /* from here on plan_free releases whatever was allocated */
 

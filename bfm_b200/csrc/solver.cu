@@ -14,6 +14,12 @@
  * the convergence flag is set the remaining launches of a chunk return immediately, and the host
  * polls the flag one chunk behind the launch front, so the GPU never idles on the poll.
  *
+ * Multi-GPU (halo != NULL): the same three kernels work on the owned block rows of a partition
+ * (pat->row_lo .. row_hi); the ghost entries of p are refreshed before every SpMV (dist.cu), and each
+ * reducing kernel leaves its partial in S->part, which an all-gather spreads to every rank; a one-thread
+ * kernel then folds the world's partials in rank order and applies the same scalar update as the last
+ * CTA does on one GPU.  Every rank computes bit-identical scalars, so all ranks stop together.
+ *
  * All three kernels are HBM-bound (FP64 SpMV ~ 0.25 flop/B): no tensor cores.  Algorithmic bytes per
  * block row (node) and iteration, structured P1 plate (7 blocks per row):
  *   k_spmv_dot  7 * (32 + 4) + 16 (p) + 16 (q)        = 284 B   (canonical CSR figure: 2 * 188 = 376 B)
@@ -39,7 +45,92 @@ struct Scalars {
 	int32_t max_iter;
 	int32_t done;   /* 0 running, 1 converged, 2 breakdown, 3 iteration limit */
 	uint32_t ticket;
+	int32_t world;  /* ranks sharing the solve; > 1: reductions finish in k_fold */
+	int32_t pad;
+	double part;                       /* this rank's share of the reduction in flight */
+	double gath[BFMG_DIST_MAX_RANKS];  /* every rank's share, in rank order */
 };
+
+/* ---- what happens once a reduction is complete (last CTA on one GPU, k_fold on several) ------------ */
+
+enum Fold { kFoldInit, kFoldPq, kFoldRr, kFoldResidual, kFoldNorm2 };
+
+template <Fold WHAT>
+__device__ __forceinline__ void fold(Scalars* S, double total) {
+	if (WHAT == kFoldInit) {
+		S->rho = total;
+		S->bnorm2 = total;
+		S->alpha = 0;
+		S->beta = 0;
+		S->iter = 0;
+		S->done = (total == 0 || !(total == total)) ? (total == 0 ? 1 : 2) : 0;
+	}
+
+	else if (WHAT == kFoldPq) {
+		if (total == 0 || !(total == total) || isinf(total)) {
+			S->done = 2;
+			S->alpha = 0;
+		}
+
+		else {
+			S->alpha = S->rho / total;
+		}
+	}
+
+	else if (WHAT == kFoldRr) {
+		S->beta = total / S->rho;
+		S->rho = total;
+		S->iter++;
+
+		if (!(total == total)) {
+			S->done = 2;
+		}
+
+		else if (total <= S->tol2 * S->bnorm2) {
+			S->done = 1;
+		}
+
+		else if (S->iter >= S->max_iter) {
+			S->done = 3;
+		}
+	}
+
+	else if (WHAT == kFoldResidual) {
+		S->sum = total;
+	}
+
+	else {
+		S->sum2 = total;
+	}
+}
+
+/* thread 0 of the last CTA: finish here (one GPU) or publish this rank's share (several) */
+template <Fold WHAT>
+__device__ __forceinline__ void reduced(Scalars* S, double total) {
+	if (S->world > 1) {
+		S->part = total;
+	}
+
+	else {
+		fold<WHAT>(S, total);
+	}
+}
+
+/* several GPUs: S->gath holds every rank's share; fold them in rank order - same bits on every rank */
+template <Fold WHAT>
+__global__ void k_fold(Scalars* S) {
+	if ((WHAT == kFoldPq || WHAT == kFoldRr) && S->done) {
+		return;
+	}
+
+	double total = 0;
+
+	for (int r = 0; r < S->world; r++) {
+		total += S->gath[r];
+	}
+
+	fold<WHAT>(S, total);
+}
 
 /* CTA-level sum; every thread calls it.  Returns true in ALL threads of the last CTA of the grid to
  * arrive, in which case *total (thread 0 only) holds the grid-wide sum folded in a fixed order. */
@@ -140,7 +231,7 @@ __global__ void k_scale_matrix(const __grid_constant__ bfmg_pattern_t P, double2
 	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
 	int const n_warps = gridDim.x * blockDim.x / kWarp;
 
-	for (int slice = warp; slice < P.n_slices; slice += n_warps) {
+	for (int slice = P.row_lo / kWarp + warp; slice < (P.row_hi + kWarp - 1) / kWarp; slice += n_warps) {
 		int const row = slice * kWarp + lane;
 		double2 const sr = row < P.nb ? dscale[row] : make_double2(0, 0);
 		int const end = P.slice_off[slice + 1];
@@ -173,14 +264,9 @@ __global__ void __launch_bounds__(kBlock) k_cg_init(int n2, double2 const* __res
 	double total;
 
 	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
-		S->rho = total;
-		S->bnorm2 = total;
 		S->tol2 = tol * tol;
-		S->alpha = 0;
-		S->beta = 0;
-		S->iter = 0;
 		S->max_iter = max_iter;
-		S->done = (total == 0 || !(total == total)) ? (total == 0 ? 1 : 2) : 0;
+		reduced<kFoldInit>(S, total);
 	}
 }
 
@@ -207,7 +293,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv(
 
 	double acc = 0;
 
-	for (int slice = warp; slice < P.n_slices; slice += n_warps) {
+	for (int slice = P.row_lo / kWarp + warp; slice < (P.row_hi + kWarp - 1) / kWarp; slice += n_warps) {
 		int const row = slice * kWarp + lane;
 		int const beg = __ldg(&P.slice_off[slice]);
 		int const end = __ldg(&P.slice_off[slice + 1]);
@@ -225,7 +311,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv(
 			y1 = fma(u.x, xv.x, fma(u.y, xv.y, y1));
 		}
 
-		if (row < P.nb) {
+		if (row >= P.row_lo && row < P.row_hi) {
 			if (MODE == kDot) {
 				double2 const pr = __ldg(&p[row]);
 
@@ -256,18 +342,11 @@ __global__ void __launch_bounds__(kBlock) k_spmv(
 
 	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
 		if (MODE == kDot) {
-			if (total == 0 || !(total == total) || isinf(total)) {
-				S->done = 2;
-				S->alpha = 0;
-			}
-
-			else {
-				S->alpha = S->rho / total;
-			}
+			reduced<kFoldPq>(S, total);
 		}
 
 		else {
-			S->sum = total;
+			reduced<kFoldResidual>(S, total);
 		}
 	}
 }
@@ -301,21 +380,7 @@ __global__ void __launch_bounds__(kBlock) k_update_xr(int n2, double2 const* __r
 	double total;
 
 	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
-		S->beta = total / S->rho;
-		S->rho = total;
-		S->iter++;
-
-		if (!(total == total)) {
-			S->done = 2;
-		}
-
-		else if (total <= S->tol2 * S->bnorm2) {
-			S->done = 1;
-		}
-
-		else if (S->iter >= S->max_iter) {
-			S->done = 3;
-		}
+		reduced<kFoldRr>(S, total);
 	}
 }
 
@@ -375,7 +440,7 @@ __global__ void __launch_bounds__(kBlock) k_norm2(int n2, double2 const* __restr
 	double total;
 
 	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
-		S->sum2 = total;
+		reduced<kFoldNorm2>(S, total);
 	}
 }
 
@@ -388,8 +453,10 @@ Grids grids_for(bfmg_pattern_t const* pat) {
 	Grids g;
 
 	/* persistent-style: exactly one wave of resident CTAs, grid-stride loops inside */
-	g.spmv = bfmg_grid((pat->n_slices + kWarpsPerBlock - 1) / kWarpsPerBlock, bfmg_resident_ctas(k_spmv<kDot>));
-	g.vec = bfmg_grid(((int64_t) pat->nb + kBlock - 1) / kBlock, bfmg_resident_ctas(k_update_xr));
+	int const active_slices = (pat->row_hi + kWarp - 1) / kWarp - pat->row_lo / kWarp;
+
+	g.spmv = bfmg_grid((active_slices + kWarpsPerBlock - 1) / kWarpsPerBlock, bfmg_resident_ctas(k_spmv<kDot>));
+	g.vec = bfmg_grid(((int64_t) (pat->row_hi - pat->row_lo) + kBlock - 1) / kBlock, bfmg_resident_ctas(k_update_xr));
 
 	return g;
 }
@@ -398,7 +465,7 @@ Grids grids_for(bfmg_pattern_t const* pat) {
 
 extern "C" {
 
-int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res) {
+int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res, bfmg_halo_t const* halo) {
 	if (!bfmg_ready()) {
 		return -1;
 	}
@@ -407,10 +474,14 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	res->true_rel_residual = NAN;
 	res->backward_error = NAN;
 
-	int const nb = pat->nb;
+	int const nb = pat->nb;                      /* local block rows (owned + ghost) */
+	int const lo = pat->row_lo;
+	int const n_own = pat->row_hi - pat->row_lo; /* rows this rank solves for */
+	int const world = halo != nullptr ? bfmg_dist_world() : 1;
+	bool const shared = world > 1;
 	size_t const launches_before = bfmg_launch_count();
 
-	if (nb == 0) {
+	if (nb == 0 || (n_own == 0 && !shared)) {
 		res->converged = 1;
 		return 0;
 	}
@@ -418,15 +489,16 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	Grids const G = grids_for(pat);
 	int const max_grid = G.spmv > G.vec ? G.spmv : G.vec;
 
-	/* workspace: scaled matrix, 6 vectors of nb double2, partials, scalars */
+	/* workspace: scaled matrix, 6 vectors of nb double2, halo send buffer, partials, scalars */
 
-	double2 *stop = nullptr, *sbot, *dscale, *bhat, *xhat, *r, *p, *q;
+	double2 *stop = nullptr, *sbot, *dscale, *bhat, *xhat, *r, *p, *q, *sendbuf;
 	double* partials;
 	Scalars* S;
 
 	size_t const vec_bytes = (size_t) nb * sizeof(double2);
 	size_t const mat_bytes = (size_t) pat->n_slots * 2 * sizeof(double2);
-	size_t const total = mat_bytes + 6 * vec_bytes + (size_t) max_grid * sizeof(double) + sizeof(Scalars) + 256;
+	size_t const send_bytes = shared ? ((size_t) halo->n_send + 1) * sizeof(double2) : 0;
+	size_t const total = mat_bytes + 6 * vec_bytes + send_bytes + (size_t) max_grid * sizeof(double) + sizeof(Scalars) + 256;
 
 	void* ws = nullptr;
 
@@ -445,6 +517,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		r = (double2*) at, at += vec_bytes;
 		p = (double2*) at, at += vec_bytes;
 		q = (double2*) at, at += vec_bytes;
+		sendbuf = (double2*) at, at += send_bytes;
 		partials = (double*) at, at += (size_t) max_grid * sizeof(double);
 		at = (char*) (((uintptr_t) at + 127) & ~(uintptr_t) 127);
 		S = (Scalars*) at;
@@ -459,14 +532,32 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	Scalars* const h_S = (Scalars*) bfmg_pinned(); /* two slots, written by the status polls */
 	cudaEvent_t const polled[2] = {bfmg_poll_event(0), bfmg_poll_event(1)};
 
-	if (BFMG_CHECK(cudaMemsetAsync(S, 0, sizeof *S, bfmg_stream())) < 0) {
-		goto out;
+	static_assert(2 * sizeof(Scalars) <= 4096, "status polls use the 4 KiB pinned page");
+
+	/* several GPUs: spread S->part to every rank's S->gath, then fold (k_fold<WHAT>) */
+#define SHARE(WHAT) (!shared || (bfmg_dist_allgather_f64(&S->part, S->gath, 1) == 0 && BFMG_LAUNCH(k_fold<WHAT>, 1, 1, 0, S) == 0))
+#define HALO(vec) (!shared || bfmg_dist_halo(halo, (double*) (vec), (double*) sendbuf) == 0)
+
+	{
+		Scalars init = {};
+		init.world = world;
+
+		/* the vectors are zeroed so that ghost entries never hold NaN patterns before their first exchange */
+		if (
+			BFMG_CHECK(cudaMemcpyAsync(S, &init, sizeof init, cudaMemcpyHostToDevice, bfmg_stream())) < 0 ||
+			BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0 || /* `init` lives on this stack frame */
+			(shared && BFMG_CHECK(cudaMemsetAsync(dscale, 0, 6 * vec_bytes, bfmg_stream())) < 0)
+		) {
+			goto out;
+		}
 	}
 
 	if (
 		BFMG_LAUNCH(k_jacobi, (nb + kBlock - 1) / kBlock, kBlock, 0, *pat, vtop, vbot, (double2 const*) d_b, dscale, bhat) < 0 ||
+		!HALO(dscale) ||
 		BFMG_LAUNCH(k_scale_matrix, G.spmv, kBlock, 0, *pat, vtop, vbot, dscale, stop, sbot) < 0 ||
-		BFMG_LAUNCH(k_cg_init, G.vec, kBlock, 0, nb, bhat, xhat, r, p, partials, S, opts->tol, opts->max_iter) < 0
+		BFMG_LAUNCH(k_cg_init, G.vec, kBlock, 0, n_own, bhat + lo, xhat + lo, r + lo, p + lo, partials, S, opts->tol, opts->max_iter) < 0 ||
+		!SHARE(kFoldInit)
 	) {
 		goto out;
 	}
@@ -476,7 +567,9 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		int restarts = 0;
 
 		for (;;) {
-			/* enqueue chunks; poll the status one chunk behind the launch front */
+			/* enqueue chunks; poll the status one chunk behind the launch front.  The decision to enqueue
+			 * chunk c + 1 depends only on the status after chunk c - 1, which is bit-identical on every
+			 * rank - so all ranks enqueue the same sequence of collectives. */
 
 			int done = 0;
 			int launched_chunks = 0;
@@ -484,9 +577,12 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 			while (!done) {
 				for (int it = 0; it < chunk; it++) {
 					if (
+						!HALO(p) ||
 						BFMG_LAUNCH(k_spmv<kDot>, G.spmv, kBlock, 0, *pat, stop, sbot, p, q, bhat, partials, S) < 0 ||
-						BFMG_LAUNCH(k_update_xr, G.vec, kBlock, 0, nb, p, q, xhat, r, partials, S) < 0 ||
-						BFMG_LAUNCH(k_update_p, G.vec, kBlock, 0, nb, r, p, S) < 0
+						!SHARE(kFoldPq) ||
+						BFMG_LAUNCH(k_update_xr, G.vec, kBlock, 0, n_own, p + lo, q + lo, xhat + lo, r + lo, partials, S) < 0 ||
+						!SHARE(kFoldRr) ||
+						BFMG_LAUNCH(k_update_p, G.vec, kBlock, 0, n_own, r + lo, p + lo, S) < 0
 					) {
 						goto out;
 					}
@@ -529,11 +625,14 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 				break;
 			}
 
-			/* true residual b^ - A^ x^ into q, its squared norm into S->sum */
+			/* true residual b^ - A^ x^ into q, its squared norm into S->sum, ||x^||^2 into S->sum2 */
 
 			if (
+				!HALO(xhat) ||
 				BFMG_LAUNCH(k_spmv<kResidual>, G.spmv, kBlock, 0, *pat, stop, sbot, xhat, q, bhat, partials, S) < 0 ||
-				BFMG_LAUNCH(k_norm2, G.vec, kBlock, 0, nb, xhat, partials, S) < 0
+				!SHARE(kFoldResidual) ||
+				BFMG_LAUNCH(k_norm2, G.vec, kBlock, 0, n_own, xhat + lo, partials, S) < 0 ||
+				!SHARE(kFoldNorm2)
 			) {
 				goto out;
 			}
@@ -570,7 +669,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 			/* residual replacement: restart CG from the true residual */
 
-			if (BFMG_LAUNCH(k_restart, G.vec, kBlock, 0, nb, q, r, p, S) < 0) {
+			if (BFMG_LAUNCH(k_restart, G.vec, kBlock, 0, n_own, q + lo, r + lo, p + lo, S) < 0) {
 				goto out;
 			}
 
@@ -578,7 +677,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		}
 	}
 
-	if (BFMG_LAUNCH(k_unscale, (nb + kBlock - 1) / kBlock, kBlock, 0, nb, dscale, xhat, (double2*) d_x) < 0) {
+	if (n_own > 0 && BFMG_LAUNCH(k_unscale, (n_own + kBlock - 1) / kBlock, kBlock, 0, n_own, dscale + lo, xhat + lo, (double2*) d_x + lo) < 0) {
 		goto out;
 	}
 
@@ -591,6 +690,9 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	rv = 0;
 
 out:
+
+#undef SHARE
+#undef HALO
 
 	bfmg_free(ws);
 	return rv;

@@ -43,7 +43,20 @@ class Stats(C.Structure):  # bfmx_stats_t
 		return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class PartitionInfo(C.Structure):  # bfmx_partition_info_t
+	_fields_ = [(name, C.c_size_t) for name in ("first_node", "end_node", "n_local_nodes", "own_begin", "own_end", "n_local_elems", "n_neighbours", "n_send")]
+
+
+DIST_ID_BYTES = 128
+
 PROTOTYPES = {
+	"bfmx_dist_unique_id": (_int, [C.c_void_p]),
+	"bfmx_dist_init": (_int, [_int, _int, C.c_void_p]),
+	"bfmx_dist_finalize": (_int, []),
+	"bfmx_dist_rank": (_int, []),
+	"bfmx_dist_world": (_int, []),
+	"bfmx_partition_sizes": (_int, [_P(abi.Mesh), _int, _int, _P(PartitionInfo)]),
+	"bfmx_partition_copy": (_int, [_P(abi.Mesh), _int, _int, abi.c_size_t_p, abi.c_size_t_p, abi.c_size_t_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
 	"bfmx_device_available": (_int, []),
 	"bfmx_device_error": (C.c_char_p, []),
 	"bfmx_device_sync": (_int, []),
@@ -68,6 +81,57 @@ PROTOTYPES = {
 	"bfmx_matrix_csr_create": (_int, [_P(abi.Matrix), _P(abi.State), C.c_size_t, abi.c_size_t_p, abi.c_size_t_p, abi.c_double_p]),
 	"bfmx_matrix_csr_export": (_int, [_P(abi.Matrix), _P(C.c_size_t), abi.c_size_t_p, abi.c_size_t_p, abi.c_double_p]),
 }
+
+
+def dist_init(binding, dist, local_rank: int | None = None):
+	"""give the library its own NCCL communicator over the ranks of an initialised torch.distributed
+	process group (used only to ship the 128-byte unique id; the data path never touches torch)"""
+
+	rank, world = dist.get_rank(), dist.get_world_size()
+	ident = C.create_string_buffer(DIST_ID_BYTES)
+
+	if rank == 0:
+		assert not binding.lib.bfmx_dist_unique_id(ident), binding.lib.bfmx_device_error()
+
+	box = [ident.raw]
+	dist.broadcast_object_list(box, src=0)
+	ident = C.create_string_buffer(box[0], DIST_ID_BYTES)
+
+	assert not binding.lib.bfmx_dist_init(rank, world, ident), binding.lib.bfmx_device_error()
+
+
+def dist_finalize(binding):
+	binding.lib.bfmx_dist_finalize()
+
+
+def partition(mesh, rank: int, world: int) -> dict:
+	"""the row partition rank `rank` of `world` would get for `mesh` (host-only, see partition.c)"""
+
+	lib = mesh.binding.lib
+	info = PartitionInfo()
+	assert not lib.bfmx_partition_sizes(C.byref(mesh.c_mesh), rank, world, C.byref(info))
+
+	kind = mesh.c_mesh.kind
+	out = {
+		"l2g": np.zeros(info.n_local_nodes, np.uint64),
+		"elems": np.zeros((info.n_local_elems, kind), np.uint64),
+		"elem_l2g": np.zeros(info.n_local_elems, np.uint64),
+		"nbr": np.zeros(info.n_neighbours, np.int32),
+		"recv_begin": np.zeros(info.n_neighbours, np.int32),
+		"recv_count": np.zeros(info.n_neighbours, np.int32),
+		"send_ptr": np.zeros(info.n_neighbours + 1, np.int32),
+		"send_idx": np.zeros(max(info.n_send, 1), np.int32),
+	}
+
+	assert not lib.bfmx_partition_copy(
+		C.byref(mesh.c_mesh), rank, world,
+		out["l2g"].ctypes.data_as(abi.c_size_t_p), out["elems"].ctypes.data_as(abi.c_size_t_p), out["elem_l2g"].ctypes.data_as(abi.c_size_t_p),
+		*[out[k].ctypes.data_as(c_int32_p) for k in ("nbr", "recv_begin", "recv_count", "send_ptr", "send_idx")],
+	)
+
+	out["send_idx"] = out["send_idx"][:info.n_send]
+	out.update({name: getattr(info, name) for name, _ in PartitionInfo._fields_})
+	return out
 
 
 def csr_export(binding, c_matrix):

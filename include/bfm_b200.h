@@ -105,6 +105,35 @@ int bfmx_mesh_plate(bfm_mesh_t* mesh, bfm_state_t* state, size_t nx, size_t ny, 
 int bfmx_mesh_pattern_sizes(bfm_mesh_t* mesh, size_t* n_slices, size_t* n_slots, size_t* n_blocks, size_t* n_contributions);
 int bfmx_mesh_pattern_copy(bfm_mesh_t* mesh, int32_t* slice_off, int32_t* row_len, int32_t* scol, int32_t* diag_pos, int32_t* ctr_ptr, uint32_t* ctr);
 
+/* ---- multi-GPU: one process per GPU of one box ---------------------------------------------------------
+ *
+ * After bfmx_dist_init, bfm_sim_run and the bfmx_job_* stages become COLLECTIVE calls: every rank builds
+ * the same simulation (same mesh, conditions, forces - SPMD, like the ranks of a torchrun job), owns a
+ * contiguous block of node rows, assembles the elements touching them, and solves with the interface
+ * DOFs and the CG dot products exchanged over NVLink.  Every rank ends with the complete displacement
+ * field in instance->effects.  The staged bfm_system_* / bfm_matrix_* API stays single-GPU. */
+
+#define BFMX_DIST_ID_BYTES 128
+
+int bfmx_dist_unique_id(void* id);                       /* call on one rank, ship the bytes to the others */
+int bfmx_dist_init(int rank, int world, void const* id); /* collective */
+int bfmx_dist_finalize(void);
+int bfmx_dist_rank(void);
+int bfmx_dist_world(void);
+
+/* the row partition a mesh would get (host-only: works without a GPU) */
+typedef struct {
+	size_t first_node, end_node;   /* owned global nodes */
+	size_t n_local_nodes;          /* owned + ghost */
+	size_t own_begin, own_end;     /* owned nodes' local ids */
+	size_t n_local_elems;
+	size_t n_neighbours;
+	size_t n_send;
+} bfmx_partition_info_t;
+
+int bfmx_partition_sizes(bfm_mesh_t* mesh, int rank, int world, bfmx_partition_info_t* out);
+int bfmx_partition_copy(bfm_mesh_t* mesh, int rank, int world, size_t* local_to_global, size_t* local_elems, size_t* elem_to_global, int32_t* neighbours, int32_t* recv_begin, int32_t* recv_count, int32_t* send_ptr, int32_t* send_idx);
+
 /* ---- matrices ---------------------------------------------------------------------------------------- */
 
 /* CSR-kind matrix from a scalar CSR triple (n even: DOFs are paired into nodes); duplicates are summed.
