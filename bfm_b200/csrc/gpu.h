@@ -153,6 +153,26 @@ typedef struct {
  * calls this collectively and d_x receives the owned rows (ghost rows of d_x are not meaningful) */
 int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res, bfmg_halo_t const* halo);
 
+/* ---- small systems: one CTA per system (batch.cu) ------------------------------------------------ */
+
+typedef struct {
+	int32_t row_lo, row_hi; /* block rows of one system inside the shared pattern; row_lo % 32 == 0 */
+} bfmg_batch_range_t;
+
+typedef struct {
+	int32_t iterations;
+	int32_t converged;      /* 1 converged, 0 hit max_iter, -1 breakdown */
+	double rel_residual;
+	double true_rel_residual;
+	double backward_error;
+} bfmg_batch_status_t;
+
+int bfmg_batch_max_rows(void); /* largest system (node rows) the one-CTA solver takes */
+
+/* solves every system of the batch (ranges/status: host arrays of n_sys entries); systems that do not
+ * converge are reported in status, not as a failure of the call */
+int bfmg_pcg_batch(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, int32_t n_sys, bfmg_batch_range_t const* ranges, bfmg_batch_status_t* status, float* ms);
+
 /* times `reps` back-to-back launches of the CG SpMV kernel (q = A p with the fused dot) on d_val */
 int bfmg_spmv_time(bfmg_pattern_t const* pat, double const* d_val, int reps, float* ms_per_launch);
 

@@ -21,6 +21,9 @@ BFMG_HIDDEN int bfmg_check(cudaError_t rc, char const* what, char const* file, i
 BFMG_HIDDEN void bfmg_set_error(char const* fmt, ...);
 BFMG_HIDDEN int bfmg_device();
 
+/* D^-1/2 of the diagonal, b^ = D^-1/2 b, A^ = D^-1/2 A D^-1/2 into d_scaled (solver.cu) */
+BFMG_HIDDEN int bfmg_scale_system(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_dscale, double* d_bhat, double* d_scaled);
+
 #define BFMG_CHECK(call) bfmg_check((call), #call, __FILE__, __LINE__)
 
 /* launch on the library stream, count it, report configuration errors */

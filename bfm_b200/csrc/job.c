@@ -944,7 +944,30 @@ int bfmx_job_solve(bfmx_job_t* job) {
 
 	bfmi_pcg_options(job->stats.n_dofs, &opts);
 
-	if (bfmg_pcg(&job->pat, job->d_val, job->d_b, job->d_x, &opts, &res, job->part != NULL ? &job->halo : NULL) < 0) {
+	/* a small mesh on one GPU: the whole PCG runs inside one CTA (batch.cu) instead of three launches
+	 * per iteration; BFM_ONE_CTA=0 forces the general path */
+
+	char const* const env = getenv("BFM_ONE_CTA");
+
+	if (job->part == NULL && job->plan->nb <= bfmg_batch_max_rows() && (env == NULL || atoi(env) != 0)) {
+		bfmg_batch_range_t const range = {0, job->plan->nb};
+		bfmg_batch_status_t st;
+		size_t const before = bfmg_launch_count();
+
+		if (bfmg_pcg_batch(&job->pat, job->d_val, job->d_b, job->d_x, &opts, 1, &range, &st, &res.ms) < 0) {
+			return BFMI_FAIL(job->state, "PCG failed: %s", bfmg_last_error());
+		}
+
+		res.iterations = st.iterations;
+		res.restarts = 0;
+		res.rel_residual = st.rel_residual;
+		res.true_rel_residual = st.true_rel_residual;
+		res.backward_error = st.backward_error;
+		res.converged = st.converged == 1 && st.backward_error > opts.true_tol ? 0 : st.converged;
+		res.launches = bfmg_launch_count() - before;
+	}
+
+	else if (bfmg_pcg(&job->pat, job->d_val, job->d_b, job->d_x, &opts, &res, job->part != NULL ? &job->halo : NULL) < 0) {
 		return BFMI_FAIL(job->state, "PCG failed: %s", bfmg_last_error());
 	}
 

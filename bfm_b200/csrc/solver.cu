@@ -463,6 +463,23 @@ Grids grids_for(bfmg_pattern_t const* pat) {
 
 } // namespace
 
+int bfmg_scale_system(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_dscale, double* d_bhat, double* d_scaled) {
+	Grids const G = grids_for(pat);
+
+	double2 const* const vtop = (double2 const*) d_val;
+	double2 const* const vbot = vtop + pat->n_slots;
+	double2* const stop = (double2*) d_scaled;
+
+	if (
+		BFMG_LAUNCH(k_jacobi, (pat->nb + kBlock - 1) / kBlock, kBlock, 0, *pat, vtop, vbot, (double2 const*) d_b, (double2*) d_dscale, (double2*) d_bhat) < 0 ||
+		BFMG_LAUNCH(k_scale_matrix, G.spmv, kBlock, 0, *pat, vtop, vbot, (double2 const*) d_dscale, stop, stop + pat->n_slots) < 0
+	) {
+		return -1;
+	}
+
+	return 0;
+}
+
 extern "C" {
 
 int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res, bfmg_halo_t const* halo) {
