@@ -201,6 +201,93 @@ def workload_config(nx: int, ny: int, gpus: int) -> dict:
 	}
 
 
+# ---- configs[4]: 1024 batched small systems ---------------------------------------------------------
+
+
+def batch_workload(args, binding):
+	"""1024 variants of config 1 (8.lepl1110 + problem.txt, 670 DOF each; Young's modulus swept): the
+	batched form of examples/benchmark.py's loop.  One assembly launch, one CTA per system."""
+
+	import numpy as np
+
+	from bfm_b200 import ext, workloads
+
+	lib = binding.lib
+	golden = os.path.join(ROOT, "tests", "golden")
+	cases_ = workloads.lepl_sweep(os.path.join(golden, "meshes", "8.lepl1110"), os.path.join(golden, "problems", "problem.txt"), args.batch, binding)
+	sims = [c.sim for c in cases_]
+
+	job = ext.Job.batch(sims)
+	job.upload()
+
+	for _ in range(args.warmup):
+		job.assemble()
+		job.solve()
+
+	sampler = ClockSampler(0)
+	sampler.start()
+	assert not lib.bfmx_device_sync()
+
+	launches0 = lib.bfmx_kernel_launches()
+	assert not lib.bfmx_timer_start(0)
+
+	for _ in range(args.steps):
+		job.assemble()
+		job.solve()
+
+	ms = lib.bfmx_timer_stop(0) / args.steps
+	launches = lib.bfmx_kernel_launches() - launches0
+	clocks = sampler.stop()
+	s = job.stats()
+	status = job.batch_status()
+	n_dofs = s["n_dofs"]
+
+	# the PCG kernel streams each system's scaled matrix once per iteration (L2-resident at this size)
+	iters_total = sum(st["iterations"] for st in status)
+	sys_bytes = s["n_slots"] * 36 / len(status)
+	solve_bytes = iters_total * sys_bytes
+
+	ext.sim_run_batch(sims)  # warm-up of the end-to-end call
+	t0 = time.perf_counter()
+	h2d = d2h = 0
+
+	for _ in range(args.steps):
+		ext.sim_run_batch(sims)
+		st = ext.last_stats(binding)
+		h2d += st["h2d_bytes"]
+		d2h += st["d2h_bytes"]
+
+	e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+	check = float(np.abs(workloads.effects_view(cases_[0].instance)).max())
+
+	cpu = None
+
+	if not args.no_cpu_baseline:
+		from oracle import ref
+
+		ref_cases = workloads.lepl_sweep(os.path.join(golden, "meshes", "8.lepl1110"), os.path.join(golden, "problems", "problem.txt"), 16, ref.binding())
+		t0 = time.perf_counter()
+
+		for c in ref_cases:
+			c.sim.run()
+
+		sec = (time.perf_counter() - t0) / len(ref_cases)
+		cpu = {"value": 670 / sec, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"16 of the {args.batch} systems, bfm_sim_run each, {sec * 1e3:.2f} ms per system (what examples/benchmark.py times)"}
+
+	print(json.dumps({
+		"metric": METRIC, "value": n_dofs / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+		"ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+		"config": {"workload": f"{len(status)} batched small systems (8.lepl1110 + problem.txt with E swept, 670 DOF each), one CTA per system (BASELINE.json configs[4])", "systems": len(status), "n_dofs": n_dofs},
+		"assembly_ms": s["ms_assemble"] + s["ms_bc"], "solve_ms": s["ms_solve"],
+		"cg_iterations_max": s["cg_iterations"], "cg_iterations_total": iters_total, "systems_per_s": len(status) / (ms * 1e-3),
+		"roofline": {"kernel": "k_pcg_cta<256> (whole PCG of one system per CTA)", "bound": "l2", "achieved": solve_bytes / (s["ms_solve"] * 1e-3) / 1e9, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+			"note": "matrix bytes streamed per second from L2/L1 (the batch's matrices total %.0f MB, inside the 126 MB L2); no HBM roofline applies" % (s["n_slots"] * 36 / 1e6)},
+		"cpu_baseline": cpu,
+		"e2e": {"value": n_dofs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms, "call": "bfmx_sim_run_batch (plan build + upload + assemble + solve + download, every step)", "max_abs_displacement": check},
+		"gpu_launches": launches, "clocks": clocks,
+	}), flush=True)
+
+
 # ---- our arm ----------------------------------------------------------------------------------------
 
 
@@ -212,6 +299,8 @@ def main():
 	ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
 	ap.add_argument("--cells", default=DEFAULT_CELLS, help="plate size NXxNY (cells)")
 	ap.add_argument("--reference-sample", default=REFERENCE_SAMPLE, help="plate size the CPU reference is timed on")
+	ap.add_argument("--workload", default="plate", choices=["plate", "batch"], help="plate: BASELINE.json configs[3] (the headline); batch: configs[4], 1024 small systems, one CTA each")
+	ap.add_argument("--batch", type=int, default=1024, help="systems in the batch workload")
 	ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
 	ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
 	args = ap.parse_args()
@@ -262,6 +351,13 @@ def main():
 		t = torch.tensor([value], dtype=torch.float64, device="cuda")
 		dist.all_reduce(t, op=dist.ReduceOp.MAX)
 		return float(t.item())
+
+	if args.workload == "batch":
+		if world != 1:
+			raise SystemExit("the batch workload is embarrassingly parallel: run one process per GPU on its own share")
+
+		batch_workload(args, binding)
+		return
 
 	nx, ny = parse_cells(args.cells)
 	case = workloads.plate_case(nx, ny, binding=binding)

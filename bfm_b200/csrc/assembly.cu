@@ -67,11 +67,14 @@ __device__ __forceinline__ void geometry(bfmg_asm_tables_t const& T, int g, doub
 	}
 }
 
-template <int KIND, bool AXI>
+/* BATCH: the pattern holds many independent systems (batch.cu); slice s belongs to system
+ * slice_tab[s], whose tables (material, forces, rule) are tabs[slice_tab[s]] in device memory */
+template <int KIND, bool AXI, bool BATCH>
 __global__ void __launch_bounds__(kBlock) k_assemble(
-	const __grid_constant__ bfmg_asm_tables_t T, const __grid_constant__ bfmg_pattern_t P,
+	const __grid_constant__ bfmg_asm_tables_t T0, const __grid_constant__ bfmg_pattern_t P,
 	double2 const* __restrict__ coords, double2 const* __restrict__ nforce,
-	double2* __restrict__ vtop, double2* __restrict__ vbot, double2* __restrict__ bvec
+	double2* __restrict__ vtop, double2* __restrict__ vbot, double2* __restrict__ bvec,
+	bfmg_asm_tables_t const* __restrict__ tabs, int32_t const* __restrict__ slice_tab
 ) {
 	int const lane = threadIdx.x & (kWarp - 1);
 	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
@@ -81,6 +84,8 @@ __global__ void __launch_bounds__(kBlock) k_assemble(
 		int const row = slice * kWarp + lane;
 		int const diag = row < P.nb ? P.diag_pos[row] : -1;
 		int const end = P.slice_off[slice + 1];
+
+		bfmg_asm_tables_t const& T = BATCH ? tabs[slice_tab[slice]] : T0;
 
 		for (int slot = P.slice_off[slice] + lane; slot < end; slot += kWarp) {
 			int const c_end = P.ctr_ptr[slot + 1];
@@ -319,7 +324,7 @@ __global__ void k_bc_add(double* __restrict__ bvec, int32_t const* __restrict__ 
 
 extern "C" {
 
-int bfmg_assemble(bfmg_pattern_t const* pat, bfmg_asm_tables_t const* tab, double const* d_coords, double const* d_nforce, double* d_val, double* d_b) {
+int bfmg_assemble(bfmg_pattern_t const* pat, bfmg_asm_tables_t const* tab, double const* d_coords, double const* d_nforce, double* d_val, double* d_b, bfmg_asm_tables_t const* d_tabs, int32_t const* d_slice_tab) {
 	if (!bfmg_ready()) {
 		return -1;
 	}
@@ -333,15 +338,20 @@ int bfmg_assemble(bfmg_pattern_t const* pat, bfmg_asm_tables_t const* tab, doubl
 
 	int const blocks_needed = (pat->n_slices + kWarpsPerBlock - 1) / kWarpsPerBlock;
 
-#define ASM_LAUNCH(KIND, AXI) BFMG_LAUNCH((k_assemble<KIND, AXI>), bfmg_grid(blocks_needed, bfmg_resident_ctas(k_assemble<KIND, AXI>)), kBlock, 0, *tab, *pat, (double2 const*) d_coords, (double2 const*) d_nforce, vtop, vbot, (double2*) d_b)
+#define ASM_LAUNCH(KIND, AXI, BATCH) BFMG_LAUNCH((k_assemble<KIND, AXI, BATCH>), bfmg_grid(blocks_needed, bfmg_resident_ctas(k_assemble<KIND, AXI, BATCH>)), kBlock, 0, *tab, *pat, (double2 const*) d_coords, (double2 const*) d_nforce, vtop, vbot, (double2*) d_b, d_tabs, d_slice_tab)
+#define ASM_PICK(KIND, AXI) (d_tabs != nullptr ? ASM_LAUNCH(KIND, AXI, true) : ASM_LAUNCH(KIND, AXI, false))
+
+	/* tab->kind / tab->axisym are common to a batch (job.c checks) */
 
 	if (tab->kind == 3) {
-		return tab->axisym ? ASM_LAUNCH(3, true) : ASM_LAUNCH(3, false);
+		return tab->axisym ? ASM_PICK(3, true) : ASM_PICK(3, false);
 	}
 
 	if (tab->kind == 4) {
-		return tab->axisym ? ASM_LAUNCH(4, true) : ASM_LAUNCH(4, false);
+		return tab->axisym ? ASM_PICK(4, true) : ASM_PICK(4, false);
 	}
+
+#undef ASM_PICK
 
 #undef ASM_LAUNCH
 

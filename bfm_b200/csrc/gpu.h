@@ -112,8 +112,10 @@ typedef struct {
 	double const_force[BFMG_MAX_FORCES][2];
 } bfmg_asm_tables_t;
 
-/* one launch: stiffness blocks + load vector.  d_val: 4 * n_slots doubles, d_b: 2 * nb doubles */
-int bfmg_assemble(bfmg_pattern_t const* pat, bfmg_asm_tables_t const* tab, double const* d_coords, double const* d_nforce, double* d_val, double* d_b);
+/* one launch: stiffness blocks + load vector.  d_val: 4 * n_slots doubles, d_b: 2 * nb doubles.
+ * Batch of independent systems in one pattern: d_tabs[system] (device) and d_slice_tab[slice] = system;
+ * tab then only supplies the common kind / axisym.  NULL, NULL for a single system. */
+int bfmg_assemble(bfmg_pattern_t const* pat, bfmg_asm_tables_t const* tab, double const* d_coords, double const* d_nforce, double* d_val, double* d_b, bfmg_asm_tables_t const* d_tabs, int32_t const* d_slice_tab);
 
 /* ---- boundary conditions --------------------------------------------------------------------- */
 

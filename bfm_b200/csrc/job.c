@@ -48,6 +48,12 @@ typedef struct {
 	double *d_vals, *d_add;
 } bc_op_t;
 
+typedef struct {
+	bfm_instance_t* instance;
+	bfm_mesh_t const* mesh;
+	size_t node_off; /* first node of this system in the combined numbering (multiple of 32) */
+} batch_sys_t;
+
 struct bfmx_job {
 	bfm_state_t* state;
 	bfm_sim_kind_t kind;
@@ -74,6 +80,19 @@ struct bfmx_job {
 	double* d_x;
 	int32_t* d_stamp;
 	double* d_cval;
+
+	size_t table_forces;          /* forces per node in d_nforce (FUNKY tables) */
+
+	/* batch of independent systems sharing one pattern (bfmx_job_create_batch); n_sys == 0 otherwise */
+	int32_t n_sys;
+	batch_sys_t* sys;
+	bfm_mesh_t combined;          /* the systems' meshes as disconnected components, each padded to 32 nodes */
+	bfmg_asm_tables_t* h_tabs;    /* [n_sys] */
+	bfmg_asm_tables_t* d_tabs;
+	int32_t* h_slice_tab;         /* [n_slices] system of each slice */
+	int32_t* d_slice_tab;
+	bfmg_batch_range_t* ranges;   /* [n_sys] */
+	bfmg_batch_status_t* status;  /* [n_sys], filled by solve */
 
 	bool uploaded, assembled, solved;
 	bfmx_stats_t stats;
@@ -138,6 +157,12 @@ int bfmx_dist_world(void) {
 	return bfmg_dist_world();
 }
 
+static int batch_download(bfmx_job_t* job);
+
+int bfmx_batch_max_nodes(void) {
+	return bfmg_batch_max_rows();
+}
+
 static double now_ms(void) {
 	struct timespec ts;
 	clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -146,14 +171,15 @@ static double now_ms(void) {
 
 /* ---- shape tables, material constants, forces --------------------------------------------------- */
 
-static int fill_tables(bfmx_job_t* job, size_t n_forces, bfm_force_t** forces) {
-	bfm_state_t* const state = job->state;
-	bfm_obj_t* const obj = job->instance->obj;
+/* T: the tables of one system.  FUNKY forces are sampled at the nodes of `mesh` into
+ * nforce[(k * table_nodes + node_off + a) * 2 + d]; *nforce is allocated on first need with room for
+ * table_forces forces over table_nodes nodes (one system: its own counts; a batch: the batch's) */
+static int fill_tables(bfm_state_t* state, bfm_sim_kind_t sim_kind, bfm_instance_t* instance, bfm_mesh_t const* mesh, size_t n_forces, bfm_force_t** forces, bfmg_asm_tables_t* T, double** nforce, size_t table_forces, size_t table_nodes, size_t node_off) {
+	bfm_obj_t* const obj = instance->obj;
 	bfm_material_t const* const material = obj->material;
 	bfm_rule_t* const rule = obj->rule;
 	bfm_shape_t* const shape = &rule->shape;
-	bfmg_asm_tables_t* const T = &job->tab;
-	size_t const kind = job->mesh->kind;
+	size_t const kind = mesh->kind;
 
 	memset(T, 0, sizeof *T);
 
@@ -167,7 +193,7 @@ static int fill_tables(bfmx_job_t* job, size_t n_forces, bfm_force_t** forces) {
 
 	T->kind = (int32_t) kind;
 	T->n_points = (int32_t) rule->n_points;
-	T->axisym = job->kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN;
+	T->axisym = sim_kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN;
 	T->rho = material->rho;
 
 	/* the rule's own shape functions, evaluated on the host exactly as the reference does per element
@@ -200,12 +226,12 @@ static int fill_tables(bfmx_job_t* job, size_t n_forces, bfm_force_t** forces) {
 	double const E = material->E;
 	double const nu = material->nu;
 
-	if (job->kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN) { /* system.c:242-244 (note '* (1 - 2 nu)') */
+	if (sim_kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN) { /* system.c:242-244 (note '* (1 - 2 nu)') */
 		T->a = E * (1 - nu) / (1 + nu) * (1 - 2 * nu);
 		T->b = E * nu / (1 + nu) / (1 - 2 * nu);
 	}
 
-	else if (job->kind == BFM_SIM_KIND_PLANAR_STRAIN) { /* system.c:454-456 */
+	else if (sim_kind == BFM_SIM_KIND_PLANAR_STRAIN) { /* system.c:454-456 */
 		T->a = E * (1 - nu) / (1 + nu) / (1 - 2 * nu);
 		T->b = E * nu / (1 + nu) / (1 - 2 * nu);
 	}
@@ -242,11 +268,13 @@ static int fill_tables(bfmx_job_t* job, size_t n_forces, bfm_force_t** forces) {
 		return 0;
 	}
 
-	size_t const nb = job->mesh->n_nodes;
+	size_t const nb = mesh->n_nodes;
 
-	job->h_nforce = malloc(n_forces * nb * 2 * sizeof *job->h_nforce + 8);
+	if (*nforce == NULL) {
+		*nforce = calloc(table_forces * table_nodes * 2 + 1, sizeof **nforce);
+	}
 
-	if (job->h_nforce == NULL) {
+	if (*nforce == NULL) {
 		return -1;
 	}
 
@@ -258,13 +286,13 @@ static int fill_tables(bfmx_job_t* job, size_t n_forces, bfm_force_t** forces) {
 
 	for (size_t k = 0; k < n_forces; k++) {
 		for (size_t a = 0; a < nb; a++) {
-			pos.data[0] = job->mesh->coords[2 * a + 0];
-			pos.data[1] = job->mesh->coords[2 * a + 1];
+			pos.data[0] = mesh->coords[2 * a + 0];
+			pos.data[1] = mesh->coords[2 * a + 1];
 
 			bfm_force_eval(forces[k], &pos, &out); /* status ignored, as in system.c:198 */
 
-			job->h_nforce[(k * nb + a) * 2 + 0] = out.data[0];
-			job->h_nforce[(k * nb + a) * 2 + 1] = out.data[1];
+			(*nforce)[(k * table_nodes + node_off + a) * 2 + 0] = out.data[0];
+			(*nforce)[(k * table_nodes + node_off + a) * 2 + 1] = out.data[1];
 		}
 	}
 
@@ -327,8 +355,8 @@ static int affected_rows(bfmi_plan_t const* plan, bc_op_t* op) {
 }
 
 /* apply_dirichlet (system.c:376-386) */
-static int op_dirichlet_xy(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t* op) {
-	size_t const nn = job->gmesh->n_nodes;
+static int op_dirichlet_xy(bfm_mesh_t const* gmesh, bfm_condition_t const* cond, bc_op_t* op) {
+	size_t const nn = gmesh->n_nodes;
 	int32_t const shift = cond->kind == BFM_CONDITION_KIND_DIRICHLET_X ? 0 : 1;
 	size_t count = 0;
 
@@ -356,8 +384,7 @@ static int op_dirichlet_xy(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t
 
 /* apply_dirichlet_normal_tangent (system.c:388-425): tangent = sum over the node's boundary edges, in
  * edge order, of (x_i - x_other) / length / 2; pow(d, 2) is d * d, as gcc -O2 compiles it */
-static int op_dirichlet_nt(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t* op) {
-	bfm_mesh_t const* const mesh = job->gmesh;
+static int op_dirichlet_nt(bfm_mesh_t const* mesh, bfm_condition_t const* cond, bc_op_t* op) {
 	size_t const nn = mesh->n_nodes;
 	bool const tangent = cond->kind == BFM_CONDITION_KIND_DIRICHLET_TANGENT;
 
@@ -446,9 +473,7 @@ static int cmp_pending(void const* a, void const* b) {
 
 /* Neumann loads (system.c:477-522; axisymmetric weighting :586-617): every mesh edge with both end
  * nodes in the mask adds to the right-hand side, in edge order */
-static int op_neumann(bfmx_job_t* job, bfm_condition_t const* cond, bc_op_t* op) {
-	bfm_mesh_t const* const mesh = job->gmesh;
-	bool const axisym = job->kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN;
+static int op_neumann(bfm_mesh_t const* mesh, bool axisym, bfm_condition_t const* cond, bc_op_t* op) {
 	bool const xy = cond->kind == BFM_CONDITION_KIND_NEUMANN_X || cond->kind == BFM_CONDITION_KIND_NEUMANN_Y;
 
 	op->kind = OP_ADD;
@@ -580,35 +605,38 @@ static void localize_op(bfmi_part_t const* part, bc_op_t* op) {
 	op->n_groups = kept_groups;
 }
 
-static int build_ops(bfmx_job_t* job) {
-	bfm_instance_t const* const instance = job->instance;
-	bool const axisym = job->kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN;
+/* one instance's conditions, in instance order, as work lists in the DOF numbering of `gmesh` */
+static int build_ops_for(bfm_mesh_t const* gmesh, bfm_sim_kind_t sim_kind, bfm_instance_t const* instance, bc_op_t** out_ops, size_t* out_n) {
+	bool const axisym = sim_kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN;
+	bc_op_t* const ops = calloc(instance->n_conditions + 1, sizeof *ops);
+	size_t n_ops = 0;
 
-	job->ops = calloc(instance->n_conditions + 1, sizeof *job->ops);
+	*out_ops = ops;
+	*out_n = 0;
 
-	if (job->ops == NULL) {
+	if (ops == NULL) {
 		return -1;
 	}
 
 	for (size_t i = 0; i < instance->n_conditions; i++) {
 		bfm_condition_t const* const cond = instance->conditions[i];
-		bc_op_t* const op = &job->ops[job->n_ops];
+		bc_op_t* const op = &ops[n_ops];
 		int rv = 0;
 
 		switch (cond->kind) {
 		case BFM_CONDITION_KIND_DIRICHLET_X:
 		case BFM_CONDITION_KIND_DIRICHLET_Y:
-			rv = op_dirichlet_xy(job, cond, op);
+			rv = op_dirichlet_xy(gmesh, cond, op);
 			break;
 
 		case BFM_CONDITION_KIND_DIRICHLET_NORMAL:
 		case BFM_CONDITION_KIND_DIRICHLET_TANGENT:
-			rv = op_dirichlet_nt(job, cond, op);
+			rv = op_dirichlet_nt(gmesh, cond, op);
 			break;
 
 		case BFM_CONDITION_KIND_NEUMANN_X:
 		case BFM_CONDITION_KIND_NEUMANN_Y:
-			rv = op_neumann(job, cond, op);
+			rv = op_neumann(gmesh, axisym, cond, op);
 			break;
 
 		case BFM_CONDITION_KIND_NEUMANN_NORMAL:
@@ -617,16 +645,44 @@ static int build_ops(bfmx_job_t* job) {
 				continue;
 			}
 
-			rv = op_neumann(job, cond, op);
+			rv = op_neumann(gmesh, axisym, cond, op);
 			break;
 
 		default:
 			continue; /* unknown kinds fall through every branch of the reference's BC loop */
 		}
 
+		*out_n = ++n_ops; /* counted before the check so that a failed list is still released */
+
 		if (rv < 0) {
 			return -1;
 		}
+	}
+
+	return 0;
+}
+
+static void free_ops(bc_op_t* ops, size_t n_ops) {
+	for (size_t i = 0; i < n_ops; i++) {
+		bc_op_t* const op = &ops[i];
+
+		free(op->dofs), free(op->vals), free(op->rows);
+		free(op->group_dof), free(op->group_ptr), free(op->add);
+
+		bfmg_free(op->d_dofs), bfmg_free(op->d_vals), bfmg_free(op->d_rows);
+		bfmg_free(op->d_group_dof), bfmg_free(op->d_group_ptr), bfmg_free(op->d_add);
+	}
+
+	free(ops);
+}
+
+static int build_ops(bfmx_job_t* job) {
+	if (build_ops_for(job->gmesh, job->kind, job->instance, &job->ops, &job->n_ops) < 0) {
+		return -1;
+	}
+
+	for (size_t i = 0; i < job->n_ops; i++) {
+		bc_op_t* const op = &job->ops[i];
 
 		if (job->part != NULL) {
 			localize_op(job->part, op);
@@ -635,14 +691,63 @@ static int build_ops(bfmx_job_t* job) {
 		if (op->kind == OP_DIRICHLET && affected_rows(job->plan, op) < 0) {
 			return -1;
 		}
-
-		job->n_ops++;
 	}
 
 	return 0;
 }
 
 /* ---- job life cycle -------------------------------------------------------------------------------- */
+
+/* device buffers of a job whose plan, tables and work lists are ready */
+static int job_alloc_device(bfmx_job_t* job, size_t table_forces) {
+	bfm_state_t* const state = job->state;
+	size_t const nb = (size_t) job->plan->nb;
+	size_t const n_forces = table_forces;
+
+	if (
+		bfmg_alloc((void**) &job->d_coords, nb * 2 * sizeof(double)) < 0 ||
+		bfmg_alloc((void**) &job->d_val, (size_t) job->plan->n_slots * 4 * sizeof(double)) < 0 ||
+		bfmg_alloc((void**) &job->d_b, nb * 2 * sizeof(double)) < 0 ||
+		bfmg_alloc((void**) &job->d_x, nb * 2 * sizeof(double)) < 0 ||
+		(job->h_nforce != NULL && bfmg_alloc((void**) &job->d_nforce, n_forces * nb * 2 * sizeof(double)) < 0)
+	) {
+		BFMI_FAIL(state, "device allocation failed: %s", bfmg_last_error());
+		return -1;
+	}
+
+	bool any_dirichlet = false;
+
+	for (size_t i = 0; i < job->n_ops; i++) {
+		bc_op_t* const op = &job->ops[i];
+		int rv = 0;
+
+		if (op->kind == OP_DIRICHLET) {
+			any_dirichlet = true;
+
+			rv |= bfmg_alloc((void**) &op->d_dofs, ((size_t) op->n_dofs + 1) * sizeof(int32_t));
+			rv |= bfmg_alloc((void**) &op->d_vals, ((size_t) op->n_dofs + 1) * sizeof(double));
+			rv |= bfmg_alloc((void**) &op->d_rows, ((size_t) op->n_rows + 1) * sizeof(int32_t));
+		}
+
+		else if (op->n_groups > 0) {
+			rv |= bfmg_alloc((void**) &op->d_group_dof, ((size_t) op->n_groups + 1) * sizeof(int32_t));
+			rv |= bfmg_alloc((void**) &op->d_group_ptr, ((size_t) op->n_groups + 2) * sizeof(int32_t));
+			rv |= bfmg_alloc((void**) &op->d_add, ((size_t) op->group_ptr[op->n_groups] + 1) * sizeof(double));
+		}
+
+		if (rv < 0) {
+			BFMI_FAIL(state, "device allocation failed: %s", bfmg_last_error());
+			return -1;
+		}
+	}
+
+	if (any_dirichlet && (bfmg_alloc((void**) &job->d_stamp, nb * 2 * sizeof(int32_t)) < 0 || bfmg_alloc((void**) &job->d_cval, nb * 2 * sizeof(double)) < 0)) {
+		BFMI_FAIL(state, "device allocation failed: %s", bfmg_last_error());
+		return -1;
+	}
+
+	return 0;
+}
 
 static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind, bfm_instance_t* instance, size_t n_forces, bfm_force_t** forces, bool partitioned) {
 	bfm_mesh_t* const mesh = instance->obj->mesh;
@@ -705,7 +810,7 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 		job->stats.h2d_bytes += ((size_t) job->plan->n_slices + 1 + 2 * (size_t) job->plan->nb + 2 * (size_t) job->plan->n_slots + 1 + (size_t) job->plan->n_ctr + job->plan->n_elems * (size_t) job->plan->kind) * 4;
 	}
 
-	if (fill_tables(job, n_forces, forces) < 0 || build_ops(job) < 0) {
+	if (fill_tables(state, kind, instance, job->mesh, n_forces, forces, &job->tab, &job->h_nforce, n_forces, job->mesh->n_nodes, 0) < 0 || build_ops(job) < 0) {
 		goto fail;
 	}
 
@@ -742,45 +847,9 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 		}
 	}
 
-	if (
-		bfmg_alloc((void**) &job->d_coords, nb * 2 * sizeof(double)) < 0 ||
-		bfmg_alloc((void**) &job->d_val, (size_t) job->plan->n_slots * 4 * sizeof(double)) < 0 ||
-		bfmg_alloc((void**) &job->d_b, nb * 2 * sizeof(double)) < 0 ||
-		bfmg_alloc((void**) &job->d_x, nb * 2 * sizeof(double)) < 0 ||
-		(job->h_nforce != NULL && bfmg_alloc((void**) &job->d_nforce, n_forces * nb * 2 * sizeof(double)) < 0)
-	) {
-		BFMI_FAIL(state, "device allocation failed: %s", bfmg_last_error());
-		goto fail;
-	}
+	job->table_forces = n_forces;
 
-	bool any_dirichlet = false;
-
-	for (size_t i = 0; i < job->n_ops; i++) {
-		bc_op_t* const op = &job->ops[i];
-		int rv = 0;
-
-		if (op->kind == OP_DIRICHLET) {
-			any_dirichlet = true;
-
-			rv |= bfmg_alloc((void**) &op->d_dofs, ((size_t) op->n_dofs + 1) * sizeof(int32_t));
-			rv |= bfmg_alloc((void**) &op->d_vals, ((size_t) op->n_dofs + 1) * sizeof(double));
-			rv |= bfmg_alloc((void**) &op->d_rows, ((size_t) op->n_rows + 1) * sizeof(int32_t));
-		}
-
-		else if (op->n_groups > 0) {
-			rv |= bfmg_alloc((void**) &op->d_group_dof, ((size_t) op->n_groups + 1) * sizeof(int32_t));
-			rv |= bfmg_alloc((void**) &op->d_group_ptr, ((size_t) op->n_groups + 2) * sizeof(int32_t));
-			rv |= bfmg_alloc((void**) &op->d_add, ((size_t) op->group_ptr[op->n_groups] + 1) * sizeof(double));
-		}
-
-		if (rv < 0) {
-			BFMI_FAIL(state, "device allocation failed: %s", bfmg_last_error());
-			goto fail;
-		}
-	}
-
-	if (any_dirichlet && (bfmg_alloc((void**) &job->d_stamp, nb * 2 * sizeof(int32_t)) < 0 || bfmg_alloc((void**) &job->d_cval, nb * 2 * sizeof(double)) < 0)) {
-		BFMI_FAIL(state, "device allocation failed: %s", bfmg_last_error());
+	if (job_alloc_device(job, n_forces) < 0) {
 		goto fail;
 	}
 
@@ -808,22 +877,435 @@ int bfmx_job_create(bfmx_job_t** job, bfm_sim_t* sim, size_t instance_index) {
 	return job_create(job, sim->state, sim->kind, sim->instances[instance_index], sim->n_forces, sim->forces, true);
 }
 
+/* ---- batches of small systems (BASELINE.json configs[4]; kernels in batch.cu) ---------------------------
+ *
+ * All systems of the batch become ONE mesh of disconnected components - system s occupies the node range
+ * [node_off[s], node_off[s] + n_nodes[s]), node_off a multiple of 32 so that no SELL-32 slice straddles
+ * two systems (the padding nodes are isolated: an empty diagonal block, x = 0).  Node and element order
+ * inside a system are kept, so each system is assembled with the reference's accumulation order, bit for
+ * bit as if it were alone.  Material, rule and forces differ per system: tables[s].  Conditions are
+ * applied in instance order per system; the c-th conditions of all systems are merged into one work list
+ * (systems are independent, so only the order inside a system matters). */
+
+static void shift_op(bc_op_t* op, size_t node_off) {
+	for (int32_t i = 0; i < op->n_dofs; i++) {
+		op->dofs[i] += (int32_t) (2 * node_off);
+	}
+
+	for (int32_t g = 0; g < op->n_groups; g++) {
+		op->group_dof[g] += (int32_t) (2 * node_off);
+	}
+}
+
+/* dst (zeroed, same kind) += src: lists are appended; systems come in ascending node order, so DOFs stay ascending */
+static int append_op(bc_op_t* dst, bc_op_t const* src) {
+	if (src->kind == OP_DIRICHLET) {
+		if (src->n_dofs == 0) {
+			return 0;
+		}
+
+		int32_t* const dofs = realloc(dst->dofs, ((size_t) dst->n_dofs + src->n_dofs + 1) * sizeof *dofs);
+		double* const vals = realloc(dst->vals, ((size_t) dst->n_dofs + src->n_dofs + 1) * sizeof *vals);
+
+		dst->dofs = dofs != NULL ? dofs : dst->dofs;
+		dst->vals = vals != NULL ? vals : dst->vals;
+
+		if (dofs == NULL || vals == NULL) {
+			return -1;
+		}
+
+		memcpy(dst->dofs + dst->n_dofs, src->dofs, (size_t) src->n_dofs * sizeof *dofs);
+		memcpy(dst->vals + dst->n_dofs, src->vals, (size_t) src->n_dofs * sizeof *vals);
+		dst->n_dofs += src->n_dofs;
+
+		return 0;
+	}
+
+	if (src->n_groups == 0) {
+		return 0;
+	}
+
+	int32_t const old_adds = dst->n_groups > 0 ? dst->group_ptr[dst->n_groups] : 0;
+	int32_t const new_adds = src->group_ptr[src->n_groups];
+
+	int32_t* const gd = realloc(dst->group_dof, ((size_t) dst->n_groups + src->n_groups + 1) * sizeof *gd);
+	int32_t* const gp = realloc(dst->group_ptr, ((size_t) dst->n_groups + src->n_groups + 2) * sizeof *gp);
+	double* const add = realloc(dst->add, ((size_t) old_adds + new_adds + 1) * sizeof *add);
+
+	dst->group_dof = gd != NULL ? gd : dst->group_dof;
+	dst->group_ptr = gp != NULL ? gp : dst->group_ptr;
+	dst->add = add != NULL ? add : dst->add;
+
+	if (gd == NULL || gp == NULL || add == NULL) {
+		return -1;
+	}
+
+	for (int32_t g = 0; g < src->n_groups; g++) {
+		dst->group_dof[dst->n_groups + g] = src->group_dof[g];
+		dst->group_ptr[dst->n_groups + g] = old_adds + src->group_ptr[g];
+	}
+
+	memcpy(dst->add + old_adds, src->add, (size_t) new_adds * sizeof *add);
+
+	dst->n_groups += src->n_groups;
+	dst->group_ptr[dst->n_groups] = old_adds + new_adds;
+
+	return 0;
+}
+
+int bfmx_job_create_batch(bfmx_job_t** out, bfm_sim_t** sims, size_t n_sims) {
+	*out = NULL;
+
+	if (n_sims == 0 || sims == NULL) {
+		return -1;
+	}
+
+	bfm_state_t* const state = sims[0]->state;
+
+	if (!bfmg_available()) {
+		return BFMI_FAIL(state, "%s", bfmg_last_error());
+	}
+
+	if (bfmg_dist_world() > 1) {
+		return BFMI_FAIL(state, "batches are independent systems: give each rank its own share instead of partitioning one batch");
+	}
+
+	bfmx_job_t* const job = calloc(1, sizeof *job);
+
+	if (job == NULL) {
+		return -1;
+	}
+
+	job->state = state;
+
+	bc_op_t** sys_ops = NULL;
+	size_t* sys_n_ops = NULL;
+	size_t n_sys = 0;
+
+	for (size_t i = 0; i < n_sims; i++) {
+		if (sims[i]->kind == BFM_SIM_KIND_NONE) {
+			continue; /* bfm_sim_run does nothing for these (sim.c:138-140) */
+		}
+
+		if (sims[i]->kind != BFM_SIM_KIND_PLANAR_STRAIN && sims[i]->kind != BFM_SIM_KIND_PLANAR_STRESS && sims[i]->kind != BFM_SIM_KIND_AXISYMMETRIC_STRAIN) {
+			goto fail;
+		}
+
+		n_sys += sims[i]->n_instances;
+	}
+
+	if (n_sys == 0 || n_sys > INT32_MAX / 64) {
+		BFMI_FAIL(state, "empty batch");
+		goto fail;
+	}
+
+	job->sys = calloc(n_sys, sizeof *job->sys);
+	job->h_tabs = calloc(n_sys, sizeof *job->h_tabs);
+	job->ranges = calloc(n_sys, sizeof *job->ranges);
+	job->status = calloc(n_sys, sizeof *job->status);
+	sys_ops = calloc(n_sys, sizeof *sys_ops);
+	sys_n_ops = calloc(n_sys, sizeof *sys_n_ops);
+
+	if (job->sys == NULL || job->h_tabs == NULL || job->ranges == NULL || job->status == NULL || sys_ops == NULL || sys_n_ops == NULL) {
+		goto fail;
+	}
+
+	/* layout */
+
+	size_t nb_total = 0;
+	size_t ne_total = 0;
+	size_t max_forces = 0;
+	size_t kind = 0;
+	bool axisym = false;
+
+	{
+		size_t s = 0;
+
+		for (size_t i = 0; i < n_sims; i++) {
+			if (sims[i]->kind == BFM_SIM_KIND_NONE) {
+				continue;
+			}
+
+			for (size_t k = 0; k < sims[i]->n_instances; k++, s++) {
+				bfm_instance_t* const instance = sims[i]->instances[k];
+				bfm_mesh_t const* const mesh = instance->obj->mesh;
+				bool const axi = sims[i]->kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN;
+
+				if (mesh->dim != 2 || (mesh->kind != BFM_ELEM_KIND_SIMPLEX && mesh->kind != BFM_ELEM_KIND_QUAD)) {
+					goto fail; /* system.c:436-442 */
+				}
+
+				if (s == 0) {
+					kind = mesh->kind;
+					axisym = axi;
+				}
+
+				else if (mesh->kind != kind || axi != axisym) {
+					BFMI_FAIL(state, "a batch must use one element kind and must not mix planar with axisymmetric problems");
+					goto fail;
+				}
+
+				if ((int64_t) mesh->n_nodes > bfmg_batch_max_rows()) {
+					BFMI_FAIL(state, "system %zu has %zu nodes; the one-CTA solver takes at most %d (run it with bfm_sim_run)", s, mesh->n_nodes, bfmg_batch_max_rows());
+					goto fail;
+				}
+
+				job->sys[s].instance = instance;
+				job->sys[s].mesh = mesh;
+				job->sys[s].node_off = nb_total;
+
+				job->ranges[s].row_lo = (int32_t) nb_total;
+				job->ranges[s].row_hi = (int32_t) (nb_total + mesh->n_nodes);
+
+				nb_total += (mesh->n_nodes + 31) / 32 * 32;
+				ne_total += mesh->n_elems;
+				max_forces = sims[i]->n_forces > max_forces ? sims[i]->n_forces : max_forces;
+			}
+		}
+	}
+
+	job->n_sys = (int32_t) n_sys;
+	job->kind = axisym ? BFM_SIM_KIND_AXISYMMETRIC_STRAIN : BFM_SIM_KIND_PLANAR_STRESS;
+
+	/* the combined mesh */
+
+	bfm_mesh_t* const cm = &job->combined;
+
+	cm->state = state;
+	cm->dim = 2;
+	cm->kind = kind;
+	cm->n_nodes = nb_total;
+	cm->n_elems = ne_total;
+	cm->coords = calloc(nb_total * 2 + 1, sizeof *cm->coords);
+	cm->elems = malloc((ne_total * kind + 1) * sizeof *cm->elems);
+
+	if (cm->coords == NULL || cm->elems == NULL) {
+		goto fail;
+	}
+
+	{
+		size_t e_off = 0;
+
+		for (size_t s = 0; s < n_sys; s++) {
+			bfm_mesh_t const* const mesh = job->sys[s].mesh;
+			size_t const off = job->sys[s].node_off;
+
+			memcpy(cm->coords + 2 * off, mesh->coords, mesh->n_nodes * 2 * sizeof *cm->coords);
+
+			for (size_t t = 0; t < mesh->n_elems * kind; t++) {
+				if (mesh->elems[t] >= mesh->n_nodes) {
+					BFMI_FAIL(state, "system %zu: connectivity points outside the node table", s);
+					goto fail;
+				}
+
+				cm->elems[e_off * kind + t] = mesh->elems[t] + off;
+			}
+
+			e_off += mesh->n_elems;
+		}
+	}
+
+	job->gmesh = cm;
+	job->mesh = cm;
+
+	double const t0 = now_ms();
+
+	job->plan = bfmi_plan_for_mesh(state, cm);
+
+	if (job->plan == NULL || bfmi_plan_upload(state, job->plan) < 0) {
+		goto fail;
+	}
+
+	job->stats.ms_plan = (float) (now_ms() - t0);
+	job->stats.h2d_bytes += ((size_t) job->plan->n_slices + 1 + 2 * (size_t) job->plan->nb + 2 * (size_t) job->plan->n_slots + 1 + (size_t) job->plan->n_ctr + job->plan->n_elems * (size_t) job->plan->kind) * 4;
+	job->pat = job->plan->dev;
+
+	job->h_slice_tab = calloc((size_t) job->plan->n_slices + 1, sizeof *job->h_slice_tab);
+
+	if (job->h_slice_tab == NULL) {
+		goto fail;
+	}
+
+	/* per-system tables and work lists */
+
+	size_t max_ops = 0;
+
+	{
+		size_t s = 0;
+
+		for (size_t i = 0; i < n_sims; i++) {
+			if (sims[i]->kind == BFM_SIM_KIND_NONE) {
+				continue;
+			}
+
+			for (size_t k = 0; k < sims[i]->n_instances; k++, s++) {
+				bfm_mesh_t const* const mesh = job->sys[s].mesh;
+				size_t const off = job->sys[s].node_off;
+
+				if (fill_tables(state, sims[i]->kind, job->sys[s].instance, mesh, sims[i]->n_forces, sims[i]->forces, &job->h_tabs[s], &job->h_nforce, max_forces, nb_total, off) < 0) {
+					goto fail;
+				}
+
+				for (size_t slice = off / 32; slice < (off + mesh->n_nodes + 31) / 32; slice++) {
+					job->h_slice_tab[slice] = (int32_t) s;
+				}
+
+				if (build_ops_for(mesh, sims[i]->kind, job->sys[s].instance, &sys_ops[s], &sys_n_ops[s]) < 0) {
+					goto fail;
+				}
+
+				for (size_t c = 0; c < sys_n_ops[s]; c++) {
+					shift_op(&sys_ops[s][c], off);
+				}
+
+				max_ops = sys_n_ops[s] > max_ops ? sys_n_ops[s] : max_ops;
+			}
+		}
+	}
+
+	job->tab = job->h_tabs[0]; /* kind / axisym for the launcher */
+
+	job->ops = calloc(2 * max_ops + 1, sizeof *job->ops);
+
+	if (job->ops == NULL) {
+		goto fail;
+	}
+
+	for (size_t c = 0; c < max_ops; c++) {
+		bc_op_t* const dir = &job->ops[job->n_ops];
+		bc_op_t* const add = &job->ops[job->n_ops + 1];
+
+		dir->kind = OP_DIRICHLET;
+		add->kind = OP_ADD;
+		job->n_ops += 2; /* both are released with the job whatever happens below */
+
+		for (size_t s = 0; s < n_sys; s++) {
+			if (c < sys_n_ops[s] && append_op(sys_ops[s][c].kind == OP_DIRICHLET ? dir : add, &sys_ops[s][c]) < 0) {
+				goto fail;
+			}
+		}
+
+		if (affected_rows(job->plan, dir) < 0) {
+			goto fail;
+		}
+	}
+
+	for (size_t s = 0; s < n_sys; s++) {
+		free_ops(sys_ops[s], sys_n_ops[s]);
+	}
+
+	free(sys_ops);
+	free(sys_n_ops);
+	sys_ops = NULL;
+
+	job->table_forces = max_forces;
+
+	if (
+		job_alloc_device(job, max_forces) < 0 ||
+		bfmg_alloc((void**) &job->d_tabs, n_sys * sizeof *job->h_tabs) < 0 ||
+		bfmg_alloc((void**) &job->d_slice_tab, ((size_t) job->plan->n_slices + 1) * sizeof(int32_t)) < 0
+	) {
+		goto fail;
+	}
+
+	job->stats.n_dofs = 0;
+
+	for (size_t s = 0; s < n_sys; s++) {
+		job->stats.n_dofs += 2 * job->sys[s].mesh->n_nodes;
+	}
+
+	job->stats.n_dofs_owned = job->stats.n_dofs;
+	job->stats.n_ranks = 1;
+	job->stats.n_blocks = (size_t) job->plan->n_blocks;
+	job->stats.n_slots = (size_t) job->plan->n_slots;
+
+	*out = job;
+	return 0;
+
+fail:
+
+	if (sys_ops != NULL) {
+		for (size_t s = 0; s < n_sys; s++) {
+			free_ops(sys_ops[s], sys_n_ops != NULL ? sys_n_ops[s] : 0);
+		}
+	}
+
+	free(sys_ops);
+	free(sys_n_ops);
+
+	bfmx_job_destroy(job);
+	return -1;
+}
+
+static int batch_download(bfmx_job_t* job) {
+	size_t const bytes = (size_t) job->plan->nb * 2 * sizeof(double);
+	double* const staged = malloc(bytes + 8);
+
+	if (staged == NULL) {
+		return -1;
+	}
+
+	int const t0 = bfmg_tick();
+
+	if (bfmg_download(staged, job->d_x, bytes) < 0) {
+		free(staged);
+		return BFMI_FAIL(job->state, "download failed: %s", bfmg_last_error());
+	}
+
+	int const t1 = bfmg_tick();
+
+	for (int32_t s = 0; s < job->n_sys; s++) { /* sim.c:127-131, per system */
+		memcpy(job->sys[s].instance->effects, staged + 2 * job->sys[s].node_off, job->sys[s].mesh->n_nodes * 2 * sizeof(double));
+	}
+
+	free(staged);
+
+	job->stats.ms_download = bfmg_lap(t0, t1);
+	job->stats.d2h_bytes += bytes;
+
+	return 0;
+}
+
+int bfmx_job_batch_size(bfmx_job_t* job) {
+	return job->n_sys;
+}
+
+int bfmx_job_batch_status(bfmx_job_t* job, size_t system, bfmx_batch_status_t* out) {
+	if (system >= (size_t) job->n_sys || !job->solved) {
+		return -1;
+	}
+
+	out->iterations = job->status[system].iterations;
+	out->converged = job->status[system].converged;
+	out->rel_residual = job->status[system].rel_residual;
+	out->true_rel_residual = job->status[system].true_rel_residual;
+	out->backward_error = job->status[system].backward_error;
+
+	return 0;
+}
+
+/* what examples/benchmark.py's loop does for many simulations at once */
+int bfmx_sim_run_batch(bfm_sim_t** sims, size_t n_sims) {
+	bfmx_job_t* job;
+
+	if (bfmx_job_create_batch(&job, sims, n_sims) < 0) {
+		return -1;
+	}
+
+	int const rv = bfmx_job_upload(job) < 0 || bfmx_job_assemble(job) < 0 || bfmx_job_solve(job) < 0 || bfmx_job_download(job) < 0 ? -1 : 0;
+
+	bfmx_publish_stats(&job->stats);
+	bfmx_job_destroy(job);
+
+	return rv;
+}
+
 int bfmx_job_destroy(bfmx_job_t* job) {
 	if (job == NULL) {
 		return 0;
 	}
 
-	for (size_t i = 0; i < job->n_ops; i++) {
-		bc_op_t* const op = &job->ops[i];
-
-		free(op->dofs), free(op->vals), free(op->rows);
-		free(op->group_dof), free(op->group_ptr), free(op->add);
-
-		bfmg_free(op->d_dofs), bfmg_free(op->d_vals), bfmg_free(op->d_rows);
-		bfmg_free(op->d_group_dof), bfmg_free(op->d_group_ptr), bfmg_free(op->d_add);
-	}
-
-	free(job->ops);
+	free_ops(job->ops, job->n_ops);
 	free(job->h_nforce);
 
 	bfmg_free(job->d_coords);
@@ -834,6 +1316,20 @@ int bfmx_job_destroy(bfmx_job_t* job) {
 	bfmg_free(job->d_stamp);
 	bfmg_free(job->d_cval);
 	bfmg_free(job->d_xg);
+	bfmg_free(job->d_tabs);
+	bfmg_free(job->d_slice_tab);
+
+	if (job->n_sys > 0) {
+		bfmi_plan_forget(&job->combined);
+	}
+
+	free(job->combined.coords);
+	free(job->combined.elems);
+	free(job->sys);
+	free(job->h_tabs);
+	free(job->h_slice_tab);
+	free(job->ranges);
+	free(job->status);
 
 	bfmi_plan_release(job->plan);
 	bfmi_part_release(job->part);
@@ -853,7 +1349,7 @@ int bfmx_job_upload(bfmx_job_t* job) {
 	rv |= UP(job->d_coords, job->mesh->coords, nb * 2, double);
 
 	if (job->h_nforce != NULL) {
-		rv |= UP(job->d_nforce, job->h_nforce, (size_t) job->tab.n_forces * nb * 2, double);
+		rv |= UP(job->d_nforce, job->h_nforce, job->table_forces * nb * 2, double);
 	}
 
 	for (size_t i = 0; i < job->n_ops; i++) {
@@ -870,6 +1366,11 @@ int bfmx_job_upload(bfmx_job_t* job) {
 			rv |= UP(op->d_group_ptr, op->group_ptr, op->n_groups + 1, int32_t);
 			rv |= UP(op->d_add, op->add, op->group_ptr[op->n_groups], double);
 		}
+	}
+
+	if (job->n_sys > 0) {
+		rv |= UP(job->d_tabs, job->h_tabs, job->n_sys, bfmg_asm_tables_t);
+		rv |= UP(job->d_slice_tab, job->h_slice_tab, job->plan->n_slices, int32_t);
 	}
 
 	if (job->d_stamp != NULL) {
@@ -897,7 +1398,7 @@ int bfmx_job_assemble(bfmx_job_t* job) {
 	size_t const before = bfmg_launch_count();
 	int const t0 = bfmg_tick();
 
-	if (bfmg_assemble(&job->plan->dev, &job->tab, job->d_coords, job->d_nforce, job->d_val, job->d_b) < 0) {
+	if (bfmg_assemble(&job->plan->dev, &job->tab, job->d_coords, job->d_nforce, job->d_val, job->d_b, job->d_tabs, job->d_slice_tab) < 0) {
 		return BFMI_FAIL(job->state, "assembly failed: %s", bfmg_last_error());
 	}
 
@@ -947,6 +1448,50 @@ int bfmx_job_solve(bfmx_job_t* job) {
 	/* a small mesh on one GPU: the whole PCG runs inside one CTA (batch.cu) instead of three launches
 	 * per iteration; BFM_ONE_CTA=0 forces the general path */
 
+	if (job->n_sys > 0) {
+		size_t const before = bfmg_launch_count();
+		float ms = 0;
+
+		if (bfmg_pcg_batch(&job->pat, job->d_val, job->d_b, job->d_x, &opts, job->n_sys, job->ranges, job->status, &ms) < 0) {
+			return BFMI_FAIL(job->state, "batched PCG failed: %s", bfmg_last_error());
+		}
+
+		/* the job's figures are the worst over the batch; per-system ones: bfmx_job_batch_status */
+
+		job->stats.cg_iterations = 0;
+		job->stats.cg_converged = 1;
+		job->stats.cg_rel_residual = job->stats.cg_true_rel_residual = job->stats.cg_backward_error = 0;
+
+		int32_t failed = 0;
+
+		for (int32_t i = 0; i < job->n_sys; i++) {
+			bfmg_batch_status_t* const st = &job->status[i];
+
+			if (st->converged == 1 && st->backward_error > opts.true_tol) {
+				st->converged = 0;
+			}
+
+			failed += st->converged != 1;
+
+			job->stats.cg_iterations = st->iterations > job->stats.cg_iterations ? st->iterations : job->stats.cg_iterations;
+			job->stats.cg_converged = st->converged < job->stats.cg_converged ? st->converged : job->stats.cg_converged;
+			job->stats.cg_rel_residual = fmax(job->stats.cg_rel_residual, st->rel_residual);
+			job->stats.cg_true_rel_residual = fmax(job->stats.cg_true_rel_residual, st->true_rel_residual);
+			job->stats.cg_backward_error = fmax(job->stats.cg_backward_error, st->backward_error);
+		}
+
+		job->stats.cg_restarts = 0;
+		job->stats.ms_solve = ms;
+		job->stats.kernel_launches += bfmg_launch_count() - before;
+		job->solved = true;
+
+		if (failed > 0) {
+			return BFMI_FAIL(job->state, "%d of the %d systems of the batch did not converge", failed, job->n_sys);
+		}
+
+		return 0;
+	}
+
 	char const* const env = getenv("BFM_ONE_CTA");
 
 	if (job->part == NULL && job->plan->nb <= bfmg_batch_max_rows() && (env == NULL || atoi(env) != 0)) {
@@ -991,6 +1536,10 @@ int bfmx_job_solve(bfmx_job_t* job) {
 int bfmx_job_download(bfmx_job_t* job) {
 	if (!job->solved) {
 		return -1;
+	}
+
+	if (job->n_sys > 0) {
+		return batch_download(job);
 	}
 
 	size_t const bytes = job->stats.n_dofs * sizeof(double);

@@ -47,6 +47,13 @@ class PartitionInfo(C.Structure):  # bfmx_partition_info_t
 	_fields_ = [(name, C.c_size_t) for name in ("first_node", "end_node", "n_local_nodes", "own_begin", "own_end", "n_local_elems", "n_neighbours", "n_send")]
 
 
+class BatchStatus(C.Structure):  # bfmx_batch_status_t
+	_fields_ = [("iterations", _int), ("converged", _int), ("rel_residual", C.c_double), ("true_rel_residual", C.c_double), ("backward_error", C.c_double)]
+
+	def as_dict(self) -> dict:
+		return {name: getattr(self, name) for name, _ in self._fields_}
+
+
 DIST_ID_BYTES = 128
 
 PROTOTYPES = {
@@ -74,6 +81,11 @@ PROTOTYPES = {
 	"bfmx_job_spmv_time": (_int, [C.c_void_p, _int, _P(C.c_float)]),
 	"bfmx_job_read": (_int, [C.c_void_p, abi.c_double_p, abi.c_double_p]),
 	"bfmx_job_destroy": (_int, [C.c_void_p]),
+	"bfmx_batch_max_nodes": (_int, []),
+	"bfmx_job_create_batch": (_int, [_P(C.c_void_p), _P(_P(abi.Sim)), C.c_size_t]),
+	"bfmx_job_batch_size": (_int, [C.c_void_p]),
+	"bfmx_job_batch_status": (_int, [C.c_void_p, C.c_size_t, _P(BatchStatus)]),
+	"bfmx_sim_run_batch": (_int, [_P(_P(abi.Sim)), C.c_size_t]),
 	"bfmx_mesh_compute_edges": (_int, [_P(abi.Mesh)]),
 	"bfmx_mesh_plate": (_int, [_P(abi.Mesh), _P(abi.State), C.c_size_t, C.c_size_t, C.c_double, C.c_double, _int, C.c_bool]),
 	"bfmx_mesh_pattern_sizes": (_int, [_P(abi.Mesh), _P(C.c_size_t), _P(C.c_size_t), _P(C.c_size_t), _P(C.c_size_t)]),
@@ -225,6 +237,22 @@ def pattern(mesh) -> dict:
 	return out
 
 
+def _sim_array(sims):
+	arr = (_P(abi.Sim) * len(sims))()
+
+	for i, sim in enumerate(sims):
+		arr[i] = C.pointer(sim.c_sim)
+
+	return arr
+
+
+def sim_run_batch(sims):
+	"""bfm_sim_run for many simulations at once: one assembly launch, one CTA per system (bfmx_sim_run_batch)"""
+
+	lib = sims[0].binding.lib
+	assert not lib.bfmx_sim_run_batch(_sim_array(sims), len(sims)), lib.bfmx_device_error()
+
+
 class Job:
 	"""staged pipeline of one instance (bfmx_job_*): create -> upload -> assemble -> solve -> download"""
 
@@ -233,6 +261,27 @@ class Job:
 		self.lib = sim.binding.lib
 		self.handle = C.c_void_p()
 		assert not self.lib.bfmx_job_create(C.byref(self.handle), C.byref(sim.c_sim), instance_index), self.lib.bfmx_device_error()
+
+	@classmethod
+	def batch(cls, sims) -> "Job":
+		"""one job for every instance of every simulation in `sims` (bfmx_job_create_batch)"""
+
+		job = cls.__new__(cls)
+		job.sim = list(sims)  # keeps them alive
+		job.lib = sims[0].binding.lib
+		job.handle = C.c_void_p()
+		assert not job.lib.bfmx_job_create_batch(C.byref(job.handle), _sim_array(sims), len(sims)), job.lib.bfmx_device_error()
+		return job
+
+	def batch_status(self) -> list[dict]:
+		out = []
+
+		for i in range(self.lib.bfmx_job_batch_size(self.handle)):
+			st = BatchStatus()
+			assert not self.lib.bfmx_job_batch_status(self.handle, i, C.byref(st))
+			out.append(st.as_dict())
+
+		return out
 
 	def __del__(self):
 		try:

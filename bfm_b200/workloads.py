@@ -96,3 +96,48 @@ def effects_view(instance: api.CInstance) -> np.ndarray:
 
 	n = instance.c_instance.n_effects
 	return np.ctypeslib.as_array(instance.c_instance.effects, shape=(n,))
+
+
+@dataclass
+class SweepCase:
+	sim: api.CSim
+	instance: api.CInstance
+	keep: list = field(default_factory=list)
+
+
+def lepl_sweep(mesh_path: str, problem_path: str, count: int, binding: api.Binding | None = None) -> list[SweepCase]:
+	"""`count` variants of one LEPL1110 problem on one shared mesh, Young's modulus scaled by 1 + i / count
+	(a design sweep: BASELINE.json configs[4]).  Conditions and gravity are those the problem file gives."""
+
+	binding = binding if binding is not None else api.default_binding()
+	mesh = api.Mesh_lepl1110(mesh_path, binding=binding)
+	ez = api.Ez_lepl1110(mesh, problem_path)
+	m = ez.c_ez.material
+	conds = ez.conditions()
+	g = ez.c_ez.gravity.linear.force
+	gravity = (g.data[0], g.data[1]) if ez.c_ez.sim.n_forces else None
+	out = []
+
+	for i in range(count):
+		material = api.Material(f"sweep{i}", m.rho, m.E * (1.0 + i / count), m.nu, binding=binding)
+		rule = api.Rule_gauss_legendre(2, mesh.kind, binding=binding)
+		obj = api.Obj(mesh, material, rule)
+		instance = api.Instance(obj)
+		keep = [mesh, ez, material, rule, obj]
+
+		for kind, value, mask in conds:
+			cond = api.Condition(mesh, kind, value)
+			cond.set_nodes(mask.astype(bool))
+			instance.add_condition(cond)
+
+		sim = api.Sim(ez.sim.kind, binding=binding)
+		sim.add_instance(instance)
+
+		if gravity is not None:
+			force = api.Force_linear(gravity, binding=binding)
+			sim.add_force(force)
+			keep.append(force)
+
+		out.append(SweepCase(sim, instance, keep))
+
+	return out

@@ -91,6 +91,29 @@ int bfmx_job_spmv_time(bfmx_job_t* job, int reps, float* ms_per_launch);
 int bfmx_job_read(bfmx_job_t* job, double* b_or_null, double* x_or_null);
 int bfmx_job_destroy(bfmx_job_t* job);
 
+/* ---- batches of small systems (BASELINE.json configs[4]) ---------------------------------------------
+ *
+ * Every instance of every simulation becomes one independent system; all of them are assembled by one
+ * launch and each is solved entirely by its own CTA (bfm_b200/csrc/batch.cu).  All systems must use the
+ * same element kind and must not mix planar with axisymmetric problems; each needs at most
+ * bfmx_batch_max_nodes() nodes.  A batch job goes through the same stages as a single one
+ * (bfmx_job_upload / _assemble / _solve / _download / _stats / _destroy). */
+
+typedef struct {
+	int iterations;
+	int converged;             /* 1 yes, 0 iteration limit or backward error above tolerance, -1 breakdown */
+	double rel_residual;
+	double true_rel_residual;
+	double backward_error;
+} bfmx_batch_status_t;
+
+int bfmx_batch_max_nodes(void);
+int bfmx_job_create_batch(bfmx_job_t** job, bfm_sim_t** sims, size_t n_sims);
+int bfmx_job_batch_size(bfmx_job_t* job);
+int bfmx_job_batch_status(bfmx_job_t* job, size_t system, bfmx_batch_status_t* out);
+/* create + upload + assemble + solve + download + destroy: bfm_sim_run for n_sims simulations at once */
+int bfmx_sim_run_batch(bfm_sim_t** sims, size_t n_sims);
+
 /* ---- meshes ------------------------------------------------------------------------------------------ */
 
 /* (re)derive mesh->edges from the connectivity exactly as the Wavefront reader does (reference mesh.c:52-102) */

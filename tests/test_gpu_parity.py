@@ -204,3 +204,104 @@ def test_large_plate_properties(nx, ny, kind, lib):
 	tip = grid[ny // 2, nx, 1]
 
 	assert -1.55e-4 < tip < -1.45e-4
+
+
+# ---- small systems: the one-CTA solver and batches (BASELINE.json configs[4]) ---------------------------
+
+
+def test_one_cta_path_equals_general_path(lib, monkeypatch):
+	"""small meshes take the one-CTA PCG (batch.cu); the three-kernel path must agree to solver accuracy"""
+
+	case = cases.build("bridge", lib)
+
+	case.sim.run()
+	one_cta = case.instance.effects.copy()
+	stats_one = ext.last_stats(lib)
+
+	monkeypatch.setenv("BFM_ONE_CTA", "0")
+	case.sim.run()
+	general = case.instance.effects.copy()
+	stats_gen = ext.last_stats(lib)
+
+	assert stats_one["kernel_launches"] < 20 < stats_gen["kernel_launches"]  # really two different paths
+	assert stats_one["cg_converged"] == 1 and stats_gen["cg_converged"] == 1
+	assert rel_l2(one_cta, general) <= 1e-10
+
+
+def test_batch_of_different_systems_matches_reference(lib, golden):
+	"""heterogeneous batch (different meshes, materials, forces, condition lists; all Q4): every system
+	within 1e-9 of the reference, and bit-identical to running it alone"""
+
+	names = ["lepl8", "plate_q4_24x6", "lepl8_all_kinds", "lepl8"]
+	batch = [cases.build(name, lib) for name in names]
+
+	ext.sim_run_batch([c.sim for c in batch])
+	stats = ext.last_stats(lib)
+
+	assert stats["cg_converged"] == 1 and stats["cg_rel_residual"] <= 1e-12
+
+	for name, case in zip(names, batch):
+		got = case.instance.effects.copy()
+		assert rel_l2(got, golden[f"{name}/effects"]) <= REL_L2, name
+
+		case.sim.run()  # alone: same kernel, same 1024-thread configuration -> same bits
+		assert np.array_equal(case.instance.effects, got), name
+
+
+def test_batch_with_funky_and_neumann_triangles(lib, golden):
+	names = ["plate_funky_20x5", "plate_neumann_16x4", "plate_40x10", "bridge"]
+	batch = [cases.build(name, lib) for name in names]
+
+	job = ext.Job.batch([c.sim for c in batch])
+	job.upload()
+	job.assemble()
+	job.solve()
+	job.download()
+
+	status = job.batch_status()
+
+	assert len(status) == len(names) and all(s["converged"] == 1 and s["rel_residual"] <= 1e-12 for s in status)
+	assert len({s["iterations"] for s in status}) > 1  # each system stopped on its own
+
+	for name, case in zip(names, batch):
+		assert rel_l2(case.instance.effects, golden[f"{name}/effects"]) <= REL_L2, name
+
+
+def test_batch_1024_systems_scale_with_stiffness(lib, golden):
+	"""config 5 shape: 1024 copies of config 1 with Young's modulus swept -> displacements scale as 1 / E"""
+
+	mesh = api.Mesh_lepl1110(cases.GOLDEN + "/meshes/8.lepl1110", binding=lib)
+	base = cases.build("lepl8", lib)
+	E0, nu, rho = base.material
+	sims, keep, factors = [], [], []
+
+	for i in range(1024):
+		f = 1.0 + i / 1024.0
+		case = cases._assemble_case("sweep", lib, mesh, base.sim_kind, (E0 * f, nu, rho), base.forces, base.conditions)
+		sims.append(case.sim)
+		keep.append(case)
+		factors.append(f)
+
+	ext.sim_run_batch(sims)
+	stats = ext.last_stats(lib)
+
+	assert stats["cg_converged"] == 1 and stats["n_dofs"] == 1024 * 670
+
+	want = golden["lepl8/effects"]
+
+	for i in (0, 1, 511, 1023):
+		assert rel_l2(keep[i].instance.effects * factors[i], want) <= REL_L2, i
+
+
+def test_batch_rejects_mixed_element_kinds_and_big_systems(lib, monkeypatch):
+	monkeypatch.setenv("BFM_QUIET", "1")
+
+	tri = cases.build("plate_40x10", lib)
+	quad = cases.build("plate_q4_24x6", lib)
+	arr = ext._sim_array([tri.sim, quad.sim])
+
+	assert lib.lib.bfmx_sim_run_batch(arr, 2) == -1
+
+	big = cases.build("gear60", lib)  # 8205 nodes > bfmx_batch_max_nodes()
+	assert big.mesh.n_nodes > lib.lib.bfmx_batch_max_nodes()
+	assert lib.lib.bfmx_sim_run_batch(ext._sim_array([big.sim]), 1) == -1
