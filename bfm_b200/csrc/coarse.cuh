@@ -1,0 +1,422 @@
+/*
+ * coarse.cuh - device side of the solver's coarse level (included by solver.cu, after Scalars / grid_sum).
+ *
+ * Two-level additive preconditioner in the Jacobi-scaled variables:  z = r + W E^-1 W^T r,  E = W^T A^ W,
+ * W_a = S_a R_a for node a of aggregate g:  S_a = diag(sqrt(a_ii)) (= 1 / dscale),  R_a = [1 0 -dy; 0 1 dx]
+ * the rigid-body modes about g's centroid (coarse.c explains the why).  Per PCG iteration:
+ *
+ *   k_restrict        g = W^T r      one CTA per aggregate over its owned nodes, fixed-order sums
+ *   k_coarse_apply    mu = E^-1 g    dense FP64 mat-vec with the explicit inverse, one warp per row;
+ *                                    last CTA: rz = r.r + g.mu, beta, rho
+ *   k_update_p_coarse p = r + W mu + beta p
+ *
+ * Setup (once per solve): E column by column through distance-2 colour probing - one plain SpMV per
+ * (colour, mode) - then an in-place blocked Gauss-Jordan inversion (E is SPD: no pivoting).  Everything
+ * is deterministic: no atomics, fixed reduction trees.  Multi-GPU: restriction partials are all-gathered
+ * and folded in rank order, E and E^-1 are replicated (bit-identical on every rank).
+ */
+#pragma once
+
+namespace {
+
+constexpr int kGjBlock = 32;
+
+struct CoarseWork {
+	bfmg_coarse_t C;      /* device pointers of the plan */
+	double2* wscale;      /* [nb] sqrt of the diagonal = 1 / dscale */
+	double* gpart;        /* [nc] this rank's W^T r */
+	double* ggath;        /* [world * nc] all ranks' (several GPUs only) */
+	double* g;            /* [nc] the complete W^T r (aliases gpart on one GPU) */
+	double* mu;           /* [nc] */
+	double* E;            /* [nc * nc] row-major; holds E, then E^-1 */
+	double* P;            /* [32 * 32] inverse of the current diagonal block during the inversion */
+	int32_t* bad;         /* set when a pivot is not positive: E not SPD, coarse level unusable */
+};
+
+__global__ void k_wscale(int nb, double2 const* __restrict__ dscale, double2* __restrict__ wscale) {
+	int const i = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (i < nb) {
+		double2 const s = dscale[i];
+		wscale[i] = make_double2(1.0 / s.x, 1.0 / s.y);
+	}
+}
+
+/* gpart[3 g + k] = sum over the owned nodes a of aggregate g of (R_a^T S_a v_a)_k; one CTA per aggregate */
+__global__ void __launch_bounds__(kBlock) k_restrict(bfmg_coarse_t C, double2 const* __restrict__ wscale, double2 const* __restrict__ v, double* __restrict__ gpart, Scalars const* S, bool obey_done) {
+	if (obey_done && S->done) {
+		return;
+	}
+
+	__shared__ double part[kWarpsPerBlock][3];
+
+	int const g = blockIdx.x;
+	int const beg = C.agg_ptr[g];
+	int const end = C.agg_ptr[g + 1];
+	double2 const* const wgeom = (double2 const*) C.wgeom;
+
+	double s0 = 0, s1 = 0, s2 = 0;
+
+	for (int i = beg + threadIdx.x; i < end; i += kBlock) {
+		int const a = C.agg_nodes[i];
+		double2 const vv = v[a];
+		double2 const w = wscale[a];
+		double2 const d = wgeom[a];
+
+		double const t0 = w.x * vv.x;
+		double const t1 = w.y * vv.y;
+
+		s0 += t0;
+		s1 += t1;
+		s2 += d.x * t1 - d.y * t0;
+	}
+
+	s0 = warp_sum(s0);
+	s1 = warp_sum(s1);
+	s2 = warp_sum(s2);
+
+	if ((threadIdx.x & (kWarp - 1)) == 0) {
+		part[threadIdx.x / kWarp][0] = s0;
+		part[threadIdx.x / kWarp][1] = s1;
+		part[threadIdx.x / kWarp][2] = s2;
+	}
+
+	__syncthreads();
+
+	if (threadIdx.x < 3) {
+		double t = 0;
+
+#pragma unroll
+		for (int w = 0; w < kWarpsPerBlock; w++) {
+			t += part[w][threadIdx.x];
+		}
+
+		gpart[3 * g + threadIdx.x] = t;
+	}
+}
+
+/* several GPUs: g[j] = sum over ranks (in rank order) of ggath[r][j] */
+__global__ void k_coarse_fold(int nc, int world, double const* __restrict__ ggath, double* __restrict__ g) {
+	int const j = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (j < nc) {
+		double t = 0;
+
+		for (int r = 0; r < world; r++) {
+			t += ggath[(size_t) r * nc + j];
+		}
+
+		g[j] = t;
+	}
+}
+
+/* mu = E^-1 g (one warp per row), then in the last CTA: rz = r.r + g.mu;  beta = rz / rho (0 when FIRST);  rho = rz */
+template <bool FIRST>
+__global__ void __launch_bounds__(kBlock) k_coarse_apply(int nc, double const* __restrict__ Einv, double const* __restrict__ g, double* __restrict__ mu, double* __restrict__ partials, Scalars* S) {
+	if (!FIRST && S->done) {
+		return;
+	}
+
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const row = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+
+	double acc = 0;
+
+	if (row < nc) {
+		double const* const e = Einv + (size_t) row * nc;
+		double t = 0;
+
+		for (int j = lane; j < nc; j += kWarp) {
+			t = fma(e[j], __ldg(&g[j]), t);
+		}
+
+		t = warp_sum(t);
+
+		if (lane == 0) {
+			mu[row] = t;
+			acc = t * g[row];
+		}
+	}
+
+	double total;
+
+	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
+		double const rz = S->rr + total;
+
+		S->beta = FIRST ? 0 : rz / S->rho;
+		S->rho = rz;
+	}
+}
+
+/* p = r + W mu + beta p */
+__global__ void __launch_bounds__(kBlock) k_update_p_coarse(int n2, int row0, bfmg_coarse_t C, double2 const* __restrict__ wscale, double const* __restrict__ mu, double2 const* __restrict__ r, double2* __restrict__ p, Scalars const* S, bool obey_done) {
+	if (obey_done && S->done) {
+		return;
+	}
+
+	double const beta = S->beta;
+	double2 const* const wgeom = (double2 const*) C.wgeom;
+
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+		int const a = row0 + i;
+		int const g = C.agg[a];
+		double2 const w = wscale[a];
+		double2 const d = wgeom[a];
+		double2 const rv = r[a];
+		double2 pv = p[a];
+
+		double const m0 = __ldg(&mu[3 * g + 0]);
+		double const m1 = __ldg(&mu[3 * g + 1]);
+		double const m2 = __ldg(&mu[3 * g + 2]);
+
+		double const z0 = rv.x + w.x * (m0 - d.y * m2);
+		double const z1 = rv.y + w.y * (m1 + d.x * m2);
+
+		pv.x = fma(beta, pv.x, z0);
+		pv.y = fma(beta, pv.y, z1);
+
+		p[a] = pv;
+	}
+}
+
+/* ---- setup: probing ------------------------------------------------------------------------------ */
+
+/* v = mode m of every aggregate of colour c, 0 elsewhere (all local rows, ghosts included: no exchange needed) */
+__global__ void k_probe_vector(int nb, bfmg_coarse_t C, double2 const* __restrict__ wscale, int color, int mode, double2* __restrict__ v) {
+	int const a = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (a >= nb) {
+		return;
+	}
+
+	double2 out = make_double2(0, 0);
+
+	if (C.color[C.agg[a]] == color) {
+		double2 const w = wscale[a];
+		double2 const d = ((double2 const*) C.wgeom)[a];
+
+		out.x = mode == 0 ? w.x : (mode == 2 ? -w.x * d.y : 0);
+		out.y = mode == 1 ? w.y : (mode == 2 ? w.y * d.x : 0);
+	}
+
+	v[a] = out;
+}
+
+/* g = W^T A^ (modes m of colour c): rows 3h..3h+2 are column 3 src + m of E, src = the colour-c aggregate near h */
+__global__ void k_probe_scatter(bfmg_coarse_t C, int color, int mode, double const* __restrict__ g, double* __restrict__ E) {
+	int const h = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (h >= C.n_agg) {
+		return;
+	}
+
+	int const src = C.color_nbr[(size_t) h * C.n_colors + color];
+
+	if (src < 0) {
+		return;
+	}
+
+	for (int k = 0; k < 3; k++) {
+		E[(size_t) (3 * h + k) * C.nc + 3 * src + mode] = g[3 * h + k];
+	}
+}
+
+/* identity on the padding rows (3 n_agg .. nc) */
+__global__ void k_coarse_pad(bfmg_coarse_t C, double* __restrict__ E) {
+	int const i = 3 * C.n_agg + blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (i < C.nc) {
+		E[(size_t) i * C.nc + i] = 1;
+	}
+}
+
+/* ---- setup: in-place blocked Gauss-Jordan inversion of the SPD matrix E (n x n, n % 32 == 0) ----------
+ *
+ * For block k (rows/columns K):  P = E_KK^-1;  E_K* = P E_K*;  E_ij -= E_iK E_Kj (i, j not in K);
+ * E_*K = -E_*K P;  E_KK = P.  After the last block E holds its inverse. */
+
+__global__ void __launch_bounds__(1024) k_gj_diag(int n, int k, double const* __restrict__ E, double* __restrict__ P, int32_t* bad) {
+	__shared__ double a[kGjBlock][kGjBlock + 1];
+
+	int const i = threadIdx.x / kGjBlock;
+	int const j = threadIdx.x % kGjBlock;
+	int const base = k * kGjBlock;
+
+	a[i][j] = E[(size_t) (base + i) * n + base + j];
+	__syncthreads();
+
+	for (int t = 0; t < kGjBlock; t++) {
+		double const piv = a[t][t];
+
+		if (!(piv > 0) && threadIdx.x == 0) {
+			*bad = 1;
+		}
+
+		double const inv = 1.0 / piv;
+		double const ait = a[i][t];
+		double const atj = a[t][j];
+
+		__syncthreads();
+
+		double v;
+
+		if (i == t) {
+			v = j == t ? inv : atj * inv;
+		}
+
+		else {
+			v = j == t ? -ait * inv : a[i][j] - ait * (atj * inv);
+		}
+
+		a[i][j] = v;
+		__syncthreads();
+	}
+
+	P[i * kGjBlock + j] = a[i][j];
+}
+
+/* row panel: E[K, J] = P * E[K, J] for every column block J != k; one CTA per J */
+__global__ void __launch_bounds__(1024) k_gj_row(int n, int k, double* __restrict__ E, double const* __restrict__ P) {
+	int const J = blockIdx.x;
+
+	if (J == k) {
+		return;
+	}
+
+	__shared__ double p[kGjBlock][kGjBlock + 1];
+	__shared__ double a[kGjBlock][kGjBlock + 1];
+
+	int const i = threadIdx.x / kGjBlock;
+	int const j = threadIdx.x % kGjBlock;
+
+	double* const tile = E + (size_t) (k * kGjBlock) * n + J * kGjBlock;
+
+	p[i][j] = P[i * kGjBlock + j];
+	a[i][j] = tile[(size_t) i * n + j];
+	__syncthreads();
+
+	double s = 0;
+
+#pragma unroll
+	for (int t = 0; t < kGjBlock; t++) {
+		s = fma(p[i][t], a[t][j], s);
+	}
+
+	tile[(size_t) i * n + j] = s;
+}
+
+/* trailing update: E[i, j] -= sum_t E[i, K_t] * E[K_t, j] for i, j outside K; 64 x 64 tile per CTA, 4 x 4 per thread */
+__global__ void __launch_bounds__(256) k_gj_update(int n, int k, double* __restrict__ E) {
+	__shared__ double col[64][kGjBlock + 1]; /* E[I, K] */
+	__shared__ double row[kGjBlock][64 + 1]; /* E[K, J] (already multiplied by P) */
+
+	int const i0 = blockIdx.y * 64;
+	int const j0 = blockIdx.x * 64;
+	int const kb = k * kGjBlock;
+
+	for (int t = threadIdx.x; t < 64 * kGjBlock; t += 256) {
+		int const r = t / kGjBlock, c = t % kGjBlock;
+		col[r][c] = i0 + r < n ? E[(size_t) (i0 + r) * n + kb + c] : 0;
+	}
+
+	for (int t = threadIdx.x; t < kGjBlock * 64; t += 256) {
+		int const r = t / 64, c = t % 64;
+		row[r][c] = j0 + c < n ? E[(size_t) (kb + r) * n + j0 + c] : 0;
+	}
+
+	__syncthreads();
+
+	int const ti = (threadIdx.x / 16) * 4;
+	int const tj = (threadIdx.x % 16) * 4;
+
+	double acc[4][4] = {};
+
+#pragma unroll 8
+	for (int t = 0; t < kGjBlock; t++) {
+		double cv[4], rv[4];
+
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			cv[u] = col[ti + u][t];
+			rv[u] = row[t][tj + u];
+		}
+
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+#pragma unroll
+			for (int w = 0; w < 4; w++) {
+				acc[u][w] = fma(cv[u], rv[w], acc[u][w]);
+			}
+		}
+	}
+
+#pragma unroll
+	for (int u = 0; u < 4; u++) {
+		int const i = i0 + ti + u;
+
+		if (i >= n || (i >= kb && i < kb + kGjBlock)) {
+			continue;
+		}
+
+#pragma unroll
+		for (int w = 0; w < 4; w++) {
+			int const j = j0 + tj + w;
+
+			if (j < n && !(j >= kb && j < kb + kGjBlock)) {
+				E[(size_t) i * n + j] -= acc[u][w];
+			}
+		}
+	}
+}
+
+/* column panel: E[I, K] = -E[I, K] * P for I != k;  E[K, K] = P; one CTA per I */
+__global__ void __launch_bounds__(1024) k_gj_col(int n, int k, double* __restrict__ E, double const* __restrict__ P) {
+	int const I = blockIdx.x;
+
+	__shared__ double p[kGjBlock][kGjBlock + 1];
+	__shared__ double a[kGjBlock][kGjBlock + 1];
+
+	int const i = threadIdx.x / kGjBlock;
+	int const j = threadIdx.x % kGjBlock;
+
+	double* const tile = E + (size_t) (I * kGjBlock) * n + k * kGjBlock;
+
+	p[i][j] = P[i * kGjBlock + j];
+	a[i][j] = tile[(size_t) i * n + j];
+	__syncthreads();
+
+	if (I == k) {
+		tile[(size_t) i * n + j] = p[i][j];
+		return;
+	}
+
+	double s = 0;
+
+#pragma unroll
+	for (int t = 0; t < kGjBlock; t++) {
+		s = fma(a[i][t], p[t][j], s);
+	}
+
+	tile[(size_t) i * n + j] = -s;
+}
+
+int coarse_invert(CoarseWork const& W) {
+	int const n = W.C.nc;
+	int const blocks = n / kGjBlock;
+	dim3 const tiles((n + 63) / 64, (n + 63) / 64);
+
+	for (int k = 0; k < blocks; k++) {
+		if (
+			BFMG_LAUNCH(k_gj_diag, 1, 1024, 0, n, k, W.E, W.P, W.bad) < 0 ||
+			BFMG_LAUNCH(k_gj_row, blocks, 1024, 0, n, k, W.E, W.P) < 0 ||
+			BFMG_LAUNCH(k_gj_update, tiles, 256, 0, n, k, W.E) < 0 ||
+			BFMG_LAUNCH(k_gj_col, blocks, 1024, 0, n, k, W.E, W.P) < 0
+		) {
+			return -1;
+		}
+	}
+
+	return 0;
+}
+
+} // namespace

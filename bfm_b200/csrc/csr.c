@@ -364,11 +364,11 @@ int bfmi_csr_solve(bfm_matrix_t* matrix, bfm_vec_t* y) {
 	}
 
 	bfmg_pcg_opts_t opts;
-	bfmg_pcg_result_t res;
+	bfmg_pcg_result_t res = {0};
 
 	bfmi_pcg_options(n, &opts);
 
-	if (bfmg_upload(d_b, rhs, n * sizeof *d_b) < 0 || bfmg_pcg(&csr->plan->dev, csr->d_val, d_b, d_x, &opts, &res, NULL) < 0) {
+	if (bfmg_upload(d_b, rhs, n * sizeof *d_b) < 0 || bfmg_pcg(&csr->plan->dev, csr->d_val, d_b, d_x, &opts, &res, NULL, NULL) < 0) {
 		BFMI_FAIL(state, "PCG failed: %s", bfmg_last_error());
 		goto done;
 	}

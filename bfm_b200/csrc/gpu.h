@@ -128,6 +128,21 @@ int bfmg_bc_dirichlet(bfmg_pattern_t const* pat, double* d_val, double* d_b, int
 /* right-hand-side additions (Neumann edge loads), grouped by DOF, applied in list order */
 int bfmg_bc_add(double* d_b, int32_t const* d_group_dof, int32_t const* d_group_ptr, double const* d_add, int32_t n_groups);
 
+/* ---- coarse level of the solver: rigid-body modes of node aggregates (coarse.c, coarse.cuh) --------- */
+
+typedef struct {
+	int32_t n_agg;
+	int32_t n_colors;
+	int32_t nc;          /* coarse dimension: 3 * n_agg rounded up to a multiple of 32 */
+
+	int32_t* agg;        /* [nb] aggregate of every local block row (owned and ghost) */
+	double* wgeom;       /* [nb] double2: node position relative to its aggregate's centroid */
+	int32_t* agg_ptr;    /* [n_agg + 1] */
+	int32_t* agg_nodes;  /* owned block rows of each aggregate, ascending */
+	int32_t* color;      /* [n_agg] */
+	int32_t* color_nbr;  /* [n_agg * n_colors] the aggregate of colour c equal or adjacent to g, or -1 */
+} bfmg_coarse_t;
+
 /* ---- FP64 conjugate gradient ----------------------------------------------------------------- */
 
 typedef struct {
@@ -147,13 +162,15 @@ typedef struct {
 	double true_rel_residual; /* ||b - A x|| / ||b||, scaled norm (NaN if not verified) */
 	double backward_error;    /* ||b - A x|| / (||x|| + ||b||), scaled norm, ||A^|| taken as 1 (NaN if not verified) */
 	float ms;
+	float ms_setup;      /* of which: scaling + coarse-level setup (probing E, inverting it) */
+	int32_t coarse_dim;  /* 0 when the coarse level was not used */
 	size_t launches;
 } bfmg_pcg_result_t;
 
 /* solves A x = b over the rows [pat->row_lo, pat->row_hi); d_val is left untouched (a scaled copy is
  * made).  halo = NULL on one GPU; otherwise the vectors are local (owned + ghost rows), every rank
  * calls this collectively and d_x receives the owned rows (ghost rows of d_x are not meaningful) */
-int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res, bfmg_halo_t const* halo);
+int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res, bfmg_halo_t const* halo, bfmg_coarse_t const* coarse);
 
 /* ---- small systems: one CTA per system (batch.cu) ------------------------------------------------ */
 

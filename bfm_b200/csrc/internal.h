@@ -109,6 +109,30 @@ BFMI_HIDDEN void bfmi_part_forget(bfm_mesh_t const* mesh);
 BFMI_HIDDEN uint64_t bfmi_mesh_hash(bfm_mesh_t const* mesh);
 
 /* ---------------------------------------------------------------------------------------------
+ * coarse level of the solver (coarse.c): node aggregates, their colouring, device mirrors
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct bfmi_coarse {
+	int32_t n_agg;
+	int32_t n_colors;
+	int32_t n_local;     /* nodes of the mesh this rank assembles (owned + ghost) */
+
+	int32_t* agg;        /* [n_local] */
+	double* wgeom;       /* [n_local][2] */
+	int32_t* agg_ptr;    /* [n_agg + 1] over OWNED nodes */
+	int32_t* agg_nodes;
+	int32_t* color;      /* [n_agg] */
+	int32_t* color_nbr;  /* [n_agg][n_colors] */
+
+	bfmg_coarse_t dev;
+} bfmi_coarse_t;
+
+/* NULL when the mesh is too small or too degenerate for a coarse level (not an error) */
+BFMI_HIDDEN bfmi_coarse_t* bfmi_coarse_build(bfm_state_t* state, bfm_mesh_t const* gmesh, bfmi_part_t const* part, int32_t target_aggregates);
+BFMI_HIDDEN int bfmi_coarse_upload(bfmi_coarse_t* coarse);
+BFMI_HIDDEN void bfmi_coarse_free(bfmi_coarse_t* coarse);
+
+/* ---------------------------------------------------------------------------------------------
  * BFM_MATRIX_KIND_CSR implementation object (matrix->csr.impl)
  * ------------------------------------------------------------------------------------------- */
 

@@ -66,6 +66,7 @@ struct bfmx_job {
 	bfmg_pattern_t pat;      /* plan->dev with the owned row range */
 	bfmg_halo_t halo;
 	double* d_xg;            /* multi-GPU: the gathered global solution */
+	bfmi_coarse_t* coarse;   /* the solver's coarse level (NULL: small mesh, or disabled) */
 	bfmg_asm_tables_t tab;
 
 	double* h_nforce; /* [n_forces][nb][2], FUNKY forces sampled at the nodes */
@@ -853,6 +854,29 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 		goto fail;
 	}
 
+	/* coarse level of the solver for meshes the one-CTA path does not take: about 128 nodes per
+	 * aggregate, at most 1024 aggregates (BFM_COARSE_AGGREGATES overrides; 0 switches it off) */
+
+	if (job->part != NULL || job->plan->nb > bfmg_batch_max_rows()) {
+		char const* const env = getenv("BFM_COARSE_AGGREGATES");
+		int64_t target = (int64_t) (mesh->n_nodes / 128);
+
+		target = target > 1024 ? 1024 : target;
+
+		if (env != NULL) {
+			target = atoll(env);
+		}
+
+		if (target >= 4) {
+			job->coarse = bfmi_coarse_build(state, mesh, job->part, (int32_t) target);
+
+			if (job->coarse != NULL && bfmi_coarse_upload(job->coarse) < 0) {
+				BFMI_FAIL(state, "uploading the coarse level failed: %s", bfmg_last_error());
+				goto fail;
+			}
+		}
+	}
+
 	job->stats.n_dofs = 2 * mesh->n_nodes;
 	job->stats.n_dofs_owned = 2 * (size_t) (job->pat.row_hi - job->pat.row_lo);
 	job->stats.n_ranks = job->part != NULL ? (size_t) job->part->world : 1;
@@ -1316,6 +1340,7 @@ int bfmx_job_destroy(bfmx_job_t* job) {
 	bfmg_free(job->d_stamp);
 	bfmg_free(job->d_cval);
 	bfmg_free(job->d_xg);
+	bfmi_coarse_free(job->coarse);
 	bfmg_free(job->d_tabs);
 	bfmg_free(job->d_slice_tab);
 
@@ -1441,7 +1466,7 @@ int bfmx_job_solve(bfmx_job_t* job) {
 	}
 
 	bfmg_pcg_opts_t opts;
-	bfmg_pcg_result_t res;
+	bfmg_pcg_result_t res = {0};
 
 	bfmi_pcg_options(job->stats.n_dofs, &opts);
 
@@ -1512,7 +1537,7 @@ int bfmx_job_solve(bfmx_job_t* job) {
 		res.launches = bfmg_launch_count() - before;
 	}
 
-	else if (bfmg_pcg(&job->pat, job->d_val, job->d_b, job->d_x, &opts, &res, job->part != NULL ? &job->halo : NULL) < 0) {
+	else if (bfmg_pcg(&job->pat, job->d_val, job->d_b, job->d_x, &opts, &res, job->part != NULL ? &job->halo : NULL, job->coarse != NULL ? &job->coarse->dev : NULL) < 0) {
 		return BFMI_FAIL(job->state, "PCG failed: %s", bfmg_last_error());
 	}
 
@@ -1523,6 +1548,8 @@ int bfmx_job_solve(bfmx_job_t* job) {
 	job->stats.cg_true_rel_residual = res.true_rel_residual;
 	job->stats.cg_backward_error = res.backward_error;
 	job->stats.ms_solve = res.ms;
+	job->stats.ms_solve_setup = res.ms_setup;
+	job->stats.coarse_dim = (size_t) res.coarse_dim;
 	job->stats.kernel_launches += res.launches;
 	job->solved = true;
 

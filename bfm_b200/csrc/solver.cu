@@ -46,7 +46,8 @@ struct Scalars {
 	int32_t done;   /* 0 running, 1 converged, 2 breakdown, 3 iteration limit */
 	uint32_t ticket;
 	int32_t world;  /* ranks sharing the solve; > 1: reductions finish in k_fold */
-	int32_t pad;
+	int32_t coarse; /* 1: two-level preconditioner - beta and rho come from k_coarse_apply, not from r.r */
+	double rr;      /* r.r of the current residual (the convergence measure; equals rho without a coarse level) */
 	double part;                       /* this rank's share of the reduction in flight */
 	double gath[BFMG_DIST_MAX_RANKS];  /* every rank's share, in rank order */
 };
@@ -59,6 +60,7 @@ template <Fold WHAT>
 __device__ __forceinline__ void fold(Scalars* S, double total) {
 	if (WHAT == kFoldInit) {
 		S->rho = total;
+		S->rr = total;
 		S->bnorm2 = total;
 		S->alpha = 0;
 		S->beta = 0;
@@ -78,8 +80,13 @@ __device__ __forceinline__ void fold(Scalars* S, double total) {
 	}
 
 	else if (WHAT == kFoldRr) {
-		S->beta = total / S->rho;
-		S->rho = total;
+		S->rr = total;
+
+		if (!S->coarse) { /* z = r: beta = r'.r' / r.r */
+			S->beta = total / S->rho;
+			S->rho = total;
+		}
+
 		S->iter++;
 
 		if (!(total == total)) {
@@ -413,6 +420,7 @@ __global__ void k_restart(int n2, double2 const* __restrict__ resid, double2* __
 
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		S->rho = S->sum;
+		S->rr = S->sum;
 		S->done = S->iter >= S->max_iter ? 3 : 0;
 	}
 }
@@ -443,6 +451,12 @@ __global__ void __launch_bounds__(kBlock) k_norm2(int n2, double2 const* __restr
 		reduced<kFoldNorm2>(S, total);
 	}
 }
+
+} // namespace
+
+#include "coarse.cuh"
+
+namespace {
 
 struct Grids {
 	int spmv;
@@ -482,7 +496,7 @@ int bfmg_scale_system(bfmg_pattern_t const* pat, double const* d_val, double con
 
 extern "C" {
 
-int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res, bfmg_halo_t const* halo) {
+int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res, bfmg_halo_t const* halo, bfmg_coarse_t const* coarse) {
 	if (!bfmg_ready()) {
 		return -1;
 	}
@@ -504,9 +518,12 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	}
 
 	Grids const G = grids_for(pat);
-	int const max_grid = G.spmv > G.vec ? G.spmv : G.vec;
+	int const nc = coarse != nullptr ? coarse->nc : 0;
+	int const coarse_grid = nc / kWarpsPerBlock; /* k_coarse_apply: one warp per coarse row */
+	int const max_grid = (G.spmv > G.vec ? G.spmv : G.vec) > coarse_grid ? (G.spmv > G.vec ? G.spmv : G.vec) : coarse_grid;
+	bool use_coarse = coarse != nullptr;
 
-	/* workspace: scaled matrix, 6 vectors of nb double2, halo send buffer, partials, scalars */
+	/* workspace: scaled matrix, 6 vectors of nb double2, halo send buffer, partials, scalars, coarse level */
 
 	double2 *stop = nullptr, *sbot, *dscale, *bhat, *xhat, *r, *p, *q, *sendbuf;
 	double* partials;
@@ -515,7 +532,10 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	size_t const vec_bytes = (size_t) nb * sizeof(double2);
 	size_t const mat_bytes = (size_t) pat->n_slots * 2 * sizeof(double2);
 	size_t const send_bytes = shared ? ((size_t) halo->n_send + 1) * sizeof(double2) : 0;
-	size_t const total = mat_bytes + 6 * vec_bytes + send_bytes + (size_t) max_grid * sizeof(double) + sizeof(Scalars) + 256;
+	size_t const coarse_bytes = coarse != nullptr ? vec_bytes + ((size_t) nc * (3 + world) + (size_t) nc * nc + kGjBlock * kGjBlock + 64) * sizeof(double) : 0;
+	size_t const total = mat_bytes + 6 * vec_bytes + send_bytes + (size_t) max_grid * sizeof(double) + sizeof(Scalars) + 512 + coarse_bytes;
+
+	CoarseWork CW = {};
 
 	void* ws = nullptr;
 
@@ -537,7 +557,20 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		sendbuf = (double2*) at, at += send_bytes;
 		partials = (double*) at, at += (size_t) max_grid * sizeof(double);
 		at = (char*) (((uintptr_t) at + 127) & ~(uintptr_t) 127);
-		S = (Scalars*) at;
+		S = (Scalars*) at, at += sizeof(Scalars);
+		at = (char*) (((uintptr_t) at + 127) & ~(uintptr_t) 127);
+
+		if (coarse != nullptr) {
+			CW.C = *coarse;
+			CW.wscale = (double2*) at, at += vec_bytes;
+			CW.gpart = (double*) at, at += (size_t) nc * sizeof(double);
+			CW.ggath = (double*) at, at += (size_t) nc * world * sizeof(double);
+			CW.g = shared ? (double*) at : CW.gpart, at += (size_t) nc * sizeof(double);
+			CW.mu = (double*) at, at += (size_t) nc * sizeof(double);
+			CW.E = (double*) at, at += (size_t) nc * nc * sizeof(double);
+			CW.P = (double*) at, at += kGjBlock * kGjBlock * sizeof(double);
+			CW.bad = (int32_t*) at;
+		}
 	}
 
 	double2 const* const vtop = (double2 const*) d_val;
@@ -554,6 +587,17 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	/* several GPUs: spread S->part to every rank's S->gath, then fold (k_fold<WHAT>) */
 #define SHARE(WHAT) (!shared || (bfmg_dist_allgather_f64(&S->part, S->gath, 1) == 0 && BFMG_LAUNCH(k_fold<WHAT>, 1, 1, 0, S) == 0))
 #define HALO(vec) (!shared || bfmg_dist_halo(halo, (double*) (vec), (double*) sendbuf) == 0)
+
+	/* g = W^T vec: per-aggregate sums over the owned rows, completed across ranks in rank order */
+#define RESTRICT(vec, obey) ( \
+		BFMG_LAUNCH(k_restrict, CW.C.n_agg, kBlock, 0, CW.C, CW.wscale, (double2 const*) (vec), CW.gpart, S, (obey)) == 0 && \
+		(!shared || (bfmg_dist_allgather_f64(CW.gpart, CW.ggath, nc) == 0 && BFMG_LAUNCH(k_coarse_fold, (nc + kBlock - 1) / kBlock, kBlock, 0, nc, world, CW.ggath, CW.g) == 0)))
+
+	/* p = z + beta p with z = r + W E^-1 W^T r (FIRST: beta = 0) */
+#define PRECONDITION(FIRST, obey) ( \
+		RESTRICT(r, (obey)) && \
+		BFMG_LAUNCH(k_coarse_apply<FIRST>, coarse_grid, kBlock, 0, nc, CW.E, CW.g, CW.mu, partials, S) == 0 && \
+		BFMG_LAUNCH(k_update_p_coarse, G.vec, kBlock, 0, n_own, lo, CW.C, CW.wscale, CW.mu, r, p, S, (obey)) == 0)
 
 	{
 		Scalars init = {};
@@ -572,11 +616,77 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	if (
 		BFMG_LAUNCH(k_jacobi, (nb + kBlock - 1) / kBlock, kBlock, 0, *pat, vtop, vbot, (double2 const*) d_b, dscale, bhat) < 0 ||
 		!HALO(dscale) ||
-		BFMG_LAUNCH(k_scale_matrix, G.spmv, kBlock, 0, *pat, vtop, vbot, dscale, stop, sbot) < 0 ||
-		BFMG_LAUNCH(k_cg_init, G.vec, kBlock, 0, n_own, bhat + lo, xhat + lo, r + lo, p + lo, partials, S, opts->tol, opts->max_iter) < 0 ||
-		!SHARE(kFoldInit)
+		BFMG_LAUNCH(k_scale_matrix, G.spmv, kBlock, 0, *pat, vtop, vbot, dscale, stop, sbot) < 0
 	) {
 		goto out;
+	}
+
+	/* coarse operator E = W^T A^ W by colour probing (p, q are free until k_cg_init), then E^-1 */
+
+	if (use_coarse) {
+		if (
+			BFMG_LAUNCH(k_wscale, (nb + kBlock - 1) / kBlock, kBlock, 0, nb, dscale, CW.wscale) < 0 ||
+			BFMG_CHECK(cudaMemsetAsync(CW.gpart, 0, coarse_bytes - vec_bytes, bfmg_stream())) < 0
+		) {
+			goto out;
+		}
+
+		for (int c = 0; c < CW.C.n_colors; c++) {
+			for (int m = 0; m < 3; m++) {
+				if (
+					BFMG_LAUNCH(k_probe_vector, (nb + kBlock - 1) / kBlock, kBlock, 0, nb, CW.C, CW.wscale, c, m, p) < 0 ||
+					BFMG_LAUNCH(k_spmv<kPlain>, G.spmv, kBlock, 0, *pat, stop, sbot, p, q, bhat, partials, S) < 0 ||
+					!RESTRICT(q, false) ||
+					BFMG_LAUNCH(k_probe_scatter, (CW.C.n_agg + kBlock - 1) / kBlock, kBlock, 0, CW.C, c, m, CW.g, CW.E) < 0
+				) {
+					goto out;
+				}
+			}
+		}
+
+		if (3 * CW.C.n_agg < nc && BFMG_LAUNCH(k_coarse_pad, 1, kBlock, 0, CW.C, CW.E) < 0) {
+			goto out;
+		}
+
+		int32_t bad = 0;
+
+		if (
+			coarse_invert(CW) < 0 ||
+			BFMG_CHECK(cudaMemcpyAsync(&bad, CW.bad, sizeof bad, cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
+			BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0
+		) {
+			goto out;
+		}
+
+		if (bad) {
+			/* E came out not positive definite (degenerate aggregates): solve with the diagonal
+			 * preconditioner alone.  Identical on every rank: E is replicated bit for bit. */
+			use_coarse = false;
+		}
+
+		else {
+			int32_t const one = 1;
+
+			if (BFMG_CHECK(cudaMemcpyAsync(&S->coarse, &one, sizeof one, cudaMemcpyHostToDevice, bfmg_stream())) < 0 || BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0) {
+				goto out;
+			}
+
+			res->coarse_dim = 3 * CW.C.n_agg;
+		}
+	}
+
+	{
+		int const t_setup = bfmg_tick();
+
+		if (
+			BFMG_LAUNCH(k_cg_init, G.vec, kBlock, 0, n_own, bhat + lo, xhat + lo, r + lo, p + lo, partials, S, opts->tol, opts->max_iter) < 0 ||
+			!SHARE(kFoldInit) ||
+			(use_coarse && !PRECONDITION(true, false))
+		) {
+			goto out;
+		}
+
+		res->ms_setup = bfmg_lap(t0, t_setup);
 	}
 
 	{
@@ -599,7 +709,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 						!SHARE(kFoldPq) ||
 						BFMG_LAUNCH(k_update_xr, G.vec, kBlock, 0, n_own, p + lo, q + lo, xhat + lo, r + lo, partials, S) < 0 ||
 						!SHARE(kFoldRr) ||
-						BFMG_LAUNCH(k_update_p, G.vec, kBlock, 0, n_own, r + lo, p + lo, S) < 0
+						(use_coarse ? !PRECONDITION(false, true) : BFMG_LAUNCH(k_update_p, G.vec, kBlock, 0, n_own, r + lo, p + lo, S) < 0)
 					) {
 						goto out;
 					}
@@ -634,7 +744,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 			Scalars const last = h_S[(launched_chunks - 1) & 1];
 
 			res->iterations = last.iter;
-			res->rel_residual = last.bnorm2 > 0 ? sqrt(last.rho / last.bnorm2) : 0;
+			res->rel_residual = last.bnorm2 > 0 ? sqrt(last.rr / last.bnorm2) : 0;
 			res->converged = last.done == 1 ? 1 : (last.done == 3 ? 0 : -1);
 			res->restarts = restarts;
 
@@ -686,7 +796,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 			/* residual replacement: restart CG from the true residual */
 
-			if (BFMG_LAUNCH(k_restart, G.vec, kBlock, 0, n_own, q + lo, r + lo, p + lo, S) < 0) {
+			if (BFMG_LAUNCH(k_restart, G.vec, kBlock, 0, n_own, q + lo, r + lo, p + lo, S) < 0 || (use_coarse && !PRECONDITION(true, false))) {
 				goto out;
 			}
 
@@ -710,6 +820,8 @@ out:
 
 #undef SHARE
 #undef HALO
+#undef RESTRICT
+#undef PRECONDITION
 
 	bfmg_free(ws);
 	return rv;

@@ -37,6 +37,8 @@ class Stats(C.Structure):  # bfmx_stats_t
 		("n_dofs_owned", C.c_size_t),
 		("n_ranks", C.c_size_t),
 		("halo_bytes_per_exchange", C.c_size_t),
+		("coarse_dim", C.c_size_t),
+		("ms_solve_setup", C.c_float),
 	]
 
 	def as_dict(self) -> dict:
@@ -62,6 +64,7 @@ PROTOTYPES = {
 	"bfmx_dist_finalize": (_int, []),
 	"bfmx_dist_rank": (_int, []),
 	"bfmx_dist_world": (_int, []),
+	"bfmx_coarse_plan": (_int, [_P(abi.Mesh), _int, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
 	"bfmx_partition_sizes": (_int, [_P(abi.Mesh), _int, _int, _P(PartitionInfo)]),
 	"bfmx_partition_copy": (_int, [_P(abi.Mesh), _int, _int, abi.c_size_t_p, abi.c_size_t_p, abi.c_size_t_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
 	"bfmx_device_available": (_int, []),

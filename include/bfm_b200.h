@@ -67,6 +67,9 @@ typedef struct {
 	size_t n_dofs_owned;
 	size_t n_ranks;
 	size_t halo_bytes_per_exchange;
+
+	size_t coarse_dim;         /* dimension of the solver's coarse space (3 rigid-body modes per aggregate); 0 = none */
+	float ms_solve_setup;      /* part of ms_solve spent scaling the matrix and building the coarse operator */
 } bfmx_stats_t;
 
 /* stats of the most recent bfm_sim_run instance / bfm_matrix_solve / job stage in this process */
@@ -156,6 +159,12 @@ typedef struct {
 
 int bfmx_partition_sizes(bfm_mesh_t* mesh, int rank, int world, bfmx_partition_info_t* out);
 int bfmx_partition_copy(bfm_mesh_t* mesh, int rank, int world, size_t* local_to_global, size_t* local_elems, size_t* elem_to_global, int32_t* neighbours, int32_t* recv_begin, int32_t* recv_count, int32_t* send_ptr, int32_t* send_idx);
+
+/* ---- solver internals open to inspection ------------------------------------------------------------- */
+
+/* the coarse level the solver would build for a mesh with `target` aggregates (host-only): aggregate of
+ * every node, colour of every aggregate; *n_aggregates = 0 when the mesh gets none */
+int bfmx_coarse_plan(bfm_mesh_t* mesh, int target, int32_t* n_aggregates, int32_t* n_colors, int32_t* node_aggregate, int32_t* aggregate_color);
 
 /* ---- matrices ---------------------------------------------------------------------------------------- */
 

@@ -305,3 +305,44 @@ def test_batch_rejects_mixed_element_kinds_and_big_systems(lib, monkeypatch):
 	big = cases.build("gear60", lib)  # 8205 nodes > bfmx_batch_max_nodes()
 	assert big.mesh.n_nodes > lib.lib.bfmx_batch_max_nodes()
 	assert lib.lib.bfmx_sim_run_batch(ext._sim_array([big.sim]), 1) == -1
+
+
+# ---- the solver's coarse level (rigid-body modes of node aggregates) -----------------------------------
+
+
+@pytest.mark.parametrize("name", ["gear60", "plate_80x20", "bridge_dam"])
+def test_coarse_level_changes_speed_not_answers(name, lib, golden, monkeypatch):
+	"""general (multi-kernel) path with and without the two-level preconditioner: same displacements to
+	the north star's tolerance, far fewer iterations with it"""
+
+	monkeypatch.setenv("BFM_ONE_CTA", "0")
+	case = cases.build(name, lib)
+	want = golden[f"{name}/effects"]
+	runs = {}
+
+	for aggregates in ("0", "24"):
+		monkeypatch.setenv("BFM_COARSE_AGGREGATES", aggregates)
+		case.sim.run()
+		stats = ext.last_stats(lib)
+
+		assert stats["cg_converged"] == 1 and stats["cg_rel_residual"] <= 1e-12
+		assert rel_l2(case.instance.effects, want) <= REL_L2, (name, aggregates)
+
+		runs[aggregates] = stats
+
+	assert runs["0"]["coarse_dim"] == 0 and runs["24"]["coarse_dim"] > 0
+	assert runs["24"]["cg_iterations"] * 2 < runs["0"]["cg_iterations"], (runs["0"]["cg_iterations"], runs["24"]["cg_iterations"])
+
+
+def test_coarse_level_is_deterministic(lib, monkeypatch):
+	monkeypatch.setenv("BFM_ONE_CTA", "0")
+	monkeypatch.setenv("BFM_COARSE_AGGREGATES", "32")
+
+	case = cases.build("gear60", lib)
+	outs = []
+
+	for _ in range(2):
+		case.sim.run()
+		outs.append(case.instance.effects.copy())
+
+	assert np.array_equal(outs[0], outs[1])

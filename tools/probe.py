@@ -26,7 +26,7 @@ for nx, ny in sizes:
 	stored = s["n_slots"] * 36 + n // 2 * 32
 	it_bytes = stored + 72 * n  # update_xr 48 B/DOF + update_p 24 B/DOF
 	print(f"{nx}x{ny}: n={n} mesh {t_mesh:.2f}s create {t_create:.2f}s (plan {s['ms_plan']:.0f} ms) upload {s['ms_upload']:.2f} ms asm {s['ms_assemble']:.3f} ms bc {s['ms_bc']:.3f} ms "
-	      f"solve {s['ms_solve']:.1f} ms wall {wall*1e3:.1f} ms iters {s['cg_iterations']} res {s['cg_rel_residual']:.2e} true {s['cg_true_rel_residual']:.2e} restarts {s['cg_restarts']} "
+	      f"solve {s["ms_solve"]:.1f} ms (setup {s["ms_solve_setup"]:.1f}, coarse {s["coarse_dim"]}) wall {wall*1e3:.1f} ms iters {s['cg_iterations']} res {s['cg_rel_residual']:.2e} true {s['cg_true_rel_residual']:.2e} restarts {s['cg_restarts']} "
 	      f"us/iter {s['ms_solve']*1e3/max(s['cg_iterations'],1):.1f} spmv {spmv*1e3:.1f} us -> canonical {canon/spmv/1e6:.0f} GB/s stored {stored/spmv/1e6:.0f} GB/s; iter stored-bytes {it_bytes/(s['ms_solve']/max(s['cg_iterations'],1))/1e6:.0f} GB/s", flush=True)
 	t = time.time(); case.sim.run(); print(f"   sim.run wall {time.time()-t:.3f}s", ext.last_stats(lib)["ms_download"], flush=True)
 	del job, case, mesh
