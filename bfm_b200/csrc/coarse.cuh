@@ -23,7 +23,9 @@ constexpr int kGjBlock = 32;
 
 struct CoarseWork {
 	bfmg_coarse_t C;      /* device pointers of the plan */
-	double2* wscale;      /* [nb] sqrt of the diagonal = 1 / dscale */
+	float4* wrow;         /* [nb] (sqrt a_00, sqrt a_11, dx, dy) of every local row, in FP32: W only shapes the
+	                       * preconditioner (E is built from the SAME rounded W, so M^-1 stays symmetric positive
+	                       * definite); halving its bytes matters, its last digits do not.  Arithmetic stays FP64. */
 	double* gpart;        /* [nc] this rank's W^T r */
 	double* ggath;        /* [world * nc] all ranks' (several GPUs only) */
 	double* g;            /* [nc] the complete W^T r (aliases gpart on one GPU) */
@@ -33,17 +35,18 @@ struct CoarseWork {
 	int32_t* bad;         /* set when a pivot is not positive: E not SPD, coarse level unusable */
 };
 
-__global__ void k_wscale(int nb, double2 const* __restrict__ dscale, double2* __restrict__ wscale) {
+__global__ void k_wrow(int nb, double2 const* __restrict__ dscale, double2 const* __restrict__ wgeom, float4* __restrict__ wrow) {
 	int const i = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (i < nb) {
 		double2 const s = dscale[i];
-		wscale[i] = make_double2(1.0 / s.x, 1.0 / s.y);
+		double2 const d = wgeom[i];
+		wrow[i] = make_float4((float) (1.0 / s.x), (float) (1.0 / s.y), (float) d.x, (float) d.y);
 	}
 }
 
 /* gpart[3 g + k] = sum over the owned nodes a of aggregate g of (R_a^T S_a v_a)_k; one CTA per aggregate */
-__global__ void __launch_bounds__(kBlock) k_restrict(bfmg_coarse_t C, double2 const* __restrict__ wscale, double2 const* __restrict__ v, double* __restrict__ gpart, Scalars const* S, bool obey_done) {
+__global__ void __launch_bounds__(kBlock) k_restrict(bfmg_coarse_t C, float4 const* __restrict__ wrow, double2 const* __restrict__ v, double* __restrict__ gpart, Scalars const* S, bool obey_done) {
 	if (obey_done && S->done) {
 		return;
 	}
@@ -53,22 +56,20 @@ __global__ void __launch_bounds__(kBlock) k_restrict(bfmg_coarse_t C, double2 co
 	int const g = blockIdx.x;
 	int const beg = C.agg_ptr[g];
 	int const end = C.agg_ptr[g + 1];
-	double2 const* const wgeom = (double2 const*) C.wgeom;
 
 	double s0 = 0, s1 = 0, s2 = 0;
 
 	for (int i = beg + threadIdx.x; i < end; i += kBlock) {
 		int const a = C.agg_nodes[i];
 		double2 const vv = v[a];
-		double2 const w = wscale[a];
-		double2 const d = wgeom[a];
+		float4 const w = wrow[a];
 
-		double const t0 = w.x * vv.x;
-		double const t1 = w.y * vv.y;
+		double const t0 = (double) w.x * vv.x;
+		double const t1 = (double) w.y * vv.y;
 
 		s0 += t0;
 		s1 += t1;
-		s2 += d.x * t1 - d.y * t0;
+		s2 += (double) w.z * t1 - (double) w.w * t0;
 	}
 
 	s0 = warp_sum(s0);
@@ -124,13 +125,25 @@ __global__ void __launch_bounds__(kBlock) k_coarse_apply(int nc, double const* _
 
 	if (row < nc) {
 		double const* const e = Einv + (size_t) row * nc;
-		double t = 0;
 
-		for (int j = lane; j < nc; j += kWarp) {
-			t = fma(e[j], __ldg(&g[j]), t);
+		/* four independent chains per lane (nc % 32 == 0; the tail loop takes what is left of 128):
+		 * the row is 24 KB at nc = 3072 and one dependent chain would be pure load latency */
+
+		double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+		int j = lane;
+
+		for (; j + 3 * kWarp < nc; j += 4 * kWarp) {
+			t0 = fma(ld_stream(&e[j]), __ldg(&g[j]), t0);
+			t1 = fma(ld_stream(&e[j + kWarp]), __ldg(&g[j + kWarp]), t1);
+			t2 = fma(ld_stream(&e[j + 2 * kWarp]), __ldg(&g[j + 2 * kWarp]), t2);
+			t3 = fma(ld_stream(&e[j + 3 * kWarp]), __ldg(&g[j + 3 * kWarp]), t3);
 		}
 
-		t = warp_sum(t);
+		for (; j < nc; j += kWarp) {
+			t0 = fma(ld_stream(&e[j]), __ldg(&g[j]), t0);
+		}
+
+		double t = warp_sum((t0 + t1) + (t2 + t3));
 
 		if (lane == 0) {
 			mu[row] = t;
@@ -149,19 +162,17 @@ __global__ void __launch_bounds__(kBlock) k_coarse_apply(int nc, double const* _
 }
 
 /* p = r + W mu + beta p */
-__global__ void __launch_bounds__(kBlock) k_update_p_coarse(int n2, int row0, bfmg_coarse_t C, double2 const* __restrict__ wscale, double const* __restrict__ mu, double2 const* __restrict__ r, double2* __restrict__ p, Scalars const* S, bool obey_done) {
+__global__ void __launch_bounds__(kBlock) k_update_p_coarse(int n2, int row0, bfmg_coarse_t C, float4 const* __restrict__ wrow, double const* __restrict__ mu, double2 const* __restrict__ r, double2* __restrict__ p, Scalars const* S, bool obey_done) {
 	if (obey_done && S->done) {
 		return;
 	}
 
 	double const beta = S->beta;
-	double2 const* const wgeom = (double2 const*) C.wgeom;
 
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
 		int const a = row0 + i;
 		int const g = C.agg[a];
-		double2 const w = wscale[a];
-		double2 const d = wgeom[a];
+		float4 const w = wrow[a];
 		double2 const rv = r[a];
 		double2 pv = p[a];
 
@@ -169,8 +180,8 @@ __global__ void __launch_bounds__(kBlock) k_update_p_coarse(int n2, int row0, bf
 		double const m1 = __ldg(&mu[3 * g + 1]);
 		double const m2 = __ldg(&mu[3 * g + 2]);
 
-		double const z0 = rv.x + w.x * (m0 - d.y * m2);
-		double const z1 = rv.y + w.y * (m1 + d.x * m2);
+		double const z0 = rv.x + (double) w.x * (m0 - (double) w.w * m2);
+		double const z1 = rv.y + (double) w.y * (m1 + (double) w.z * m2);
 
 		pv.x = fma(beta, pv.x, z0);
 		pv.y = fma(beta, pv.y, z1);
@@ -182,7 +193,7 @@ __global__ void __launch_bounds__(kBlock) k_update_p_coarse(int n2, int row0, bf
 /* ---- setup: probing ------------------------------------------------------------------------------ */
 
 /* v = mode m of every aggregate of colour c, 0 elsewhere (all local rows, ghosts included: no exchange needed) */
-__global__ void k_probe_vector(int nb, bfmg_coarse_t C, double2 const* __restrict__ wscale, int color, int mode, double2* __restrict__ v) {
+__global__ void k_probe_vector(int nb, bfmg_coarse_t C, float4 const* __restrict__ wrow, int color, int mode, double2* __restrict__ v) {
 	int const a = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (a >= nb) {
@@ -192,11 +203,10 @@ __global__ void k_probe_vector(int nb, bfmg_coarse_t C, double2 const* __restric
 	double2 out = make_double2(0, 0);
 
 	if (C.color[C.agg[a]] == color) {
-		double2 const w = wscale[a];
-		double2 const d = ((double2 const*) C.wgeom)[a];
+		float4 const w = wrow[a];
 
-		out.x = mode == 0 ? w.x : (mode == 2 ? -w.x * d.y : 0);
-		out.y = mode == 1 ? w.y : (mode == 2 ? w.y * d.x : 0);
+		out.x = mode == 0 ? (double) w.x : (mode == 2 ? -((double) w.x * (double) w.w) : 0);
+		out.y = mode == 1 ? (double) w.y : (mode == 2 ? (double) w.y * (double) w.z : 0);
 	}
 
 	v[a] = out;

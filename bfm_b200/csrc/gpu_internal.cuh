@@ -65,6 +65,12 @@ __device__ __forceinline__ double2 ld_stream(double2 const* p) {
 	return v;
 }
 
+__device__ __forceinline__ double ld_stream(double const* p) {
+	double v;
+	asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+	return v;
+}
+
 __device__ __forceinline__ int ld_stream(int const* p) {
 	int v;
 	asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));

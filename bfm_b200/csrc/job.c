@@ -699,6 +699,14 @@ static int build_ops(bfmx_job_t* job) {
 
 /* ---- job life cycle -------------------------------------------------------------------------------- */
 
+/* a small mesh on one GPU: the whole PCG runs inside one CTA (batch.cu) instead of three launches per
+ * iteration; BFM_ONE_CTA=0 forces the general path */
+static bool takes_one_cta(bfmx_job_t const* job) {
+	char const* const env = getenv("BFM_ONE_CTA");
+
+	return job->n_sys == 0 && job->part == NULL && job->plan->nb <= bfmg_batch_max_rows() && (env == NULL || atoi(env) != 0);
+}
+
 /* device buffers of a job whose plan, tables and work lists are ready */
 static int job_alloc_device(bfmx_job_t* job, size_t table_forces) {
 	bfm_state_t* const state = job->state;
@@ -857,7 +865,7 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 	/* coarse level of the solver for meshes the one-CTA path does not take: about 128 nodes per
 	 * aggregate, at most 1024 aggregates (BFM_COARSE_AGGREGATES overrides; 0 switches it off) */
 
-	if (job->part != NULL || job->plan->nb > bfmg_batch_max_rows()) {
+	if (!takes_one_cta(job)) {
 		char const* const env = getenv("BFM_COARSE_AGGREGATES");
 		int64_t target = (int64_t) (mesh->n_nodes / 128);
 
@@ -1470,9 +1478,6 @@ int bfmx_job_solve(bfmx_job_t* job) {
 
 	bfmi_pcg_options(job->stats.n_dofs, &opts);
 
-	/* a small mesh on one GPU: the whole PCG runs inside one CTA (batch.cu) instead of three launches
-	 * per iteration; BFM_ONE_CTA=0 forces the general path */
-
 	if (job->n_sys > 0) {
 		size_t const before = bfmg_launch_count();
 		float ms = 0;
@@ -1517,9 +1522,7 @@ int bfmx_job_solve(bfmx_job_t* job) {
 		return 0;
 	}
 
-	char const* const env = getenv("BFM_ONE_CTA");
-
-	if (job->part == NULL && job->plan->nb <= bfmg_batch_max_rows() && (env == NULL || atoi(env) != 0)) {
+	if (takes_one_cta(job)) {
 		bfmg_batch_range_t const range = {0, job->plan->nb};
 		bfmg_batch_status_t st;
 		size_t const before = bfmg_launch_count();

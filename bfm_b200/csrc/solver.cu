@@ -562,7 +562,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 		if (coarse != nullptr) {
 			CW.C = *coarse;
-			CW.wscale = (double2*) at, at += vec_bytes;
+			CW.wrow = (float4*) at, at += vec_bytes;
 			CW.gpart = (double*) at, at += (size_t) nc * sizeof(double);
 			CW.ggath = (double*) at, at += (size_t) nc * world * sizeof(double);
 			CW.g = shared ? (double*) at : CW.gpart, at += (size_t) nc * sizeof(double);
@@ -590,14 +590,14 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 	/* g = W^T vec: per-aggregate sums over the owned rows, completed across ranks in rank order */
 #define RESTRICT(vec, obey) ( \
-		BFMG_LAUNCH(k_restrict, CW.C.n_agg, kBlock, 0, CW.C, CW.wscale, (double2 const*) (vec), CW.gpart, S, (obey)) == 0 && \
+		BFMG_LAUNCH(k_restrict, CW.C.n_agg, kBlock, 0, CW.C, CW.wrow, (double2 const*) (vec), CW.gpart, S, (obey)) == 0 && \
 		(!shared || (bfmg_dist_allgather_f64(CW.gpart, CW.ggath, nc) == 0 && BFMG_LAUNCH(k_coarse_fold, (nc + kBlock - 1) / kBlock, kBlock, 0, nc, world, CW.ggath, CW.g) == 0)))
 
 	/* p = z + beta p with z = r + W E^-1 W^T r (FIRST: beta = 0) */
 #define PRECONDITION(FIRST, obey) ( \
 		RESTRICT(r, (obey)) && \
 		BFMG_LAUNCH(k_coarse_apply<FIRST>, coarse_grid, kBlock, 0, nc, CW.E, CW.g, CW.mu, partials, S) == 0 && \
-		BFMG_LAUNCH(k_update_p_coarse, G.vec, kBlock, 0, n_own, lo, CW.C, CW.wscale, CW.mu, r, p, S, (obey)) == 0)
+		BFMG_LAUNCH(k_update_p_coarse, G.vec, kBlock, 0, n_own, lo, CW.C, CW.wrow, CW.mu, r, p, S, (obey)) == 0)
 
 	{
 		Scalars init = {};
@@ -625,7 +625,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 	if (use_coarse) {
 		if (
-			BFMG_LAUNCH(k_wscale, (nb + kBlock - 1) / kBlock, kBlock, 0, nb, dscale, CW.wscale) < 0 ||
+			BFMG_LAUNCH(k_wrow, (nb + kBlock - 1) / kBlock, kBlock, 0, nb, dscale, (double2 const*) CW.C.wgeom, CW.wrow) < 0 ||
 			BFMG_CHECK(cudaMemsetAsync(CW.gpart, 0, coarse_bytes - vec_bytes, bfmg_stream())) < 0
 		) {
 			goto out;
@@ -634,7 +634,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		for (int c = 0; c < CW.C.n_colors; c++) {
 			for (int m = 0; m < 3; m++) {
 				if (
-					BFMG_LAUNCH(k_probe_vector, (nb + kBlock - 1) / kBlock, kBlock, 0, nb, CW.C, CW.wscale, c, m, p) < 0 ||
+					BFMG_LAUNCH(k_probe_vector, (nb + kBlock - 1) / kBlock, kBlock, 0, nb, CW.C, CW.wrow, c, m, p) < 0 ||
 					BFMG_LAUNCH(k_spmv<kPlain>, G.spmv, kBlock, 0, *pat, stop, sbot, p, q, bhat, partials, S) < 0 ||
 					!RESTRICT(q, false) ||
 					BFMG_LAUNCH(k_probe_scatter, (CW.C.n_agg + kBlock - 1) / kBlock, kBlock, 0, CW.C, c, m, CW.g, CW.E) < 0
