@@ -195,7 +195,7 @@ def workload_config(nx: int, ny: int, gpus: int) -> dict:
 		"cells": f"{nx}x{ny}",
 		"n_dofs": 2 * (nx + 1) * (ny + 1),
 		"element": "P1 triangle, 3-point Gauss",
-		"solver": "FP64 PCG, Jacobi scaling + rigid-body-mode coarse level (<= 1024 aggregates), relative residual 1e-12",
+		"solver": "FP64 PCG, Jacobi scaling + rigid-body-mode coarse level (<= 2048 aggregates), relative residual 1e-12",
 		"partition": "none" if gpus == 1 else f"{gpus} contiguous node-row blocks, halo exchange + dot-product reductions over NVLink",
 		"l2": "inputs larger than L2 (matrix ~1 GB at the default size); no flush needed",
 	}

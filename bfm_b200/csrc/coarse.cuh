@@ -111,44 +111,60 @@ __global__ void k_coarse_fold(int nc, int world, double const* __restrict__ ggat
 	}
 }
 
-/* mu = E^-1 g (one warp per row), then in the last CTA: rz = r.r + g.mu;  beta = rz / rho (0 when FIRST);  rho = rz */
+/* mu = E^-1 g, then in the last CTA: rz = r.r + g.mu;  beta = rz / rho (0 when FIRST);  rho = rz.
+ * A CTA takes kCoarseRows rows, four warps per row (a quarter of the row each, four independent FMA
+ * chains per lane): E^-1 is 75 MB at nc = 3072 and one chain per row would be pure load latency.
+ * Partial sums are combined in a fixed order. */
+constexpr int kCoarseRows = kWarpsPerBlock / 4;
+
 template <bool FIRST>
 __global__ void __launch_bounds__(kBlock) k_coarse_apply(int nc, double const* __restrict__ Einv, double const* __restrict__ g, double* __restrict__ mu, double* __restrict__ partials, Scalars* S) {
 	if (!FIRST && S->done) {
 		return;
 	}
 
-	int const lane = threadIdx.x & (kWarp - 1);
-	int const row = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+	__shared__ double quarter_sum[kWarpsPerBlock];
 
-	double acc = 0;
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = threadIdx.x / kWarp;
+	int const row = blockIdx.x * kCoarseRows + warp / 4;
+	int const span = ((nc + 3) / 4 + kWarp - 1) / kWarp * kWarp; /* columns per quarter, a multiple of 32 */
+	int const j_end = min(nc, (warp % 4 + 1) * span);
+
+	double t = 0;
 
 	if (row < nc) {
 		double const* const e = Einv + (size_t) row * nc;
-
-		/* four independent chains per lane (nc % 32 == 0; the tail loop takes what is left of 128):
-		 * the row is 24 KB at nc = 3072 and one dependent chain would be pure load latency */
-
 		double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-		int j = lane;
+		int j = (warp % 4) * span + lane;
 
-		for (; j + 3 * kWarp < nc; j += 4 * kWarp) {
+		for (; j + 3 * kWarp < j_end; j += 4 * kWarp) {
 			t0 = fma(ld_stream(&e[j]), __ldg(&g[j]), t0);
 			t1 = fma(ld_stream(&e[j + kWarp]), __ldg(&g[j + kWarp]), t1);
 			t2 = fma(ld_stream(&e[j + 2 * kWarp]), __ldg(&g[j + 2 * kWarp]), t2);
 			t3 = fma(ld_stream(&e[j + 3 * kWarp]), __ldg(&g[j + 3 * kWarp]), t3);
 		}
 
-		for (; j < nc; j += kWarp) {
+		for (; j < j_end; j += kWarp) {
 			t0 = fma(ld_stream(&e[j]), __ldg(&g[j]), t0);
 		}
 
-		double t = warp_sum((t0 + t1) + (t2 + t3));
+		t = warp_sum((t0 + t1) + (t2 + t3));
+	}
 
-		if (lane == 0) {
-			mu[row] = t;
-			acc = t * g[row];
-		}
+	if (lane == 0) {
+		quarter_sum[warp] = t;
+	}
+
+	__syncthreads();
+
+	double acc = 0;
+
+	if (lane == 0 && warp % 4 == 0 && row < nc) {
+		double const m = (quarter_sum[warp] + quarter_sum[warp + 1]) + (quarter_sum[warp + 2] + quarter_sum[warp + 3]);
+
+		mu[row] = m;
+		acc = m * g[row];
 	}
 
 	double total;

@@ -863,13 +863,15 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 	}
 
 	/* coarse level of the solver for meshes the one-CTA path does not take: about 128 nodes per
-	 * aggregate, at most 1024 aggregates (BFM_COARSE_AGGREGATES overrides; 0 switches it off) */
+	 * aggregate, at most 2048 aggregates - beyond that the replicated dense E^-1 (8 * (3 n_agg)^2 bytes
+	 * per iteration, n_agg^3 to invert) costs more than the iterations it saves
+	 * (BFM_COARSE_AGGREGATES overrides; 0 switches the coarse level off) */
 
 	if (!takes_one_cta(job)) {
 		char const* const env = getenv("BFM_COARSE_AGGREGATES");
 		int64_t target = (int64_t) (mesh->n_nodes / 128);
 
-		target = target > 1024 ? 1024 : target;
+		target = target > 2048 ? 2048 : target;
 
 		if (env != NULL) {
 			target = atoll(env);

@@ -519,7 +519,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 	Grids const G = grids_for(pat);
 	int const nc = coarse != nullptr ? coarse->nc : 0;
-	int const coarse_grid = nc / kWarpsPerBlock; /* k_coarse_apply: one warp per coarse row */
+	int const coarse_grid = (nc + kCoarseRows - 1) / kCoarseRows; /* k_coarse_apply: kCoarseRows rows per CTA */
 	int const max_grid = (G.spmv > G.vec ? G.spmv : G.vec) > coarse_grid ? (G.spmv > G.vec ? G.spmv : G.vec) : coarse_grid;
 	bool use_coarse = coarse != nullptr;
 
