@@ -94,20 +94,40 @@ __global__ void __launch_bounds__(kBlock) k_restrict(bfmg_coarse_t C, float4 con
 
 		gpart[3 * g + threadIdx.x] = t;
 	}
+
+	/* several GPUs: this rank's share of the pending scalar reduction (r.r) rides along in slot nc, so that
+	 * one all-gather serves both */
+
+	if (g == 0 && threadIdx.x == 32 && S->world > 1) {
+		gpart[C.nc] = S->part;
+	}
 }
 
-/* several GPUs: g[j] = sum over ranks (in rank order) of ggath[r][j] */
-__global__ void k_coarse_fold(int nc, int world, double const* __restrict__ ggath, double* __restrict__ g) {
+/* several GPUs: g[j] = sum over ranks (in rank order) of ggath[r][j]; rows are kCoarseStride = nc + 8 long,
+ * slot nc holding the ranks' shares of r.r, folded here too when FOLD_RR (k_fold<kFoldRr>'s job otherwise) */
+template <bool FOLD_RR>
+__global__ void k_coarse_fold(int nc, int world, double const* __restrict__ ggath, double* __restrict__ g, Scalars* S) {
 	int const j = blockIdx.x * blockDim.x + threadIdx.x;
+	size_t const stride = (size_t) nc + 8;
 
 	if (j < nc) {
 		double t = 0;
 
 		for (int r = 0; r < world; r++) {
-			t += ggath[(size_t) r * nc + j];
+			t += ggath[r * stride + j];
 		}
 
 		g[j] = t;
+	}
+
+	if (FOLD_RR && j == nc && !S->done) {
+		double total = 0;
+
+		for (int r = 0; r < world; r++) {
+			total += ggath[r * stride + nc];
+		}
+
+		fold<kFoldRr>(S, total);
 	}
 }
 

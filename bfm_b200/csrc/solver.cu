@@ -532,7 +532,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	size_t const vec_bytes = (size_t) nb * sizeof(double2);
 	size_t const mat_bytes = (size_t) pat->n_slots * 2 * sizeof(double2);
 	size_t const send_bytes = shared ? ((size_t) halo->n_send + 1) * sizeof(double2) : 0;
-	size_t const coarse_bytes = coarse != nullptr ? vec_bytes + ((size_t) nc * (3 + world) + (size_t) nc * nc + kGjBlock * kGjBlock + 64) * sizeof(double) : 0;
+	size_t const coarse_bytes = coarse != nullptr ? vec_bytes + (((size_t) nc + 8) * (3 + world) + (size_t) nc * nc + kGjBlock * kGjBlock + 64) * sizeof(double) : 0;
 	size_t const total = mat_bytes + 6 * vec_bytes + send_bytes + (size_t) max_grid * sizeof(double) + sizeof(Scalars) + 512 + coarse_bytes;
 
 	CoarseWork CW = {};
@@ -563,10 +563,10 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		if (coarse != nullptr) {
 			CW.C = *coarse;
 			CW.wrow = (float4*) at, at += vec_bytes;
-			CW.gpart = (double*) at, at += (size_t) nc * sizeof(double);
-			CW.ggath = (double*) at, at += (size_t) nc * world * sizeof(double);
-			CW.g = shared ? (double*) at : CW.gpart, at += (size_t) nc * sizeof(double);
-			CW.mu = (double*) at, at += (size_t) nc * sizeof(double);
+			CW.gpart = (double*) at, at += ((size_t) nc + 8) * sizeof(double); /* + slot nc: the r.r share (several GPUs) */
+			CW.ggath = (double*) at, at += ((size_t) nc + 8) * world * sizeof(double);
+			CW.g = shared ? (double*) at : CW.gpart, at += ((size_t) nc + 8) * sizeof(double);
+			CW.mu = (double*) at, at += ((size_t) nc + 8) * sizeof(double);
 			CW.E = (double*) at, at += (size_t) nc * nc * sizeof(double);
 			CW.P = (double*) at, at += kGjBlock * kGjBlock * sizeof(double);
 			CW.bad = (int32_t*) at;
@@ -589,13 +589,14 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 #define HALO(vec) (!shared || bfmg_dist_halo(halo, (double*) (vec), (double*) sendbuf) == 0)
 
 	/* g = W^T vec: per-aggregate sums over the owned rows, completed across ranks in rank order */
-#define RESTRICT(vec, obey) ( \
+	/* WITH_RR: the all-gather also carries the ranks' r.r shares and the fold finishes that reduction */
+#define RESTRICT(vec, obey, WITH_RR) ( \
 		BFMG_LAUNCH(k_restrict, CW.C.n_agg, kBlock, 0, CW.C, CW.wrow, (double2 const*) (vec), CW.gpart, S, (obey)) == 0 && \
-		(!shared || (bfmg_dist_allgather_f64(CW.gpart, CW.ggath, nc) == 0 && BFMG_LAUNCH(k_coarse_fold, (nc + kBlock - 1) / kBlock, kBlock, 0, nc, world, CW.ggath, CW.g) == 0)))
+		(!shared || (bfmg_dist_allgather_f64(CW.gpart, CW.ggath, nc + 8) == 0 && BFMG_LAUNCH(k_coarse_fold<WITH_RR>, (nc + 8 + kBlock - 1) / kBlock, kBlock, 0, nc, world, CW.ggath, CW.g, S) == 0)))
 
 	/* p = z + beta p with z = r + W E^-1 W^T r (FIRST: beta = 0) */
-#define PRECONDITION(FIRST, obey) ( \
-		RESTRICT(r, (obey)) && \
+#define PRECONDITION(FIRST, obey, WITH_RR) ( \
+		RESTRICT(r, (obey), WITH_RR) && \
 		BFMG_LAUNCH(k_coarse_apply<FIRST>, coarse_grid, kBlock, 0, nc, CW.E, CW.g, CW.mu, partials, S) == 0 && \
 		BFMG_LAUNCH(k_update_p_coarse, G.vec, kBlock, 0, n_own, lo, CW.C, CW.wrow, CW.mu, r, p, S, (obey)) == 0)
 
@@ -636,7 +637,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 				if (
 					BFMG_LAUNCH(k_probe_vector, (nb + kBlock - 1) / kBlock, kBlock, 0, nb, CW.C, CW.wrow, c, m, p) < 0 ||
 					BFMG_LAUNCH(k_spmv<kPlain>, G.spmv, kBlock, 0, *pat, stop, sbot, p, q, bhat, partials, S) < 0 ||
-					!RESTRICT(q, false) ||
+					!RESTRICT(q, false, false) ||
 					BFMG_LAUNCH(k_probe_scatter, (CW.C.n_agg + kBlock - 1) / kBlock, kBlock, 0, CW.C, c, m, CW.g, CW.E) < 0
 				) {
 					goto out;
@@ -681,7 +682,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		if (
 			BFMG_LAUNCH(k_cg_init, G.vec, kBlock, 0, n_own, bhat + lo, xhat + lo, r + lo, p + lo, partials, S, opts->tol, opts->max_iter) < 0 ||
 			!SHARE(kFoldInit) ||
-			(use_coarse && !PRECONDITION(true, false))
+			(use_coarse && !PRECONDITION(true, false, false))
 		) {
 			goto out;
 		}
@@ -708,8 +709,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 						BFMG_LAUNCH(k_spmv<kDot>, G.spmv, kBlock, 0, *pat, stop, sbot, p, q, bhat, partials, S) < 0 ||
 						!SHARE(kFoldPq) ||
 						BFMG_LAUNCH(k_update_xr, G.vec, kBlock, 0, n_own, p + lo, q + lo, xhat + lo, r + lo, partials, S) < 0 ||
-						!SHARE(kFoldRr) ||
-						(use_coarse ? !PRECONDITION(false, true) : BFMG_LAUNCH(k_update_p, G.vec, kBlock, 0, n_own, r + lo, p + lo, S) < 0)
+						(use_coarse ? !PRECONDITION(false, true, true) : (!SHARE(kFoldRr) || BFMG_LAUNCH(k_update_p, G.vec, kBlock, 0, n_own, r + lo, p + lo, S) < 0))
 					) {
 						goto out;
 					}
@@ -796,7 +796,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 			/* residual replacement: restart CG from the true residual */
 
-			if (BFMG_LAUNCH(k_restart, G.vec, kBlock, 0, n_own, q + lo, r + lo, p + lo, S) < 0 || (use_coarse && !PRECONDITION(true, false))) {
+			if (BFMG_LAUNCH(k_restart, G.vec, kBlock, 0, n_own, q + lo, r + lo, p + lo, S) < 0 || (use_coarse && !PRECONDITION(true, false, false))) {
 				goto out;
 			}
 
