@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 METRIC = "assembly+solve throughput"
 UNIT = "DOF/s"
 
-DEFAULT_CELLS = "4000x1000"       # 4001 x 1001 nodes = 8.0 M DOF: the matrix alone (1.0 GB) is 8x the 126 MB L2
+DEFAULT_CELLS = "10000x2500"      # 10001 x 2501 nodes = 50.0 M DOF, the north star's plate: 6.3 GB of matrix, 50x the 126 MB L2
 REFERENCE_SAMPLE = "160x40"       # 13 202 DOF: the largest SURVEY.md parity size the dense reference does in ~10 s
 
 
@@ -197,7 +197,7 @@ def workload_config(nx: int, ny: int, gpus: int) -> dict:
 		"element": "P1 triangle, 3-point Gauss",
 		"solver": "FP64 PCG, Jacobi scaling + rigid-body-mode coarse level (<= 2048 aggregates), relative residual 1e-12",
 		"partition": "none" if gpus == 1 else f"{gpus} contiguous node-row blocks, halo exchange + dot-product reductions over NVLink",
-		"l2": "inputs larger than L2 (matrix ~1 GB at the default size); no flush needed",
+		"l2": "inputs larger than L2 (matrix 6.3 GB at the default size, 126 MB of L2); no flush needed",
 	}
 
 
@@ -309,6 +309,10 @@ def main():
 	world = int(os.environ.get("WORLD_SIZE", "1"))
 	local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+	# host-side symbolic work (sparsity plan, partition, aggregates) is OpenMP code in libbfm; torchrun pins
+	# OMP_NUM_THREADS to 1 unless told otherwise, so share the host cores between the ranks instead
+	os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(world, 1)))
+
 	if args.impl == "reference":
 		reference_arm(args, rank)
 		return
@@ -332,9 +336,22 @@ def main():
 		import torch
 		import torch.distributed as dist
 
-		torch.cuda.set_device(local_rank)
-		dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-		ext.dist_init(binding, dist, local_rank)  # hands the library its own communicator (bfmx_dist_init)
+		# NCCL announces its version on stdout when a communicator comes up; stdout is reserved for the one
+		# JSON line, so it points at stderr until the communicators exist
+		sys.stdout.flush()
+		saved_stdout = os.dup(1)
+		os.dup2(2, 1)
+
+		try:
+			torch.cuda.set_device(local_rank)
+			dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+			dist.barrier()
+			ext.dist_init(binding, dist, local_rank)  # hands the library its own communicator (bfmx_dist_init)
+			torch.cuda.synchronize()
+		finally:
+			sys.stdout.flush()
+			os.dup2(saved_stdout, 1)
+			os.close(saved_stdout)
 
 	def barrier():
 		if dist is not None:

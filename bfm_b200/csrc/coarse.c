@@ -462,6 +462,12 @@ static int mirror(void** d_ptr, void const* src, size_t bytes) {
 int bfmi_coarse_upload(bfmi_coarse_t* c) {
 	bfmg_coarse_t* const d = &c->dev;
 
+	if (c->on_device) {
+		return 0;
+	}
+
+	c->on_device = true; /* bfmi_coarse_free releases whatever got allocated */
+
 	d->n_agg = c->n_agg;
 	d->n_colors = c->n_colors;
 	d->nc = (3 * c->n_agg + 31) / 32 * 32;
@@ -478,6 +484,107 @@ int bfmi_coarse_upload(bfmi_coarse_t* c) {
 	}
 
 	return 0;
+}
+
+/* ---- cache --------------------------------------------------------------------------------------------
+ * examples/benchmark.py-style loops call bfm_sim_run again and again on one mesh: aggregates, colouring
+ * and their device mirrors are kept as long as mesh identity, connectivity, coordinates and partition
+ * are the same. */
+
+static bfmi_coarse_t* cached;
+static bool cached_none;          /* the last key produced no coarse level */
+static bfmi_coarse_t cached_key;  /* key of that negative result */
+
+static uint64_t hash_coords(bfm_mesh_t const* mesh) {
+	size_t const count = mesh->n_nodes * 2;
+	size_t const chunk = 1 << 16;
+	size_t const n_chunks = (count + chunk - 1) / chunk;
+	uint64_t total = 0x51ed270b7a2c3f11ull ^ count;
+
+#pragma omp parallel for schedule(static) reduction(^ : total) if (n_chunks > 16)
+	for (size_t c = 0; c < n_chunks; c++) {
+		size_t const end = (c + 1) * chunk < count ? (c + 1) * chunk : count;
+		uint64_t h = 0xcbf29ce484222325ull + c;
+
+		for (size_t i = c * chunk; i < end; i++) {
+			uint64_t bits;
+			memcpy(&bits, &mesh->coords[i], sizeof bits);
+			h = (h ^ bits) * 0x100000001b3ull;
+			h ^= h >> 31;
+		}
+
+		total ^= h * (2 * c + 1);
+	}
+
+	return total;
+}
+
+static bool same_key(bfmi_coarse_t const* c, bfm_mesh_t const* gmesh, uint64_t elems_hash, uint64_t coords_hash, int rank, int world, int32_t target) {
+	return c->gmesh == gmesh && c->key_nodes == gmesh->n_nodes && c->key_elems == gmesh->n_elems && c->elems_hash == elems_hash && c->coords_hash == coords_hash && c->rank == rank && c->world == world && c->target == target;
+}
+
+static void set_key(bfmi_coarse_t* c, bfm_mesh_t const* gmesh, uint64_t elems_hash, uint64_t coords_hash, int rank, int world, int32_t target) {
+	c->gmesh = gmesh;
+	c->key_nodes = gmesh->n_nodes;
+	c->key_elems = gmesh->n_elems;
+	c->elems_hash = elems_hash;
+	c->coords_hash = coords_hash;
+	c->rank = rank;
+	c->world = world;
+	c->target = target;
+}
+
+void bfmi_coarse_release(bfmi_coarse_t* c) {
+	if (c != NULL && __atomic_sub_fetch(&c->refs, 1, __ATOMIC_ACQ_REL) == 0) {
+		bfmi_coarse_free(c);
+	}
+}
+
+bfmi_coarse_t* bfmi_coarse_for_mesh(bfm_state_t* state, bfm_mesh_t const* gmesh, uint64_t elems_hash, bfmi_part_t const* part, int32_t target, bool* none) {
+	int const rank = part != NULL ? part->rank : 0;
+	int const world = part != NULL ? part->world : 1;
+	uint64_t const coords_hash = hash_coords(gmesh);
+
+	*none = false;
+
+	if (cached != NULL && same_key(cached, gmesh, elems_hash, coords_hash, rank, world, target)) {
+		__atomic_add_fetch(&cached->refs, 1, __ATOMIC_RELAXED);
+		return cached;
+	}
+
+	if (cached_none && same_key(&cached_key, gmesh, elems_hash, coords_hash, rank, world, target)) {
+		*none = true;
+		return NULL;
+	}
+
+	bfmi_coarse_t* const c = bfmi_coarse_build(state, gmesh, part, target);
+
+	if (c == NULL) {
+		cached_none = true;
+		set_key(&cached_key, gmesh, elems_hash, coords_hash, rank, world, target);
+		*none = true;
+		return NULL;
+	}
+
+	c->refs = 1; /* the cache's */
+	set_key(c, gmesh, elems_hash, coords_hash, rank, world, target);
+
+	bfmi_coarse_release(cached);
+	cached = c;
+
+	__atomic_add_fetch(&c->refs, 1, __ATOMIC_RELAXED); /* the caller's */
+	return c;
+}
+
+void bfmi_coarse_forget(bfm_mesh_t const* gmesh) {
+	if (cached != NULL && cached->gmesh == gmesh) {
+		bfmi_coarse_release(cached);
+		cached = NULL;
+	}
+
+	if (cached_none && cached_key.gmesh == gmesh) {
+		cached_none = false;
+	}
 }
 
 /* introspection for tests (bfm_b200.h) */

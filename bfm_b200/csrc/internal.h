@@ -113,6 +113,16 @@ BFMI_HIDDEN uint64_t bfmi_mesh_hash(bfm_mesh_t const* mesh);
  * ------------------------------------------------------------------------------------------- */
 
 typedef struct bfmi_coarse {
+	int refs;
+
+	/* cache key */
+	bfm_mesh_t const* gmesh;
+	size_t key_nodes, key_elems;
+	uint64_t elems_hash, coords_hash;
+	int rank, world;
+	int32_t target;
+	bool on_device;
+
 	int32_t n_agg;
 	int32_t n_colors;
 	int32_t n_local;     /* nodes of the mesh this rank assembles (owned + ghost) */
@@ -131,6 +141,11 @@ typedef struct bfmi_coarse {
 BFMI_HIDDEN bfmi_coarse_t* bfmi_coarse_build(bfm_state_t* state, bfm_mesh_t const* gmesh, bfmi_part_t const* part, int32_t target_aggregates);
 BFMI_HIDDEN int bfmi_coarse_upload(bfmi_coarse_t* coarse);
 BFMI_HIDDEN void bfmi_coarse_free(bfmi_coarse_t* coarse);
+/* cached (one entry, keyed by mesh identity + connectivity and coordinate hashes + partition), retained;
+ * *none is set when the mesh simply gets no coarse level */
+BFMI_HIDDEN bfmi_coarse_t* bfmi_coarse_for_mesh(bfm_state_t* state, bfm_mesh_t const* gmesh, uint64_t elems_hash, bfmi_part_t const* part, int32_t target, bool* none);
+BFMI_HIDDEN void bfmi_coarse_release(bfmi_coarse_t* coarse);
+BFMI_HIDDEN void bfmi_coarse_forget(bfm_mesh_t const* gmesh);
 
 /* ---------------------------------------------------------------------------------------------
  * BFM_MATRIX_KIND_CSR implementation object (matrix->csr.impl)

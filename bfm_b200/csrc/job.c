@@ -878,7 +878,9 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 		}
 
 		if (target >= 4) {
-			job->coarse = bfmi_coarse_build(state, mesh, job->part, (int32_t) target);
+			bool none;
+
+			job->coarse = bfmi_coarse_for_mesh(state, mesh, job->plan->elems_hash, job->part, (int32_t) target, &none);
 
 			if (job->coarse != NULL && bfmi_coarse_upload(job->coarse) < 0) {
 				BFMI_FAIL(state, "uploading the coarse level failed: %s", bfmg_last_error());
@@ -1350,7 +1352,7 @@ int bfmx_job_destroy(bfmx_job_t* job) {
 	bfmg_free(job->d_stamp);
 	bfmg_free(job->d_cval);
 	bfmg_free(job->d_xg);
-	bfmi_coarse_free(job->coarse);
+	bfmi_coarse_release(job->coarse);
 	bfmg_free(job->d_tabs);
 	bfmg_free(job->d_slice_tab);
 

@@ -29,6 +29,7 @@ int bfm_mesh_destroy(bfm_mesh_t* mesh) {
 
 	bfmi_plan_forget(mesh); /* drop any cached symbolic plan keyed on this mesh */
 	bfmi_part_forget(mesh); /* ... and its row partition */
+	bfmi_coarse_forget(mesh); /* ... and the solver's aggregates */
 
 	state->free(mesh->coords);
 	state->free(mesh->elems);

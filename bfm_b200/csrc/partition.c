@@ -416,6 +416,14 @@ static bfmi_part_t* cached;
 
 bfmi_part_t* bfmi_part_for_mesh(bfm_state_t* state, bfm_mesh_t const* mesh, uint64_t hash, int rank, int world) {
 	if (cached != NULL && cached->global == mesh && cached->n_nodes == mesh->n_nodes && cached->n_elems == mesh->n_elems && cached->hash == hash && cached->rank == rank && cached->world == world) {
+		/* same connectivity: the partition stands, but the caller may have moved the nodes since */
+
+#pragma omp parallel for schedule(static) if (cached->n_local > 100000)
+		for (int32_t l = 0; l < cached->n_local; l++) {
+			cached->local.coords[2 * l + 0] = mesh->coords[2 * cached->l2g[l] + 0];
+			cached->local.coords[2 * l + 1] = mesh->coords[2 * cached->l2g[l] + 1];
+		}
+
 		__atomic_add_fetch(&cached->refs, 1, __ATOMIC_RELAXED);
 		return cached;
 	}
