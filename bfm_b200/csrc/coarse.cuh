@@ -351,72 +351,64 @@ __global__ void __launch_bounds__(1024) k_gj_row(int n, int k, double* __restric
 	tile[(size_t) i * n + j] = s;
 }
 
-/* trailing update: E[i, j] -= sum_t E[i, K_t] * E[K_t, j] for i, j outside K.  128 x 128 tile per CTA, 8 x 8
- * outputs per thread (rows ty + 16 u, columns tx + 16 w: conflict-free shared-memory reads, 128-byte global
- * segments), the rank-32 product taken in two chunks of 16 so that the panels fit static shared memory.
- * (The first version - 64 x 64 tiles, 4 x 4 per thread - ran at 19 % of the FP64 pipe and 19 % of DRAM:
- * shared-memory bound, profiles/r1_summary.md.) */
-constexpr int kGjTile = 128;
-constexpr int kGjChunk = 16;
-
+/* trailing update: E[i, j] -= sum_t E[i, K_t] * E[K_t, j] for i, j outside K; 64 x 64 tile per CTA, 4 x 4 per thread.
+ * (A 128 x 128 / 8 x 8-per-thread variant was measured SLOWER - 168 registers, one CTA per SM: 620 us against 380 us
+ * per launch at n = 6304 - so the small tile stays.) */
 __global__ void __launch_bounds__(256) k_gj_update(int n, int k, double* __restrict__ E) {
-	__shared__ double col[kGjTile][kGjChunk + 1]; /* E[I, K chunk] */
-	__shared__ double row[kGjChunk][kGjTile];     /* E[K chunk, J] (already multiplied by P) */
+	__shared__ double col[64][kGjBlock + 1]; /* E[I, K] */
+	__shared__ double row[kGjBlock][64 + 1]; /* E[K, J] (already multiplied by P) */
 
-	int const i0 = blockIdx.y * kGjTile;
-	int const j0 = blockIdx.x * kGjTile;
+	int const i0 = blockIdx.y * 64;
+	int const j0 = blockIdx.x * 64;
 	int const kb = k * kGjBlock;
-	int const ty = threadIdx.x / 16;
-	int const tx = threadIdx.x % 16;
 
-	double acc[8][8] = {};
+	for (int t = threadIdx.x; t < 64 * kGjBlock; t += 256) {
+		int const r = t / kGjBlock, c = t % kGjBlock;
+		col[r][c] = i0 + r < n ? E[(size_t) (i0 + r) * n + kb + c] : 0;
+	}
 
-	for (int c0 = 0; c0 < kGjBlock; c0 += kGjChunk) {
-		for (int t = threadIdx.x; t < kGjTile * kGjChunk; t += 256) {
-			int const r = t / kGjChunk, c = t % kGjChunk;
-			col[r][c] = i0 + r < n ? E[(size_t) (i0 + r) * n + kb + c0 + c] : 0;
-		}
+	for (int t = threadIdx.x; t < kGjBlock * 64; t += 256) {
+		int const r = t / 64, c = t % 64;
+		row[r][c] = j0 + c < n ? E[(size_t) (kb + r) * n + j0 + c] : 0;
+	}
 
-		for (int t = threadIdx.x; t < kGjChunk * kGjTile; t += 256) {
-			int const r = t / kGjTile, c = t % kGjTile;
-			row[r][c] = j0 + c < n ? E[(size_t) (kb + c0 + r) * n + j0 + c] : 0;
-		}
+	__syncthreads();
 
-		__syncthreads();
+	int const ti = (threadIdx.x / 16) * 4;
+	int const tj = (threadIdx.x % 16) * 4;
 
-#pragma unroll 4
-		for (int t = 0; t < kGjChunk; t++) {
-			double cv[8], rv[8];
+	double acc[4][4] = {};
+
+#pragma unroll 8
+	for (int t = 0; t < kGjBlock; t++) {
+		double cv[4], rv[4];
 
 #pragma unroll
-			for (int u = 0; u < 8; u++) {
-				cv[u] = col[ty + 16 * u][t];
-				rv[u] = row[t][tx + 16 * u];
+		for (int u = 0; u < 4; u++) {
+			cv[u] = col[ti + u][t];
+			rv[u] = row[t][tj + u];
+		}
+
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+#pragma unroll
+			for (int w = 0; w < 4; w++) {
+				acc[u][w] = fma(cv[u], rv[w], acc[u][w]);
 			}
-
-#pragma unroll
-			for (int u = 0; u < 8; u++) {
-#pragma unroll
-				for (int w = 0; w < 8; w++) {
-					acc[u][w] = fma(cv[u], rv[w], acc[u][w]);
-				}
-			}
 		}
-
-		__syncthreads();
 	}
 
 #pragma unroll
-	for (int u = 0; u < 8; u++) {
-		int const i = i0 + ty + 16 * u;
+	for (int u = 0; u < 4; u++) {
+		int const i = i0 + ti + u;
 
 		if (i >= n || (i >= kb && i < kb + kGjBlock)) {
 			continue;
 		}
 
 #pragma unroll
-		for (int w = 0; w < 8; w++) {
-			int const j = j0 + tx + 16 * w;
+		for (int w = 0; w < 4; w++) {
+			int const j = j0 + tj + w;
 
 			if (j < n && !(j >= kb && j < kb + kGjBlock)) {
 				E[(size_t) i * n + j] -= acc[u][w];
@@ -459,7 +451,7 @@ __global__ void __launch_bounds__(1024) k_gj_col(int n, int k, double* __restric
 int coarse_invert(CoarseWork const& W) {
 	int const n = W.C.nc;
 	int const blocks = n / kGjBlock;
-	dim3 const tiles((n + kGjTile - 1) / kGjTile, (n + kGjTile - 1) / kGjTile);
+	dim3 const tiles((n + 63) / 64, (n + 63) / 64);
 
 	for (int k = 0; k < blocks; k++) {
 		if (

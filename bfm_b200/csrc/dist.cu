@@ -17,6 +17,7 @@
  * (and a process that already carries torch's NCCL shares that copy).
  */
 #include "gpu_internal.cuh"
+#include "p2p.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -48,6 +49,13 @@ struct Dist {
 	int rank = 0;
 	int world = 1;
 	size_t collectives = 0;
+
+	/* NVLink peer-memory mailboxes (p2p.cuh); p2p_ok is false when IPC / peer access is unavailable
+	 * or BFM_P2P=0, and the solver then uses the NCCL exchanges for everything */
+	bool p2p_ok = false;
+	void* mailbox = nullptr;
+	P2p p2p = {};
+	char p2p_why[256] = "";
 };
 
 Dist D;
@@ -105,6 +113,179 @@ int nccl_check(ncclResult_t rc, char const* what, int line) {
 }
 
 #define NCCL_CHECK(call) nccl_check(D.api.call, #call, __LINE__)
+
+size_t align_up(size_t v, size_t a) {
+	return (v + a - 1) / a * a;
+}
+
+P2pLayout mailbox_layout(int world) {
+	P2pLayout L = {};
+	size_t at = 0;
+
+	L.scalar_seq = at, at += 2 * kP2pMaxRanks * sizeof(uint64_t);
+	L.scalar_val = at, at += 2 * kP2pMaxRanks * kP2pScalarSlots * sizeof(double);
+	L.coarse_seq = at, at += 2 * kP2pMaxRanks * sizeof(uint64_t);
+	L.mu_seq = at, at += 2 * kP2pMaxRanks * sizeof(uint64_t);
+	L.halo_seq = at, at += 2 * kP2pMaxRanks * sizeof(uint64_t);
+	L.error = at, at += 64;
+	at = align_up(at, 256);
+
+	L.coarse_cap = 3 * 2048 + 32 + 8 + 24; /* n_c of 2048 aggregates, padded, + the slot row */
+	L.halo_cap = 1 << 16;                  /* interface nodes per neighbour */
+
+	L.coarse_val = at, at += align_up((size_t) 2 * world * L.coarse_cap * sizeof(double), 256);
+	L.mu_val = at, at += align_up((size_t) 2 * L.coarse_cap * sizeof(double), 256);
+	L.halo_val = at, at += align_up((size_t) 2 * world * L.halo_cap * 2 * sizeof(double), 256);
+	L.total = at;
+
+	return L;
+}
+
+/* cudaMalloc a mailbox, exchange IPC handles over the communicator, map the peers' */
+void setup_p2p() {
+	char const* const env = getenv("BFM_P2P");
+
+	D.p2p_ok = false;
+
+	if (env != nullptr && atoi(env) == 0) {
+		snprintf(D.p2p_why, sizeof D.p2p_why, "disabled by BFM_P2P=0");
+		return;
+	}
+
+	P2pLayout const L = mailbox_layout(D.world);
+	cudaIpcMemHandle_t mine;
+	cudaIpcMemHandle_t all[kP2pMaxRanks];
+	void* d_all = nullptr;
+
+#define P2P_TRY(call)                                                                         \
+	do {                                                                                      \
+		cudaError_t const rc_ = (call);                                                       \
+		if (rc_ != cudaSuccess) {                                                             \
+			snprintf(D.p2p_why, sizeof D.p2p_why, "%s: %s", #call, cudaGetErrorString(rc_)); \
+			cudaGetLastError();                                                               \
+			failed = true;                                                                    \
+		}                                                                                     \
+	} while (0)
+
+	bool failed = false;
+
+	P2P_TRY(cudaMalloc(&D.mailbox, L.total));
+
+	if (!failed) {
+		P2P_TRY(cudaMemset(D.mailbox, 0, L.total));
+		P2P_TRY(cudaIpcGetMemHandle(&mine, D.mailbox));
+		P2P_TRY(cudaMalloc(&d_all, sizeof all));
+	}
+
+	/* every rank takes part in the all-gather whatever happened locally: a failed rank sends zeros */
+
+	if (failed) {
+		memset(&mine, 0, sizeof mine);
+	}
+
+	if (d_all == nullptr && cudaMalloc(&d_all, sizeof all) != cudaSuccess) {
+		snprintf(D.p2p_why, sizeof D.p2p_why, "cudaMalloc for the handle exchange failed");
+		return; /* cannot even take part; peers will time out in NCCL - as any allocation failure here would */
+	}
+
+	int ok_local = failed ? 0 : 1;
+
+	cudaMemcpy((char*) d_all + (size_t) D.rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice);
+
+	if (nccl_check(D.api.AllGather((char*) d_all + (size_t) D.rank * sizeof mine, d_all, sizeof mine, ncclChar, D.comm, bfmg_stream()), "handle exchange", __LINE__) < 0 || cudaStreamSynchronize(bfmg_stream()) != cudaSuccess) {
+		snprintf(D.p2p_why, sizeof D.p2p_why, "handle exchange failed");
+		cudaFree(d_all);
+		return;
+	}
+
+	cudaMemcpy(all, d_all, sizeof mine * D.world, cudaMemcpyDeviceToHost);
+	cudaFree(d_all);
+
+	cudaIpcMemHandle_t zero;
+	memset(&zero, 0, sizeof zero);
+
+	for (int r = 0; r < D.world; r++) {
+		if (memcmp(&all[r], &zero, sizeof zero) == 0) {
+			ok_local = 0; /* some rank has no mailbox: nobody uses peer memory */
+		}
+	}
+
+	D.p2p = P2p {};
+	D.p2p.me = D.rank;
+	D.p2p.world = D.world;
+	D.p2p.L = L;
+
+	for (int r = 0; r < D.world && ok_local; r++) {
+		if (r == D.rank) {
+			D.p2p.box[r] = (char*) D.mailbox;
+			continue;
+		}
+
+		void* ptr = nullptr;
+		cudaError_t const rc = cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess);
+
+		if (rc != cudaSuccess) {
+			snprintf(D.p2p_why, sizeof D.p2p_why, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(rc));
+			cudaGetLastError();
+			ok_local = 0;
+			break;
+		}
+
+		D.p2p.box[r] = (char*) ptr;
+	}
+
+	/* all or nothing: agree over the communicator (reuse the first bytes of the mailbox-less path) */
+
+	double* d_flag = nullptr;
+
+	if (cudaMalloc((void**) &d_flag, sizeof(double) * (kP2pMaxRanks + 1)) != cudaSuccess) {
+		return;
+	}
+
+	double const mine_ok = ok_local;
+	double everyone[kP2pMaxRanks] = {};
+
+	cudaMemcpy(d_flag, &mine_ok, sizeof mine_ok, cudaMemcpyHostToDevice);
+
+	if (nccl_check(D.api.AllGather(d_flag, d_flag + 1, 1, ncclDouble, D.comm, bfmg_stream()), "p2p agreement", __LINE__) == 0 && cudaStreamSynchronize(bfmg_stream()) == cudaSuccess) {
+		cudaMemcpy(everyone, d_flag + 1, sizeof(double) * D.world, cudaMemcpyDeviceToHost);
+
+		bool all_ok = true;
+
+		for (int r = 0; r < D.world; r++) {
+			all_ok = all_ok && everyone[r] == 1;
+		}
+
+		D.p2p_ok = all_ok;
+
+		if (!all_ok && D.p2p_why[0] == 0) {
+			snprintf(D.p2p_why, sizeof D.p2p_why, "a peer could not map the mailboxes");
+		}
+	}
+
+	cudaFree(d_flag);
+
+#undef P2P_TRY
+}
+
+void teardown_p2p() {
+	if (D.mailbox == nullptr) {
+		return;
+	}
+
+	for (int r = 0; r < D.world; r++) {
+		if (r != D.rank && D.p2p.box[r] != nullptr) {
+			cudaIpcCloseMemHandle(D.p2p.box[r]);
+		}
+	}
+
+	cudaFree(D.mailbox);
+	cudaGetLastError();
+
+	D.mailbox = nullptr;
+	D.p2p = P2p {};
+	D.p2p_ok = false;
+}
 
 /* sendbuf[i] = v[send_idx[i]] : the owned entries the neighbours ghost, grouped by neighbour */
 __global__ void k_halo_pack(double2 const* __restrict__ v, int32_t const* __restrict__ send_idx, double2* __restrict__ sendbuf, int n) {
@@ -172,12 +353,15 @@ int bfmg_dist_init(int rank, int world, void const* id) {
 	D.rank = rank;
 	D.world = world;
 
+	setup_p2p(); /* collective; on failure the NCCL exchanges stay in charge (bfmg_dist_p2p_status says why) */
+
 	return 0;
 }
 
 int bfmg_dist_finalize(void) {
 	if (D.comm != nullptr) {
 		cudaStreamSynchronize(bfmg_stream());
+		teardown_p2p();
 		D.api.CommDestroy(D.comm);
 		D.comm = nullptr;
 	}
@@ -198,6 +382,10 @@ int bfmg_dist_rank(void) {
 
 size_t bfmg_dist_collectives(void) {
 	return D.collectives;
+}
+
+char const* bfmg_dist_p2p_status(void) {
+	return D.p2p_ok ? "" : (D.p2p_why[0] ? D.p2p_why : "not initialised");
 }
 
 int bfmg_dist_halo(bfmg_halo_t const* halo, double* d_vec, double* d_sendbuf) {
@@ -271,3 +459,42 @@ int bfmg_dist_gather_blocks(double const* d_owned, size_t const* first_node, dou
 }
 
 } // extern "C"
+
+/* ---- gpu_internal.cuh: peer-memory access for solver.cu --------------------------------------------- */
+
+P2p const* bfmg_dist_p2p() {
+	return D.p2p_ok ? &D.p2p : nullptr;
+}
+
+/* start of a solve: zero this rank's round words, then make sure every rank has done so before anyone
+ * posts (one tiny all-gather as the barrier) */
+int bfmg_dist_p2p_begin() {
+	if (!D.p2p_ok) {
+		return 0;
+	}
+
+	if (BFMG_CHECK(cudaMemsetAsync(D.mailbox, 0, D.p2p.L.coarse_val, bfmg_stream())) < 0) {
+		return -1;
+	}
+
+	double* const scratch = (double*) ((char*) D.mailbox + D.p2p.L.mu_val); /* unused until the first mu round */
+
+	D.collectives++;
+	return NCCL_CHECK(AllGather(scratch + D.rank, scratch, 1, ncclDouble, D.comm, bfmg_stream()));
+}
+
+/* end of a solve (stream synchronised): 1 when a peer wait timed out */
+int bfmg_dist_p2p_failed() {
+	if (!D.p2p_ok) {
+		return 0;
+	}
+
+	int32_t err = 0;
+
+	if (cudaMemcpy(&err, (char*) D.mailbox + D.p2p.L.error, sizeof err, cudaMemcpyDeviceToHost) != cudaSuccess) {
+		cudaGetLastError();
+		return 1;
+	}
+
+	return err != 0;
+}

@@ -68,6 +68,7 @@ int bfmg_dist_finalize(void);
 int bfmg_dist_world(void);                               /* 1 until bfmg_dist_init */
 int bfmg_dist_rank(void);
 size_t bfmg_dist_collectives(void);                      /* NCCL operations enqueued so far */
+char const* bfmg_dist_p2p_status(void);                  /* "" when the NVLink peer-memory exchanges are in use, else why not */
 
 /* halo plan of one rank (partition.c); arrays are host memory except d_send_idx */
 typedef struct {

@@ -24,6 +24,12 @@ BFMG_HIDDEN int bfmg_device();
 /* D^-1/2 of the diagonal, b^ = D^-1/2 b, A^ = D^-1/2 A D^-1/2 into d_scaled (solver.cu) */
 BFMG_HIDDEN int bfmg_scale_system(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_dscale, double* d_bhat, double* d_scaled);
 
+/* NVLink peer-memory mailboxes (p2p.cuh, dist.cu): NULL when unavailable */
+struct P2p;
+BFMG_HIDDEN P2p const* bfmg_dist_p2p();
+BFMG_HIDDEN int bfmg_dist_p2p_begin();
+BFMG_HIDDEN int bfmg_dist_p2p_failed();
+
 #define BFMG_CHECK(call) bfmg_check((call), #call, __FILE__, __LINE__)
 
 /* launch on the library stream, count it, report configuration errors */

@@ -1,0 +1,104 @@
+/*
+ * p2p.cuh - exchanges over NVLink peer memory, done from inside the solver's own kernels.
+ *
+ * One process per GPU; at bfmx_dist_init every rank cudaMalloc's a "mailbox", exports it with CUDA IPC and
+ * maps every peer's (dist.cu).  The small exchanges of a PCG iteration then need no collective launch:
+ *
+ *   scalars   the last CTA of a reducing kernel STORES its partial dot product into slot [me] of every
+ *             peer's mailbox; the one-thread k_fold that follows spins until all slots of the round are
+ *             there and folds them in rank order
+ *   coarse    k_restrict stores W^T r (and the r.r share) into every peer; k_coarse_fold waits and folds
+ *   mu        each rank applies ITS rows of E^-1 and stores its part of mu into every peer
+ *   halo      k_halo_post packs the interface entries of p straight into the neighbour's staging area;
+ *             k_halo_take waits for the neighbours' rounds and copies them into the ghost range of p
+ *
+ * Protocol (per channel): data stores, __threadfence_system(), then a store of the round number into
+ * seq[buffer][me] on the receiver; the receiver polls its LOCAL seq words (volatile) and reads the data
+ * with ld.cg (L2 is the point of coherence for peer writes).  Rounds are double-buffered by parity: a rank
+ * can be at most one round ahead of a peer, because its next post needs that peer's current one.  Round
+ * counters live on the device (Scalars) so that kernels skipped after convergence skip their rounds on
+ * every rank alike; each solve starts from zeroed seq words behind a collective barrier.
+ * Every spin has a time-out that raises the mailbox's error word instead of hanging the GPU.
+ */
+#pragma once
+
+#include <cstdint>
+
+constexpr int kP2pMaxRanks = BFMG_DIST_MAX_RANKS;
+constexpr int kP2pScalarSlots = 8;
+
+/* byte offsets inside a mailbox (identical on every rank) */
+struct P2pLayout {
+	size_t scalar_seq;  /* uint64 [2][kP2pMaxRanks] */
+	size_t scalar_val;  /* double [2][kP2pMaxRanks][kP2pScalarSlots] */
+	size_t coarse_seq;  /* uint64 [2][kP2pMaxRanks] */
+	size_t mu_seq;      /* uint64 [2][kP2pMaxRanks] */
+	size_t halo_seq;    /* uint64 [2][kP2pMaxRanks] */
+	size_t error;       /* int32 */
+	size_t coarse_val;  /* double [2][world][coarse_cap] */
+	size_t mu_val;      /* double [2][coarse_cap] */
+	size_t halo_val;    /* double2 [2][world][halo_cap] */
+	size_t total;
+	int32_t coarse_cap; /* doubles per rank in the coarse channel (n_c + 8 must fit) */
+	int32_t halo_cap;   /* node entries per neighbour in the halo channel */
+};
+
+struct P2p {
+	char* box[kP2pMaxRanks]; /* box[me] is this rank's own mailbox, the others are IPC mappings */
+	int32_t me;
+	int32_t world;
+	P2pLayout L;
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void p2p_store_u64(uint64_t* p, uint64_t v) {
+	asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ uint64_t p2p_load_u64(uint64_t const* p) {
+	uint64_t v;
+	asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void p2p_store_f64(double* p, double v) {
+	asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ uint64_t p2p_now_ns() {
+	uint64_t t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+
+/* spin until the local word reaches `round`; false (and the error word set) after ~4 s */
+__device__ __forceinline__ bool p2p_wait(P2p const& X, uint64_t const* seq, uint64_t round) {
+	if (p2p_load_u64(seq) >= round) {
+		return true;
+	}
+
+	uint64_t const t0 = p2p_now_ns();
+
+	for (uint32_t spins = 0;; spins++) {
+		if (p2p_load_u64(seq) >= round) {
+			return true;
+		}
+
+		if ((spins & 1023) == 1023 && p2p_now_ns() - t0 > 4000000000ull) {
+			*(volatile int32_t*) (X.box[X.me] + X.L.error) = 1;
+			return false;
+		}
+	}
+}
+
+__device__ __forceinline__ uint64_t* p2p_seq(P2p const& X, int rank, size_t channel_off, uint64_t round, int slot) {
+	return (uint64_t*) (X.box[rank] + channel_off) + (round & 1) * kP2pMaxRanks + slot;
+}
+
+/* after this thread's (and, through a ticket, its grid's) data stores: publish `round` of a channel to `rank` */
+__device__ __forceinline__ void p2p_publish(P2p const& X, int rank, size_t channel_off, uint64_t round) {
+	p2p_store_u64(p2p_seq(X, rank, channel_off, round, X.me), round);
+}
+
+#endif
