@@ -533,6 +533,7 @@ def main():
 			"solve_ms": ms_solve,
 			"cg_iterations": iters,
 		"coarse_dim": s.get("coarse_dim", 0),
+		"exchange": ("NVLink peer memory (CUDA IPC mailboxes), posted from inside the kernels" if s.get("uses_peer_memory") else "NCCL") if world > 1 else "none",
 		"solve_setup_ms": s.get("ms_solve_setup", 0.0),
 			"cg_rel_residual": s["cg_rel_residual"],
 			"cg_true_rel_residual": s["cg_true_rel_residual"],

@@ -46,7 +46,7 @@ __global__ void k_wrow(int nb, double2 const* __restrict__ dscale, double2 const
 }
 
 /* gpart[3 g + k] = sum over the owned nodes a of aggregate g of (R_a^T S_a v_a)_k; one CTA per aggregate */
-__global__ void __launch_bounds__(kBlock) k_restrict(bfmg_coarse_t C, float4 const* __restrict__ wrow, double2 const* __restrict__ v, double* __restrict__ gpart, Scalars const* S, bool obey_done) {
+__global__ void __launch_bounds__(kBlock) k_restrict(bfmg_coarse_t C, float4 const* __restrict__ wrow, double2 const* __restrict__ v, double* __restrict__ gpart, Scalars* S, bool obey_done) {
 	if (obey_done && S->done) {
 		return;
 	}
@@ -84,6 +84,10 @@ __global__ void __launch_bounds__(kBlock) k_restrict(bfmg_coarse_t C, float4 con
 
 	__syncthreads();
 
+	bool const p2p = S->world > 1 && S->use_p2p;
+	P2p const& X = S->X;
+	uint64_t const round = S->ep_coarse + 1;
+
 	if (threadIdx.x < 3) {
 		double t = 0;
 
@@ -93,28 +97,90 @@ __global__ void __launch_bounds__(kBlock) k_restrict(bfmg_coarse_t C, float4 con
 		}
 
 		gpart[3 * g + threadIdx.x] = t;
+
+		if (p2p) { /* straight into slot [me] of every peer's coarse channel */
+			for (int r = 0; r < X.world; r++) {
+				p2p_store_f64((double*) (X.box[r] + X.L.coarse_val) + ((round & 1) * X.world + X.me) * (size_t) X.L.coarse_cap + 3 * g + threadIdx.x, t);
+			}
+
+			__threadfence_system();
+		}
 	}
 
 	/* several GPUs: this rank's share of the pending scalar reduction (r.r) rides along in slot nc, so that
-	 * one all-gather serves both */
+	 * one exchange serves both */
 
 	if (g == 0 && threadIdx.x == 32 && S->world > 1) {
 		gpart[C.nc] = S->part;
+
+		if (p2p) {
+			for (int r = 0; r < X.world; r++) {
+				p2p_store_f64((double*) (X.box[r] + X.L.coarse_val) + ((round & 1) * X.world + X.me) * (size_t) X.L.coarse_cap + C.nc, S->part);
+			}
+
+			__threadfence_system();
+		}
+	}
+
+	if (!p2p) {
+		return;
+	}
+
+	/* the last CTA to get here publishes the round */
+
+	__shared__ bool last;
+
+	__syncthreads();
+
+	if (threadIdx.x == 0) {
+		__threadfence_system();
+		last = atomicAdd(&S->ticket2, 1u) == gridDim.x - 1;
+	}
+
+	__syncthreads();
+
+	if (last && threadIdx.x == 0) {
+		__threadfence_system();
+
+		for (int r = 0; r < X.world; r++) {
+			p2p_publish(X, r, X.L.coarse_seq, round);
+		}
+
+		S->ep_coarse = round;
+		S->ticket2 = 0;
 	}
 }
 
 /* several GPUs: g[j] = sum over ranks (in rank order) of ggath[r][j]; rows are kCoarseStride = nc + 8 long,
  * slot nc holding the ranks' shares of r.r, folded here too when FOLD_RR (k_fold<kFoldRr>'s job otherwise) */
 template <bool FOLD_RR>
-__global__ void k_coarse_fold(int nc, int world, double const* __restrict__ ggath, double* __restrict__ g, Scalars* S) {
+__global__ void k_coarse_fold(int nc, int world, double const* __restrict__ ggath, double* __restrict__ g, Scalars* S, bool obey_done) {
+	if (obey_done && S->done) {
+		return;
+	}
+
 	int const j = blockIdx.x * blockDim.x + threadIdx.x;
-	size_t const stride = (size_t) nc + 8;
+	size_t stride = (size_t) nc + 8;
+
+	if (S->use_p2p) { /* the ranks' posts are in MY mailbox: wait for the round, then read them from there */
+		P2p const& X = S->X;
+		uint64_t const round = S->ep_coarse;
+
+		if (threadIdx.x < world) {
+			p2p_wait(X, p2p_seq(X, X.me, X.L.coarse_seq, round, threadIdx.x), round);
+		}
+
+		__syncthreads();
+
+		ggath = (double const*) (X.box[X.me] + X.L.coarse_val) + (round & 1) * (size_t) X.world * X.L.coarse_cap;
+		stride = (size_t) X.L.coarse_cap;
+	}
 
 	if (j < nc) {
 		double t = 0;
 
 		for (int r = 0; r < world; r++) {
-			t += ggath[r * stride + j];
+			t += __ldcg(&ggath[r * stride + j]);
 		}
 
 		g[j] = t;
@@ -124,7 +190,7 @@ __global__ void k_coarse_fold(int nc, int world, double const* __restrict__ ggat
 		double total = 0;
 
 		for (int r = 0; r < world; r++) {
-			total += ggath[r * stride + nc];
+			total += __ldcg(&ggath[r * stride + nc]);
 		}
 
 		fold<kFoldRr>(S, total);
@@ -137,8 +203,10 @@ __global__ void k_coarse_fold(int nc, int world, double const* __restrict__ ggat
  * Partial sums are combined in a fixed order. */
 constexpr int kCoarseRows = kWarpsPerBlock / 4;
 
-template <bool FIRST>
-__global__ void __launch_bounds__(kBlock) k_coarse_apply(int nc, double const* __restrict__ Einv, double const* __restrict__ g, double* __restrict__ mu, double* __restrict__ partials, Scalars* S) {
+/* DIST (several GPUs with peer memory): this rank applies rows [row0, row0 + gridDim.x * kCoarseRows) only and
+ * stores its part of mu into every peer's mailbox; k_coarse_finish then does the scalar part */
+template <bool FIRST, bool DIST>
+__global__ void __launch_bounds__(kBlock) k_coarse_apply(int nc, int row0, double const* __restrict__ Einv, double const* __restrict__ g, double* __restrict__ mu, double* __restrict__ partials, Scalars* S) {
 	if (!FIRST && S->done) {
 		return;
 	}
@@ -147,7 +215,7 @@ __global__ void __launch_bounds__(kBlock) k_coarse_apply(int nc, double const* _
 
 	int const lane = threadIdx.x & (kWarp - 1);
 	int const warp = threadIdx.x / kWarp;
-	int const row = blockIdx.x * kCoarseRows + warp / 4;
+	int const row = row0 + blockIdx.x * kCoarseRows + warp / 4;
 	int const span = ((nc + 3) / 4 + kWarp - 1) / kWarp * kWarp; /* columns per quarter, a multiple of 32 */
 	int const j_end = min(nc, (warp % 4 + 1) * span);
 
@@ -183,13 +251,93 @@ __global__ void __launch_bounds__(kBlock) k_coarse_apply(int nc, double const* _
 	if (lane == 0 && warp % 4 == 0 && row < nc) {
 		double const m = (quarter_sum[warp] + quarter_sum[warp + 1]) + (quarter_sum[warp + 2] + quarter_sum[warp + 3]);
 
-		mu[row] = m;
-		acc = m * g[row];
+		if (DIST) {
+			P2p const& X = S->X;
+			uint64_t const round = S->ep_mu + 1;
+
+			for (int r = 0; r < X.world; r++) {
+				p2p_store_f64((double*) (X.box[r] + X.L.mu_val) + (round & 1) * (size_t) X.L.coarse_cap + row, m);
+			}
+
+			__threadfence_system();
+		}
+
+		else {
+			mu[row] = m;
+			acc = m * g[row];
+		}
 	}
 
 	double total;
 
 	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
+		if (DIST) { /* every CTA of this rank has stored and fenced its rows: publish the round */
+			P2p const& X = S->X;
+			uint64_t const round = S->ep_mu + 1;
+
+			__threadfence_system();
+
+			for (int r = 0; r < X.world; r++) {
+				p2p_publish(X, r, X.L.mu_seq, round);
+			}
+
+			S->ep_mu = round;
+		}
+
+		else {
+			double const rz = S->rr + total;
+
+			S->beta = FIRST ? 0 : rz / S->rho;
+			S->rho = rz;
+		}
+	}
+}
+
+/* DIST: all parts of mu are in MY mailbox once every rank's round is there; copy them out (mu) and finish
+ * the scalars: rz = r.r + g.mu, beta, rho.  One CTA. */
+template <bool FIRST>
+__global__ void __launch_bounds__(kBlock) k_coarse_finish(int nc, double const* __restrict__ g, double* __restrict__ mu, Scalars* S) {
+	if (!FIRST && S->done) {
+		return;
+	}
+
+	__shared__ double warp_part[kWarpsPerBlock];
+
+	P2p const& X = S->X;
+	uint64_t const round = S->ep_mu;
+
+	if (threadIdx.x < X.world) {
+		p2p_wait(X, p2p_seq(X, X.me, X.L.mu_seq, round, threadIdx.x), round);
+	}
+
+	__syncthreads();
+
+	double const* const src = (double const*) (X.box[X.me] + X.L.mu_val) + (round & 1) * (size_t) X.L.coarse_cap;
+	double acc = 0;
+
+	for (int i = threadIdx.x; i < nc; i += kBlock) {
+		double const m = __ldcg(&src[i]);
+
+		mu[i] = m;
+		acc = fma(m, g[i], acc);
+	}
+
+	acc = warp_sum(acc);
+
+	if ((threadIdx.x & (kWarp - 1)) == 0) {
+		warp_part[threadIdx.x / kWarp] = acc;
+	}
+
+	__syncthreads();
+
+	if (threadIdx.x == 0) {
+		double total = 0;
+
+#pragma unroll
+		for (int w = 0; w < kWarpsPerBlock; w++) {
+			total += warp_part[w];
+		}
+
 		double const rz = S->rr + total;
 
 		S->beta = FIRST ? 0 : rz / S->rho;

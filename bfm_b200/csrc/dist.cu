@@ -468,19 +468,43 @@ P2p const* bfmg_dist_p2p() {
 
 /* start of a solve: zero this rank's round words, then make sure every rank has done so before anyone
  * posts (one tiny all-gather as the barrier) */
-int bfmg_dist_p2p_begin() {
+int bfmg_dist_p2p_begin(int fits, int* all_fit) {
+	*all_fit = 0;
+
 	if (!D.p2p_ok) {
-		return 0;
+		return 0; /* decided collectively at init: the same on every rank */
 	}
 
-	if (BFMG_CHECK(cudaMemsetAsync(D.mailbox, 0, D.p2p.L.coarse_val, bfmg_stream())) < 0) {
+	/* the mu channel is idle until the first coarse round: its first doubles carry the votes */
+	double* const votes = (double*) ((char*) D.mailbox + D.p2p.L.mu_val);
+	double const mine = fits ? 1 : 0;
+	double everyone[kP2pMaxRanks] = {};
+
+	if (
+		BFMG_CHECK(cudaMemsetAsync(D.mailbox, 0, D.p2p.L.coarse_val, bfmg_stream())) < 0 ||
+		BFMG_CHECK(cudaMemcpyAsync(votes + D.rank, &mine, sizeof mine, cudaMemcpyHostToDevice, bfmg_stream())) < 0
+	) {
 		return -1;
 	}
 
-	double* const scratch = (double*) ((char*) D.mailbox + D.p2p.L.mu_val); /* unused until the first mu round */
-
 	D.collectives++;
-	return NCCL_CHECK(AllGather(scratch + D.rank, scratch, 1, ncclDouble, D.comm, bfmg_stream()));
+
+	if (
+		NCCL_CHECK(AllGather(votes + D.rank, votes, 1, ncclDouble, D.comm, bfmg_stream())) < 0 ||
+		BFMG_CHECK(cudaMemcpyAsync(everyone, votes, sizeof(double) * D.world, cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
+		BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0
+	) {
+		return -1;
+	}
+
+	int all = 1;
+
+	for (int r = 0; r < D.world; r++) {
+		all = all && everyone[r] == 1;
+	}
+
+	*all_fit = all;
+	return 0;
 }
 
 /* end of a solve (stream synchronised): 1 when a peer wait timed out */

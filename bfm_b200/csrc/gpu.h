@@ -165,6 +165,7 @@ typedef struct {
 	float ms;
 	float ms_setup;      /* of which: scaling + coarse-level setup (probing E, inverting it) */
 	int32_t coarse_dim;  /* 0 when the coarse level was not used */
+	int32_t peer_memory; /* 1 when the exchanges of the iteration went over NVLink peer memory, 0: NCCL or one GPU */
 	size_t launches;
 } bfmg_pcg_result_t;
 

@@ -27,7 +27,7 @@ BFMG_HIDDEN int bfmg_scale_system(bfmg_pattern_t const* pat, double const* d_val
 /* NVLink peer-memory mailboxes (p2p.cuh, dist.cu): NULL when unavailable */
 struct P2p;
 BFMG_HIDDEN P2p const* bfmg_dist_p2p();
-BFMG_HIDDEN int bfmg_dist_p2p_begin();
+BFMG_HIDDEN int bfmg_dist_p2p_begin(int fits, int* all_fit); /* collective: zero the round words, agree on using peer memory */
 BFMG_HIDDEN int bfmg_dist_p2p_failed();
 
 #define BFMG_CHECK(call) bfmg_check((call), #call, __FILE__, __LINE__)

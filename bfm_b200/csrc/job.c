@@ -1557,6 +1557,7 @@ int bfmx_job_solve(bfmx_job_t* job) {
 	job->stats.ms_solve = res.ms;
 	job->stats.ms_solve_setup = res.ms_setup;
 	job->stats.coarse_dim = (size_t) res.coarse_dim;
+	job->stats.uses_peer_memory = res.peer_memory;
 	job->stats.kernel_launches += res.launches;
 	job->solved = true;
 

@@ -27,6 +27,7 @@
  *   k_update_p  2 * 16 read + 16 write                =  48 B
  */
 #include "gpu_internal.cuh"
+#include "p2p.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -50,6 +51,15 @@ struct Scalars {
 	double rr;      /* r.r of the current residual (the convergence measure; equals rho without a coarse level) */
 	double part;                       /* this rank's share of the reduction in flight */
 	double gath[BFMG_DIST_MAX_RANKS];  /* every rank's share, in rank order */
+
+	/* exchanges over NVLink peer memory (p2p.cuh): round counters per channel, advanced by the posting
+	 * kernel's last CTA, so that kernels skipped after convergence skip their rounds on every rank alike */
+	int32_t use_p2p;
+	int32_t rr_rides;    /* the r.r share travels with the coarse restriction instead of the scalar channel */
+	uint32_t ticket2;    /* last-CTA ticket of k_restrict / k_halo_post (grid_sum has its own) */
+	int32_t pad2;
+	uint64_t ep_scalar, ep_coarse, ep_mu, ep_halo;
+	P2p X;
 };
 
 /* ---- what happens once a reduction is complete (last CTA on one GPU, k_fold on several) ------------ */
@@ -115,7 +125,28 @@ __device__ __forceinline__ void fold(Scalars* S, double total) {
 template <Fold WHAT>
 __device__ __forceinline__ void reduced(Scalars* S, double total) {
 	if (S->world > 1) {
-		S->part = total;
+		if (!S->use_p2p || (WHAT == kFoldRr && S->rr_rides)) {
+			S->part = total; /* NCCL all-gather, or k_restrict forwards it */
+			return;
+		}
+
+		/* store this rank's share into slot [me] of every peer's mailbox, then publish the round */
+
+		P2p const& X = S->X;
+		uint64_t const round = S->ep_scalar + 1;
+
+		for (int r = 0; r < X.world; r++) {
+			double* const slot = (double*) (X.box[r] + X.L.scalar_val) + ((round & 1) * kP2pMaxRanks + X.me) * kP2pScalarSlots;
+			p2p_store_f64(slot, total);
+		}
+
+		__threadfence_system();
+
+		for (int r = 0; r < X.world; r++) {
+			p2p_publish(X, r, X.L.scalar_seq, round);
+		}
+
+		S->ep_scalar = round;
 	}
 
 	else {
@@ -132,11 +163,105 @@ __global__ void k_fold(Scalars* S) {
 
 	double total = 0;
 
-	for (int r = 0; r < S->world; r++) {
-		total += S->gath[r];
+	if (S->use_p2p) { /* wait for every rank's post of this round in MY mailbox, fold in rank order */
+		P2p const& X = S->X;
+		uint64_t const round = S->ep_scalar;
+
+		for (int r = 0; r < X.world; r++) {
+			p2p_wait(X, p2p_seq(X, X.me, X.L.scalar_seq, round, r), round);
+			total += __ldcg((double const*) (X.box[X.me] + X.L.scalar_val) + ((round & 1) * kP2pMaxRanks + r) * kP2pScalarSlots);
+		}
+	}
+
+	else {
+		for (int r = 0; r < S->world; r++) {
+			total += S->gath[r];
+		}
 	}
 
 	fold<WHAT>(S, total);
+}
+
+/* ---- halo over peer memory: pack straight into the neighbours' staging areas, then take what they sent ----- */
+
+struct HaloDev {
+	int32_t n_nbr;
+	int32_t n_send;
+	int32_t nbr[kP2pMaxRanks];
+	int32_t recv_begin[kP2pMaxRanks];
+	int32_t recv_count[kP2pMaxRanks];
+	int32_t send_ptr[kP2pMaxRanks + 1];
+};
+
+__global__ void __launch_bounds__(kBlock) k_halo_post(const __grid_constant__ HaloDev H, double2 const* __restrict__ v, int32_t const* __restrict__ send_idx, Scalars* S, bool obey_done) {
+	if (obey_done && S->done) {
+		return;
+	}
+
+	P2p const& X = S->X;
+	uint64_t const round = S->ep_halo + 1;
+	int const i = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (i < H.n_send) {
+		int k = 0;
+
+		while (i >= H.send_ptr[k + 1]) {
+			k++;
+		}
+
+		double2 const val = v[send_idx[i]];
+		double* const dst = (double*) (X.box[H.nbr[k]] + X.L.halo_val) + (((round & 1) * X.world + X.me) * (size_t) X.L.halo_cap + (i - H.send_ptr[k])) * 2;
+
+		p2p_store_f64(dst, val.x);
+		p2p_store_f64(dst + 1, val.y);
+		__threadfence_system();
+	}
+
+	__shared__ bool last;
+
+	__syncthreads();
+
+	if (threadIdx.x == 0) {
+		__threadfence_system();
+		last = atomicAdd(&S->ticket2, 1u) == gridDim.x - 1;
+	}
+
+	__syncthreads();
+
+	if (last && threadIdx.x == 0) {
+		__threadfence_system();
+
+		for (int k = 0; k < H.n_nbr; k++) {
+			p2p_publish(X, H.nbr[k], X.L.halo_seq, round);
+		}
+
+		S->ep_halo = round;
+		S->ticket2 = 0;
+	}
+}
+
+/* one CTA per neighbour: wait for its round, copy its entries into the ghost range of v */
+__global__ void __launch_bounds__(kBlock) k_halo_take(const __grid_constant__ HaloDev H, double2* __restrict__ v, Scalars* S, bool obey_done) {
+	if (obey_done && S->done) {
+		return;
+	}
+
+	P2p const& X = S->X;
+	uint64_t const round = S->ep_halo;
+	int const k = blockIdx.x;
+	int const src = H.nbr[k];
+
+	if (threadIdx.x == 0) {
+		p2p_wait(X, p2p_seq(X, X.me, X.L.halo_seq, round, src), round);
+	}
+
+	__syncthreads();
+
+	double2 const* const staged = (double2 const*) (X.box[X.me] + X.L.halo_val) + ((round & 1) * X.world + src) * (size_t) X.L.halo_cap;
+
+	for (int i = threadIdx.x; i < H.recv_count[k]; i += kBlock) {
+		v[H.recv_begin[k] + i] = __ldcg(&staged[i]);
+	}
 }
 
 /* CTA-level sum; every thread calls it.  Returns true in ALL threads of the last CTA of the grid to
@@ -585,24 +710,74 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	static_assert(2 * sizeof(Scalars) <= 4096, "status polls use the 4 KiB pinned page");
 
 	/* several GPUs: spread S->part to every rank's S->gath, then fold (k_fold<WHAT>) */
-#define SHARE(WHAT) (!shared || (bfmg_dist_allgather_f64(&S->part, S->gath, 1) == 0 && BFMG_LAUNCH(k_fold<WHAT>, 1, 1, 0, S) == 0))
-#define HALO(vec) (!shared || bfmg_dist_halo(halo, (double*) (vec), (double*) sendbuf) == 0)
+	/* p2p: the producing kernel has already stored this rank's share into every peer's mailbox (reduced<>) */
+#define SHARE(WHAT) (!shared || ((p2p || bfmg_dist_allgather_f64(&S->part, S->gath, 1) == 0) && BFMG_LAUNCH(k_fold<WHAT>, 1, 1, 0, S) == 0))
+#define HALO(vec, obey) (!shared || (p2p \
+		? ((HD.n_send == 0 || BFMG_LAUNCH(k_halo_post, (HD.n_send + kBlock - 1) / kBlock, kBlock, 0, HD, (double2 const*) (vec), halo->d_send_idx, S, (obey)) == 0) && \
+		   (HD.n_nbr == 0 || BFMG_LAUNCH(k_halo_take, HD.n_nbr, kBlock, 0, HD, (double2*) (vec), S, (obey)) == 0)) \
+		: bfmg_dist_halo(halo, (double*) (vec), (double*) sendbuf) == 0))
 
 	/* g = W^T vec: per-aggregate sums over the owned rows, completed across ranks in rank order */
 	/* WITH_RR: the all-gather also carries the ranks' r.r shares and the fold finishes that reduction */
 #define RESTRICT(vec, obey, WITH_RR) ( \
 		BFMG_LAUNCH(k_restrict, CW.C.n_agg, kBlock, 0, CW.C, CW.wrow, (double2 const*) (vec), CW.gpart, S, (obey)) == 0 && \
-		(!shared || (bfmg_dist_allgather_f64(CW.gpart, CW.ggath, nc + 8) == 0 && BFMG_LAUNCH(k_coarse_fold<WITH_RR>, (nc + 8 + kBlock - 1) / kBlock, kBlock, 0, nc, world, CW.ggath, CW.g, S) == 0)))
+		(!shared || ((p2p || bfmg_dist_allgather_f64(CW.gpart, CW.ggath, nc + 8) == 0) && BFMG_LAUNCH(k_coarse_fold<WITH_RR>, (nc + 8 + kBlock - 1) / kBlock, kBlock, 0, nc, world, CW.ggath, CW.g, S, (obey)) == 0)))
 
 	/* p = z + beta p with z = r + W E^-1 W^T r (FIRST: beta = 0) */
 #define PRECONDITION(FIRST, obey, WITH_RR) ( \
 		RESTRICT(r, (obey), WITH_RR) && \
-		BFMG_LAUNCH(k_coarse_apply<FIRST>, coarse_grid, kBlock, 0, nc, CW.E, CW.g, CW.mu, partials, S) == 0 && \
+		(p2p \
+			? (BFMG_LAUNCH((k_coarse_apply<FIRST, true>), my_coarse_grid, kBlock, 0, nc, my_row0, CW.E, CW.g, CW.mu, partials, S) == 0 && \
+			   BFMG_LAUNCH(k_coarse_finish<FIRST>, 1, kBlock, 0, nc, CW.g, CW.mu, S) == 0) \
+			: BFMG_LAUNCH((k_coarse_apply<FIRST, false>), coarse_grid, kBlock, 0, nc, 0, CW.E, CW.g, CW.mu, partials, S) == 0) && \
 		BFMG_LAUNCH(k_update_p_coarse, G.vec, kBlock, 0, n_own, lo, CW.C, CW.wrow, CW.mu, r, p, S, (obey)) == 0)
+
+	/* with peer memory each rank applies its own block of rows of E^-1 (an even number of rows each) */
+	int const my_rows = shared ? ((nc + world - 1) / world + 1) / 2 * 2 : nc;
+	int const my_row0 = shared ? bfmg_dist_rank() * my_rows : 0;
+	int const my_coarse_grid = my_rows / kCoarseRows > 0 ? my_rows / kCoarseRows : 1;
+
+	/* exchanges over NVLink peer memory when every rank's halo and coarse vectors fit the mailboxes */
+
+	P2p const* const px = shared ? bfmg_dist_p2p() : nullptr;
+	bool p2p = false;
+	HaloDev HD = {};
+
+	if (shared) {
+		int fits = px != nullptr && halo->n_nbr <= kP2pMaxRanks && (nc == 0 || nc + 8 <= px->L.coarse_cap);
+
+		HD.n_nbr = halo->n_nbr <= kP2pMaxRanks ? halo->n_nbr : 0;
+		HD.n_send = halo->n_send;
+
+		for (int k = 0; k < HD.n_nbr; k++) {
+			HD.nbr[k] = halo->nbr[k];
+			HD.recv_begin[k] = halo->recv_begin[k];
+			HD.recv_count[k] = halo->recv_count[k];
+			HD.send_ptr[k] = halo->send_ptr[k];
+			HD.send_ptr[k + 1] = halo->send_ptr[k + 1];
+
+			if (px != nullptr && (halo->recv_count[k] > px->L.halo_cap || halo->send_ptr[k + 1] - halo->send_ptr[k] > px->L.halo_cap)) {
+				fits = 0;
+			}
+		}
+
+		int all_fit = 0;
+
+		if (bfmg_dist_p2p_begin(fits, &all_fit) < 0) {
+			goto out;
+		}
+
+		p2p = all_fit != 0;
+	}
 
 	{
 		Scalars init = {};
 		init.world = world;
+		init.use_p2p = p2p;
+
+		if (p2p) {
+			init.X = *px;
+		}
 
 		/* the vectors are zeroed so that ghost entries never hold NaN patterns before their first exchange */
 		if (
@@ -616,7 +791,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 	if (
 		BFMG_LAUNCH(k_jacobi, (nb + kBlock - 1) / kBlock, kBlock, 0, *pat, vtop, vbot, (double2 const*) d_b, dscale, bhat) < 0 ||
-		!HALO(dscale) ||
+		!HALO(dscale, false) ||
 		BFMG_LAUNCH(k_scale_matrix, G.spmv, kBlock, 0, *pat, vtop, vbot, dscale, stop, sbot) < 0
 	) {
 		goto out;
@@ -667,8 +842,13 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 		else {
 			int32_t const one = 1;
+			int32_t const rides = shared;
 
-			if (BFMG_CHECK(cudaMemcpyAsync(&S->coarse, &one, sizeof one, cudaMemcpyHostToDevice, bfmg_stream())) < 0 || BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0) {
+			if (
+				BFMG_CHECK(cudaMemcpyAsync(&S->coarse, &one, sizeof one, cudaMemcpyHostToDevice, bfmg_stream())) < 0 ||
+				BFMG_CHECK(cudaMemcpyAsync(&S->rr_rides, &rides, sizeof rides, cudaMemcpyHostToDevice, bfmg_stream())) < 0 ||
+				BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0
+			) {
 				goto out;
 			}
 
@@ -705,7 +885,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 			while (!done) {
 				for (int it = 0; it < chunk; it++) {
 					if (
-						!HALO(p) ||
+						!HALO(p, true) ||
 						BFMG_LAUNCH(k_spmv<kDot>, G.spmv, kBlock, 0, *pat, stop, sbot, p, q, bhat, partials, S) < 0 ||
 						!SHARE(kFoldPq) ||
 						BFMG_LAUNCH(k_update_xr, G.vec, kBlock, 0, n_own, p + lo, q + lo, xhat + lo, r + lo, partials, S) < 0 ||
@@ -755,7 +935,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 			/* true residual b^ - A^ x^ into q, its squared norm into S->sum, ||x^||^2 into S->sum2 */
 
 			if (
-				!HALO(xhat) ||
+				!HALO(xhat, false) ||
 				BFMG_LAUNCH(k_spmv<kResidual>, G.spmv, kBlock, 0, *pat, stop, sbot, xhat, q, bhat, partials, S) < 0 ||
 				!SHARE(kFoldResidual) ||
 				BFMG_LAUNCH(k_norm2, G.vec, kBlock, 0, n_own, xhat + lo, partials, S) < 0 ||
@@ -814,6 +994,13 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	}
 
 	res->launches = bfmg_launch_count() - launches_before;
+	res->peer_memory = p2p;
+
+	if (p2p && bfmg_dist_p2p_failed()) {
+		bfmg_set_error("an exchange over NVLink peer memory timed out (a peer rank failed or fell out of step)");
+		goto out;
+	}
+
 	rv = 0;
 
 out:

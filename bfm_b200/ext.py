@@ -39,6 +39,7 @@ class Stats(C.Structure):  # bfmx_stats_t
 		("halo_bytes_per_exchange", C.c_size_t),
 		("coarse_dim", C.c_size_t),
 		("ms_solve_setup", C.c_float),
+		("uses_peer_memory", _int),
 	]
 
 	def as_dict(self) -> dict:

@@ -70,6 +70,7 @@ typedef struct {
 
 	size_t coarse_dim;         /* dimension of the solver's coarse space (3 rigid-body modes per aggregate); 0 = none */
 	float ms_solve_setup;      /* part of ms_solve spent scaling the matrix and building the coarse operator */
+	int uses_peer_memory;      /* multi-GPU: 1 when the per-iteration exchanges went over NVLink peer memory (CUDA IPC), 0 when over NCCL */
 } bfmx_stats_t;
 
 /* stats of the most recent bfm_sim_run instance / bfm_matrix_solve / job stage in this process */

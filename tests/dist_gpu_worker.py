@@ -75,7 +75,7 @@ def main():
 		report[name] = {
 			"err": err, "same_on_all_ranks": same, "b_bitwise": b_equal, "staged_equals_run": staged_equal,
 			"converged": stats["cg_converged"], "rel_residual": stats["cg_rel_residual"], "iterations": stats["cg_iterations"],
-			"n_ranks": stats["n_ranks"], "owned": stats["n_dofs_owned"], "halo_bytes": stats["halo_bytes_per_exchange"],
+			"n_ranks": stats["n_ranks"], "peer_memory": stats["uses_peer_memory"], "coarse": stats["coarse_dim"], "owned": stats["n_dofs_owned"], "halo_bytes": stats["halo_bytes_per_exchange"],
 		}
 
 		del job, case
