@@ -347,6 +347,9 @@ def main():
 			dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 			dist.barrier()
 			ext.dist_init(binding, dist, local_rank)  # hands the library its own communicator (bfmx_dist_init)
+
+			if rank == 0 and binding.lib.bfmx_dist_peer_memory_status():
+				sys.stderr.write("peer memory off: " + binding.lib.bfmx_dist_peer_memory_status().decode() + "\n")
 			torch.cuda.synchronize()
 		finally:
 			sys.stdout.flush()

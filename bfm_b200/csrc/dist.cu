@@ -130,7 +130,7 @@ P2pLayout mailbox_layout(int world) {
 	L.error = at, at += 64;
 	at = align_up(at, 256);
 
-	L.coarse_cap = 3 * 2048 + 32 + 8 + 24; /* n_c of 2048 aggregates, padded, + the slot row */
+	L.coarse_cap = 3 * 4096 + 64;          /* n_c + 8 doubles per rank: the binning may exceed its 2048-aggregate target */
 	L.halo_cap = 1 << 16;                  /* interface nodes per neighbour */
 
 	L.coarse_val = at, at += align_up((size_t) 2 * world * L.coarse_cap * sizeof(double), 256);

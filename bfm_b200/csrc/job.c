@@ -158,6 +158,10 @@ int bfmx_dist_world(void) {
 	return bfmg_dist_world();
 }
 
+char const* bfmx_dist_peer_memory_status(void) {
+	return bfmg_dist_p2p_status();
+}
+
 static int batch_download(bfmx_job_t* job);
 
 int bfmx_batch_max_nodes(void) {

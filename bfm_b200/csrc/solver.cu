@@ -704,6 +704,10 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	int rv = -1;
 	int const t0 = bfmg_tick();
 
+	cudaGraphExec_t chunk_exec = nullptr;
+	size_t launches_per_chunk = 0;
+	bool graphable = false;
+
 	Scalars* const h_S = (Scalars*) bfmg_pinned(); /* two slots, written by the status polls */
 	cudaEvent_t const polled[2] = {bfmg_poll_event(0), bfmg_poll_event(1)};
 
@@ -874,6 +878,11 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		int const chunk = opts->chunk > 0 ? opts->chunk : 64;
 		int restarts = 0;
 
+		{
+			char const* const env = getenv("BFM_CG_GRAPH");
+			graphable = (!shared || p2p) && (env == nullptr || atoi(env) != 0);
+		}
+
 		for (;;) {
 			/* enqueue chunks; poll the status one chunk behind the launch front.  The decision to enqueue
 			 * chunk c + 1 depends only on the status after chunk c - 1, which is bit-identical on every
@@ -883,16 +892,61 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 			int launched_chunks = 0;
 
 			while (!done) {
-				for (int it = 0; it < chunk; it++) {
-					if (
-						!HALO(p, true) ||
-						BFMG_LAUNCH(k_spmv<kDot>, G.spmv, kBlock, 0, *pat, stop, sbot, p, q, bhat, partials, S) < 0 ||
-						!SHARE(kFoldPq) ||
-						BFMG_LAUNCH(k_update_xr, G.vec, kBlock, 0, n_own, p + lo, q + lo, xhat + lo, r + lo, partials, S) < 0 ||
-						(use_coarse ? !PRECONDITION(false, true, true) : (!SHARE(kFoldRr) || BFMG_LAUNCH(k_update_p, G.vec, kBlock, 0, n_own, r + lo, p + lo, S) < 0))
-					) {
+				/* one chunk of iterations.  Without NCCL calls in it (one GPU, or peer-memory exchanges) the
+				 * chunk is captured once into a CUDA graph and replayed: ten small kernels per iteration
+				 * leave the host's launch path and the gaps between them shrink */
+
+				bool const capture = graphable && chunk_exec == nullptr;
+
+				if (capture && BFMG_CHECK(cudaStreamBeginCapture(bfmg_stream(), cudaStreamCaptureModeThreadLocal)) < 0) {
+					goto out;
+				}
+
+				if (capture || !graphable) {
+					size_t const before = bfmg_launch_count();
+					bool ok = true;
+
+					for (int it = 0; it < chunk && ok; it++) {
+						ok =
+							HALO(p, true) &&
+							BFMG_LAUNCH(k_spmv<kDot>, G.spmv, kBlock, 0, *pat, stop, sbot, p, q, bhat, partials, S) == 0 &&
+							SHARE(kFoldPq) &&
+							BFMG_LAUNCH(k_update_xr, G.vec, kBlock, 0, n_own, p + lo, q + lo, xhat + lo, r + lo, partials, S) == 0 &&
+							(use_coarse ? PRECONDITION(false, true, true) : (SHARE(kFoldRr) && BFMG_LAUNCH(k_update_p, G.vec, kBlock, 0, n_own, r + lo, p + lo, S) == 0));
+					}
+
+					launches_per_chunk = bfmg_launch_count() - before;
+
+					if (capture) {
+						cudaGraph_t graph = nullptr;
+						cudaError_t const rc = cudaStreamEndCapture(bfmg_stream(), &graph);
+
+						if (ok && rc == cudaSuccess && graph != nullptr) {
+							ok = BFMG_CHECK(cudaGraphInstantiate(&chunk_exec, graph, 0)) == 0;
+						}
+
+						else if (ok) {
+							ok = BFMG_CHECK(rc) == 0 && false;
+						}
+
+						if (graph != nullptr) {
+							cudaGraphDestroy(graph);
+						}
+
+						bfmg_count_launch((size_t) 0 - launches_per_chunk); /* recorded, not run: the replay below counts them */
+					}
+
+					if (!ok) {
 						goto out;
 					}
+				}
+
+				if (graphable) {
+					if (BFMG_CHECK(cudaGraphLaunch(chunk_exec, bfmg_stream())) < 0) {
+						goto out;
+					}
+
+					bfmg_count_launch(launches_per_chunk);
 				}
 
 				int const cur = launched_chunks & 1;
@@ -1009,6 +1063,10 @@ out:
 #undef HALO
 #undef RESTRICT
 #undef PRECONDITION
+
+	if (chunk_exec != nullptr) {
+		cudaGraphExecDestroy(chunk_exec);
+	}
 
 	bfmg_free(ws);
 	return rv;

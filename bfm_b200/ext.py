@@ -65,6 +65,7 @@ PROTOTYPES = {
 	"bfmx_dist_finalize": (_int, []),
 	"bfmx_dist_rank": (_int, []),
 	"bfmx_dist_world": (_int, []),
+	"bfmx_dist_peer_memory_status": (C.c_char_p, []),
 	"bfmx_coarse_plan": (_int, [_P(abi.Mesh), _int, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
 	"bfmx_partition_sizes": (_int, [_P(abi.Mesh), _int, _int, _P(PartitionInfo)]),
 	"bfmx_partition_copy": (_int, [_P(abi.Mesh), _int, _int, abi.c_size_t_p, abi.c_size_t_p, abi.c_size_t_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),

@@ -147,6 +147,8 @@ int bfmx_dist_init(int rank, int world, void const* id); /* collective */
 int bfmx_dist_finalize(void);
 int bfmx_dist_rank(void);
 int bfmx_dist_world(void);
+/* "" when the per-iteration exchanges use NVLink peer memory (CUDA IPC mailboxes); otherwise why they use NCCL */
+char const* bfmx_dist_peer_memory_status(void);
 
 /* the row partition a mesh would get (host-only: works without a GPU) */
 typedef struct {
