@@ -866,15 +866,17 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 		goto fail;
 	}
 
-	/* coarse level of the solver for meshes the one-CTA path does not take: about 128 nodes per
-	 * aggregate, at most 2048 aggregates - beyond that the replicated dense E^-1 (8 * (3 n_agg)^2 bytes
-	 * per iteration, n_agg^3 to invert) costs more than the iterations it saves
-	 * (BFM_COARSE_AGGREGATES overrides; 0 switches the coarse level off) */
+	/* coarse level of the solver for meshes the one-CTA path does not take.  Aggregates: about sqrt(nodes)
+	 * - iterations fall like 1 / sqrt(n_agg) while inverting E grows like n_agg^3 and applying E^-1 like
+	 * n_agg^2 per iteration (measured optimum: ~500 at 0.25 M nodes, ~2000 at 4 M) - at least 32 nodes
+	 * each, at most 2048 (the dense E^-1 is replicated on every rank).
+	 * BFM_COARSE_AGGREGATES overrides; 0 switches the coarse level off. */
 
 	if (!takes_one_cta(job)) {
 		char const* const env = getenv("BFM_COARSE_AGGREGATES");
-		int64_t target = (int64_t) (mesh->n_nodes / 128);
+		int64_t target = (int64_t) floor(sqrt((double) mesh->n_nodes) + 0.5);
 
+		target = target > (int64_t) (mesh->n_nodes / 32) ? (int64_t) (mesh->n_nodes / 32) : target;
 		target = target > 2048 ? 2048 : target;
 
 		if (env != NULL) {
