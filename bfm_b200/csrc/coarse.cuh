@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kBlock) k_restrict(bfmg_coarse_t C, float4 con
 /* several GPUs: g[j] = sum over ranks (in rank order) of ggath[r][j]; rows are kCoarseStride = nc + 8 long,
  * slot nc holding the ranks' shares of r.r, folded here too when FOLD_RR (k_fold<kFoldRr>'s job otherwise) */
 template <bool FOLD_RR>
-__global__ void k_coarse_fold(int nc, int world, double const* __restrict__ ggath, double* __restrict__ g, Scalars* S, bool obey_done) {
+__global__ void k_coarse_fold(int nc, int n_real, int world, double const* __restrict__ ggath, double* __restrict__ g, Scalars* S, bool obey_done) {
 	if (obey_done && S->done) {
 		return;
 	}
@@ -179,7 +179,10 @@ __global__ void k_coarse_fold(int nc, int world, double const* __restrict__ ggat
 	if (j < nc) {
 		double t = 0;
 
-		for (int r = 0; r < world; r++) {
+		/* only the 3 n_agg real entries are ever posted; the padding up to nc is zero by definition (a mailbox
+		 * keeps what an earlier, larger solve left there) */
+
+		for (int r = 0; r < world && j < n_real; r++) {
 			t += __ldcg(&ggath[r * stride + j]);
 		}
 

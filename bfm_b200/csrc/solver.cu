@@ -725,7 +725,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	/* WITH_RR: the all-gather also carries the ranks' r.r shares and the fold finishes that reduction */
 #define RESTRICT(vec, obey, WITH_RR) ( \
 		BFMG_LAUNCH(k_restrict, CW.C.n_agg, kBlock, 0, CW.C, CW.wrow, (double2 const*) (vec), CW.gpart, S, (obey)) == 0 && \
-		(!shared || ((p2p || bfmg_dist_allgather_f64(CW.gpart, CW.ggath, nc + 8) == 0) && BFMG_LAUNCH(k_coarse_fold<WITH_RR>, (nc + 8 + kBlock - 1) / kBlock, kBlock, 0, nc, world, CW.ggath, CW.g, S, (obey)) == 0)))
+		(!shared || ((p2p || bfmg_dist_allgather_f64(CW.gpart, CW.ggath, nc + 8) == 0) && BFMG_LAUNCH(k_coarse_fold<WITH_RR>, (nc + 8 + kBlock - 1) / kBlock, kBlock, 0, nc, 3 * CW.C.n_agg, world, CW.ggath, CW.g, S, (obey)) == 0)))
 
 	/* p = z + beta p with z = r + W E^-1 W^T r (FIRST: beta = 0) */
 #define PRECONDITION(FIRST, obey, WITH_RR) ( \

@@ -42,8 +42,17 @@ def main():
 
 	for name in names:
 		case = cases.build(name, lib)
-		case.sim.run()
+
+		try:
+			case.sim.run()
+		except AssertionError:
+			sys.stderr.write(f"[rank {rank}] bfm_sim_run failed on case {name}: {ext.last_stats(lib)}\n")
+			raise
+
 		stats = ext.last_stats(lib)
+
+		if rank == 0:
+			sys.stderr.write(f"case {name}: {stats['cg_iterations']} iterations, coarse {stats['coarse_dim']}, peer memory {stats['uses_peer_memory']}\n")
 		u = case.instance.effects.copy()
 
 		want = golden[f"{name}/effects"]
