@@ -368,7 +368,37 @@ int bfmi_csr_solve(bfm_matrix_t* matrix, bfm_vec_t* y) {
 
 	bfmi_pcg_options(n, &opts);
 
-	if (bfmg_upload(d_b, rhs, n * sizeof *d_b) < 0 || bfmg_pcg(&csr->plan->dev, csr->d_val, d_b, d_x, &opts, &res, NULL, NULL) < 0) {
+	if (bfmg_upload(d_b, rhs, n * sizeof *d_b) < 0) {
+		BFMI_FAIL(state, "%s", bfmg_last_error());
+		goto done;
+	}
+
+	/* small systems: the whole PCG inside one CTA, as bfm_sim_run does (batch.cu); the coarse level needs
+	 * node coordinates, which a bare matrix does not carry, so large ones get the diagonal preconditioner */
+
+	char const* const one_cta = getenv("BFM_ONE_CTA");
+	int solved;
+
+	if (csr->plan->nb <= bfmg_batch_max_rows() && (one_cta == NULL || atoi(one_cta) != 0)) {
+		bfmg_batch_range_t const range = {0, csr->plan->nb};
+		bfmg_batch_status_t st;
+		size_t const before = bfmg_launch_count();
+
+		solved = bfmg_pcg_batch(&csr->plan->dev, csr->d_val, d_b, d_x, &opts, 1, &range, &st, &res.ms);
+
+		res.iterations = st.iterations;
+		res.rel_residual = st.rel_residual;
+		res.true_rel_residual = st.true_rel_residual;
+		res.backward_error = st.backward_error;
+		res.converged = st.converged == 1 && st.backward_error > opts.true_tol ? 0 : st.converged;
+		res.launches = bfmg_launch_count() - before;
+	}
+
+	else {
+		solved = bfmg_pcg(&csr->plan->dev, csr->d_val, d_b, d_x, &opts, &res, NULL, NULL);
+	}
+
+	if (solved < 0) {
 		BFMI_FAIL(state, "PCG failed: %s", bfmg_last_error());
 		goto done;
 	}
