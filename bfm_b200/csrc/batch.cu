@@ -37,14 +37,25 @@ __device__ __forceinline__ double cta_sum(double v, double* warp_part) {
 
 	__syncthreads();
 
-	double s = 0;
+	/* every thread folds the warp partials itself, as a fixed pairwise tree over independent loads (a serial
+	 * chain of 32 dependent loads + adds was a visible share of a ~3 us iteration) */
+
+	double v[kWarps];
 
 #pragma unroll
 	for (int w = 0; w < kWarps; w++) {
-		s += warp_part[w];
+		v[w] = warp_part[w];
 	}
 
-	return s;
+#pragma unroll
+	for (int width = kWarps / 2; width > 0; width /= 2) {
+#pragma unroll
+		for (int w = 0; w < width; w++) {
+			v[w] += v[w + width];
+		}
+	}
+
+	return v[0];
 }
 
 /* y = A^ v over the block rows [lo, hi) of this CTA's system; v is the CTA's shared-memory vector
