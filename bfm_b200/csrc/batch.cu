@@ -15,7 +15,9 @@
  *     recompute b^ - A^ x^ and the backward error;  write x = D^-1/2 x^ and the per-system status.
  * The Jacobi-scaled matrix A^ and b^ come from k_jacobi / k_scale_matrix (one launch each for the whole
  * batch).  Matrix values and columns are streamed from L1/L2 every iteration (a 670-DOF system is
- * 108 KB, 1024 of them 110 MB - inside the 126 MB L2); the four vectors live in shared memory.
+ * 108 KB, 1024 of them 110 MB - inside the 126 MB L2); the four vectors live in shared memory.  (Keeping the
+ * matrix itself in shared memory was tried and measured no faster for one system and slower for a batch, where
+ * it leaves room for a single CTA per SM: an iteration is bound by its chain of barriers, not by the stream.)
  * Reductions are fixed-order (shuffle tree, then warp partials summed by every thread in warp order):
  * deterministic, identical in every thread, so the convergence branch is CTA-uniform.
  */
@@ -40,28 +42,28 @@ __device__ __forceinline__ double cta_sum(double v, double* warp_part) {
 	/* every thread folds the warp partials itself, as a fixed pairwise tree over independent loads (a serial
 	 * chain of 32 dependent loads + adds was a visible share of a ~3 us iteration) */
 
-	double v[kWarps];
+	double part[kWarps];
 
 #pragma unroll
 	for (int w = 0; w < kWarps; w++) {
-		v[w] = warp_part[w];
+		part[w] = warp_part[w];
 	}
 
 #pragma unroll
 	for (int width = kWarps / 2; width > 0; width /= 2) {
 #pragma unroll
 		for (int w = 0; w < width; w++) {
-			v[w] += v[w + width];
+			part[w] += part[w + width];
 		}
 	}
 
-	return v[0];
+	return part[0];
 }
 
 /* y = A^ v over the block rows [lo, hi) of this CTA's system; v is the CTA's shared-memory vector
  * (indexed from lo); calls f(row - lo, y0, y1) for every real row */
 template <int THREADS, typename F>
-__device__ __forceinline__ void cta_spmv(bfmg_pattern_t const& P, double2 const* stop, double2 const* sbot, int32_t const* scol, int lo, int hi, double2 const* v, F&& f) {
+__device__ __forceinline__ void cta_spmv(bfmg_pattern_t const& P, double2 const* __restrict__ stop, double2 const* __restrict__ sbot, int lo, int hi, double2 const* v, F&& f) {
 	int const lane = threadIdx.x & (kWarp - 1);
 	int const warp = threadIdx.x / kWarp;
 
@@ -72,11 +74,11 @@ __device__ __forceinline__ void cta_spmv(bfmg_pattern_t const& P, double2 const*
 
 		double y0 = 0, y1 = 0;
 
-#pragma unroll 2
+#pragma unroll 8
 		for (int slot = beg + lane; slot < end; slot += kWarp) {
-			int const col = scol[slot];
-			double2 const t = stop[slot];
-			double2 const u = sbot[slot];
+			int const col = __ldg(&P.scol[slot]);
+			double2 const t = __ldg(&stop[slot]);
+			double2 const u = __ldg(&sbot[slot]);
 			double2 const xv = v[col - lo];
 
 			y0 = fma(t.x, xv.x, fma(t.y, xv.y, y0));
@@ -89,12 +91,9 @@ __device__ __forceinline__ void cta_spmv(bfmg_pattern_t const& P, double2 const*
 	}
 }
 
-/* RESIDENT: the system's scaled matrix (values + columns of its slices) is copied into shared memory once and
- * every iteration runs out of it - 670 DOF are 114 KB of matrix + 21 KB of vectors, inside the 227 KB a CTA
- * may use; otherwise the matrix is streamed from L1/L2 each iteration */
-template <int THREADS, bool RESIDENT>
+template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_pcg_cta(
-	const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ gtop, double2 const* __restrict__ gbot,
+	const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ stop, double2 const* __restrict__ sbot,
 	double2 const* __restrict__ bhat, double2 const* __restrict__ dscale, double2* __restrict__ x_out,
 	bfmg_batch_range_t const* __restrict__ ranges, bfmg_batch_status_t* __restrict__ status, double tol, int max_iter
 ) {
@@ -110,31 +109,6 @@ __global__ void __launch_bounds__(THREADS) k_pcg_cta(
 	double2* const r = x + n;
 	double2* const p = r + n;
 	double2* const q = p + n;
-
-	double2 const* stop = gtop;
-	double2 const* sbot = gbot;
-	int32_t const* scol = P.scol;
-
-	if (RESIDENT) {
-		int const slot0 = P.slice_off[lo / kWarp];
-		int const slot1 = P.slice_off[(hi + kWarp - 1) / kWarp];
-		int const n_slots = slot1 - slot0;
-
-		double2* const mtop = q + n;
-		double2* const mbot = mtop + n_slots;
-		int32_t* const mcol = (int32_t*) (mbot + n_slots);
-
-		for (int i = threadIdx.x; i < n_slots; i += THREADS) {
-			mtop[i] = gtop[slot0 + i];
-			mbot[i] = gbot[slot0 + i];
-			mcol[i] = P.scol[slot0 + i];
-		}
-
-		/* index with global slot numbers, as the streaming variant does */
-		stop = mtop - slot0;
-		sbot = mbot - slot0;
-		scol = mcol - slot0;
-	}
 
 	double acc = 0;
 
@@ -162,7 +136,7 @@ __global__ void __launch_bounds__(THREADS) k_pcg_cta(
 
 		acc = 0;
 
-		cta_spmv<THREADS>(P, stop, sbot, scol, lo, hi, p, [&](int i, double y0, double y1) {
+		cta_spmv<THREADS>(P, stop, sbot, lo, hi, p, [&](int i, double y0, double y1) {
 			double2 const pv = p[i];
 			q[i] = make_double2(y0, y1);
 			acc = fma(pv.x, y0, fma(pv.y, y1, acc));
@@ -240,7 +214,7 @@ __global__ void __launch_bounds__(THREADS) k_pcg_cta(
 	if (bnorm2 > 0) {
 		acc = 0;
 
-		cta_spmv<THREADS>(P, stop, sbot, scol, lo, hi, x, [&](int i, double y0, double y1) {
+		cta_spmv<THREADS>(P, stop, sbot, lo, hi, x, [&](int i, double y0, double y1) {
 			double2 const bb = bhat[lo + i];
 			double const r0 = bb.x - y0;
 			double const r1 = bb.y - y1;
@@ -287,7 +261,7 @@ int bfmg_batch_max_rows(void) {
 	return (200 * 1024) / (4 * (int) sizeof(double2));
 }
 
-int bfmg_pcg_batch(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, int32_t n_sys, bfmg_batch_range_t const* ranges, int32_t max_slots, bfmg_batch_status_t* status, float* ms) {
+int bfmg_pcg_batch(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, int32_t n_sys, bfmg_batch_range_t const* ranges, bfmg_batch_status_t* status, float* ms) {
 	if (!bfmg_ready()) {
 		return -1;
 	}
@@ -342,20 +316,12 @@ int bfmg_pcg_batch(bfmg_pattern_t const* pat, double const* d_val, double const*
 	int rv = -1;
 	int const t0 = bfmg_tick();
 
-	/* shared memory: four vectors, plus the matrix when the largest system's fits (the slices of a system are
-	 * consecutive, so its slots are slice_off[hi / 32] - slice_off[lo / 32]; that needs the host copy of
-	 * slice_off, which the caller passes through max_slots) */
+	size_t const smem = (size_t) max_rows * 4 * sizeof(double2);
 
-	size_t const vec_smem = (size_t) max_rows * 4 * sizeof(double2);
-	size_t const mat_smem = (size_t) max_slots * (2 * sizeof(double2) + sizeof(int32_t));
-	bool const resident = max_slots > 0 && vec_smem + mat_smem + 16 <= 220 * 1024;
-	size_t const smem = vec_smem + (resident ? mat_smem + 16 : 0);
+	/* many systems: 256-thread CTAs, several per SM, so that independent systems hide each other's
+	 * latencies; few systems: 1024 threads on each */
 
-	/* many systems: 256-thread CTAs, several per SM, so that independent systems hide each other's latencies
-	 * (with a resident matrix one CTA fills an SM: then the wide CTA is the better use of it); few systems:
-	 * 1024 threads on each */
-
-	bool const wide = resident || n_sys < 2 * bfmg_sm_count();
+	bool const wide = n_sys < 2 * bfmg_sm_count();
 	double2 const* const stop = (double2 const*) scaled;
 	double2 const* const sbot = stop + pat->n_slots;
 
@@ -366,15 +332,25 @@ int bfmg_pcg_batch(bfmg_pattern_t const* pat, double const* d_val, double const*
 		goto out;
 	}
 
-#define PCG_CTA(THREADS, RESIDENT) \
-	(BFMG_CHECK(cudaFuncSetAttribute((k_pcg_cta<THREADS, RESIDENT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) == 0 && \
-	 BFMG_LAUNCH((k_pcg_cta<THREADS, RESIDENT>), n_sys, THREADS, smem, *pat, stop, sbot, (double2 const*) bhat, (double2 const*) dscale, (double2*) d_x, d_ranges, d_status, opts->tol, opts->max_iter) == 0)
+	if (wide) {
+		if (BFMG_CHECK(cudaFuncSetAttribute(k_pcg_cta<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) < 0) {
+			goto out;
+		}
 
-	if (!(resident ? PCG_CTA(1024, true) : (wide ? PCG_CTA(1024, false) : PCG_CTA(256, false)))) {
-		goto out;
+		if (BFMG_LAUNCH(k_pcg_cta<1024>, n_sys, 1024, smem, *pat, stop, sbot, (double2 const*) bhat, (double2 const*) dscale, (double2*) d_x, d_ranges, d_status, opts->tol, opts->max_iter) < 0) {
+			goto out;
+		}
 	}
 
-#undef PCG_CTA
+	else {
+		if (BFMG_CHECK(cudaFuncSetAttribute(k_pcg_cta<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) < 0) {
+			goto out;
+		}
+
+		if (BFMG_LAUNCH(k_pcg_cta<256>, n_sys, 256, smem, *pat, stop, sbot, (double2 const*) bhat, (double2 const*) dscale, (double2*) d_x, d_ranges, d_status, opts->tol, opts->max_iter) < 0) {
+			goto out;
+		}
+	}
 
 	{
 		int const t1 = bfmg_tick();

@@ -384,7 +384,7 @@ int bfmi_csr_solve(bfm_matrix_t* matrix, bfm_vec_t* y) {
 		bfmg_batch_status_t st;
 		size_t const before = bfmg_launch_count();
 
-		solved = bfmg_pcg_batch(&csr->plan->dev, csr->d_val, d_b, d_x, &opts, 1, &range, bfmi_plan_max_slots(csr->plan, &range, 1), &st, &res.ms);
+		solved = bfmg_pcg_batch(&csr->plan->dev, csr->d_val, d_b, d_x, &opts, 1, &range, &st, &res.ms);
 
 		res.iterations = st.iterations;
 		res.rel_residual = st.rel_residual;

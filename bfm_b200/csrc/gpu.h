@@ -191,10 +191,8 @@ typedef struct {
 int bfmg_batch_max_rows(void); /* largest system (node rows) the one-CTA solver takes */
 
 /* solves every system of the batch (ranges/status: host arrays of n_sys entries); systems that do not
- * converge are reported in status, not as a failure of the call.  max_slots = the largest number of pattern
- * slots one system spans (from the host copy of slice_off); when matrix + vectors of that system fit in
- * shared memory the CTAs keep their matrix resident.  0 = stream it. */
-int bfmg_pcg_batch(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, int32_t n_sys, bfmg_batch_range_t const* ranges, int32_t max_slots, bfmg_batch_status_t* status, float* ms);
+ * converge are reported in status, not as a failure of the call */
+int bfmg_pcg_batch(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, int32_t n_sys, bfmg_batch_range_t const* ranges, bfmg_batch_status_t* status, float* ms);
 
 /* times `reps` back-to-back launches of the CG SpMV kernel (q = A p with the fused dot) on d_val */
 int bfmg_spmv_time(bfmg_pattern_t const* pat, double const* d_val, int reps, float* ms_per_launch);

@@ -64,9 +64,6 @@ BFMI_HIDDEN void bfmi_plan_release(bfmi_plan_t* plan);
 BFMI_HIDDEN void bfmi_plan_forget(bfm_mesh_t const* mesh); /* mesh is going away */
 BFMI_HIDDEN int bfmi_plan_upload(bfm_state_t* state, bfmi_plan_t* plan);
 
-/* most pattern slots spanned by one of the given row ranges (each starting on a slice boundary) */
-BFMI_HIDDEN int32_t bfmi_plan_max_slots(bfmi_plan_t const* plan, bfmg_batch_range_t const* ranges, int32_t n);
-
 /* slot of block (a, b), or -1 */
 BFMI_HIDDEN int64_t bfmi_plan_find(bfmi_plan_t const* plan, int32_t a, int32_t b);
 

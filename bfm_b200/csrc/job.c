@@ -1490,7 +1490,7 @@ int bfmx_job_solve(bfmx_job_t* job) {
 		size_t const before = bfmg_launch_count();
 		float ms = 0;
 
-		if (bfmg_pcg_batch(&job->pat, job->d_val, job->d_b, job->d_x, &opts, job->n_sys, job->ranges, bfmi_plan_max_slots(job->plan, job->ranges, job->n_sys), job->status, &ms) < 0) {
+		if (bfmg_pcg_batch(&job->pat, job->d_val, job->d_b, job->d_x, &opts, job->n_sys, job->ranges, job->status, &ms) < 0) {
 			return BFMI_FAIL(job->state, "batched PCG failed: %s", bfmg_last_error());
 		}
 
@@ -1535,7 +1535,7 @@ int bfmx_job_solve(bfmx_job_t* job) {
 		bfmg_batch_status_t st;
 		size_t const before = bfmg_launch_count();
 
-		if (bfmg_pcg_batch(&job->pat, job->d_val, job->d_b, job->d_x, &opts, 1, &range, bfmi_plan_max_slots(job->plan, &range, 1), &st, &res.ms) < 0) {
+		if (bfmg_pcg_batch(&job->pat, job->d_val, job->d_b, job->d_x, &opts, 1, &range, &st, &res.ms) < 0) {
 			return BFMI_FAIL(job->state, "PCG failed: %s", bfmg_last_error());
 		}
 

@@ -159,20 +159,6 @@ static inline int64_t slot_of(bfmi_plan_t const* plan, int32_t a, int32_t t) {
 	return (int64_t) plan->slice_off[a / SLICE] + (int64_t) t * SLICE + a % SLICE;
 }
 
-int32_t bfmi_plan_max_slots(bfmi_plan_t const* plan, bfmg_batch_range_t const* ranges, int32_t n) {
-	int32_t most = 0;
-
-	for (int32_t i = 0; i < n; i++) {
-		int32_t const first = ranges[i].row_lo / SLICE;
-		int32_t const last = (ranges[i].row_hi + SLICE - 1) / SLICE;
-		int32_t const slots = plan->slice_off[last] - plan->slice_off[first];
-
-		most = slots > most ? slots : most;
-	}
-
-	return most;
-}
-
 int64_t bfmi_plan_find(bfmi_plan_t const* plan, int32_t a, int32_t b) {
 	int32_t lo = 0;
 	int32_t hi = plan->row_len[a];
