@@ -15,9 +15,10 @@
  *     recompute b^ - A^ x^ and the backward error;  write x = D^-1/2 x^ and the per-system status.
  * The Jacobi-scaled matrix A^ and b^ come from k_jacobi / k_scale_matrix (one launch each for the whole
  * batch).  Matrix values and columns are streamed from L1/L2 every iteration (a 670-DOF system is
- * 108 KB, 1024 of them 110 MB - inside the 126 MB L2); the four vectors live in shared memory.  (Keeping the
- * matrix itself in shared memory was tried and measured no faster for one system and slower for a batch, where
- * it leaves room for a single CTA per SM: an iteration is bound by its chain of barriers, not by the stream.)
+ * 108 KB, 1024 of them 110 MB - inside the 126 MB L2); the four vectors live in shared memory.
+ * Measured dead ends (round 1): keeping the matrix itself in shared memory (no faster for one system, slower for a
+ * batch - one CTA per SM), a tree fold of the warp partials and a deeper unroll of the slot loop (both slightly
+ * slower): an iteration is bound by its chain of three barriers and the 11-of-32-warp SpMV phase, not by the stream.
  * Reductions are fixed-order (shuffle tree, then warp partials summed by every thread in warp order):
  * deterministic, identical in every thread, so the convergence branch is CTA-uniform.
  */
@@ -39,25 +40,14 @@ __device__ __forceinline__ double cta_sum(double v, double* warp_part) {
 
 	__syncthreads();
 
-	/* every thread folds the warp partials itself, as a fixed pairwise tree over independent loads (a serial
-	 * chain of 32 dependent loads + adds was a visible share of a ~3 us iteration) */
-
-	double part[kWarps];
+	double s = 0;
 
 #pragma unroll
 	for (int w = 0; w < kWarps; w++) {
-		part[w] = warp_part[w];
+		s += warp_part[w];
 	}
 
-#pragma unroll
-	for (int width = kWarps / 2; width > 0; width /= 2) {
-#pragma unroll
-		for (int w = 0; w < width; w++) {
-			part[w] += part[w + width];
-		}
-	}
-
-	return part[0];
+	return s;
 }
 
 /* y = A^ v over the block rows [lo, hi) of this CTA's system; v is the CTA's shared-memory vector
@@ -74,7 +64,7 @@ __device__ __forceinline__ void cta_spmv(bfmg_pattern_t const& P, double2 const*
 
 		double y0 = 0, y1 = 0;
 
-#pragma unroll 8
+#pragma unroll 2
 		for (int slot = beg + lane; slot < end; slot += kWarp) {
 			int const col = __ldg(&P.scol[slot]);
 			double2 const t = __ldg(&stop[slot]);
