@@ -449,6 +449,13 @@ def main():
 	peak = float(peaks.get("hbm_gbs", 6650.0))
 	peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
 
+	# DRAM traffic of the same kernel on the same workload from the committed ncu --set full capture (one GPU)
+	traffic = None
+	traffic_path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+
+	if world == 1 and os.path.exists(traffic_path):
+		traffic = (json.load(open(traffic_path)).get(args.cells) or {}).get("dram_bytes_per_launch")
+
 	achieved = stored_bytes / (spmv_ms * 1e-3) / 1e9
 	us_iter = ms_solve * 1e3 / max(iters, 1)
 
@@ -461,7 +468,7 @@ def main():
 		"frac": achieved / peak,
 		"frac_of_nominal_8TBs": achieved / 8000.0,
 		"peak_source": peak_src,
-		"traffic": None,  # dram__bytes from the ncu --set full capture: see profiles/
+		"traffic": traffic,  # dram__bytes_read + write per launch, ncu --set full (profiles/r1_ncu_traffic.json); None when not captured for this workload
 		"bytes_per_launch": stored_bytes,
 		"us_per_launch": spmv_ms * 1e3,
 		"canonical_csr_bytes_per_launch": canonical_bytes,

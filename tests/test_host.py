@@ -520,3 +520,33 @@ def test_hot_path_fails_loudly_without_a_device(lib):
 		assert not case.instance.effects.any()  # nothing was computed anywhere
 	finally:
 		del os.environ["BFM_QUIET"]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+	"""bench.py --impl reference: the reference's own CPU implementation (oracle/_ref) on a bounded sample"""
+
+	import json
+	import subprocess
+	import sys
+
+	from oracle import ref as ref_mod
+
+	if not ref_mod.available():
+		pytest.skip("oracle/_ref/libbfm_ref.so not available")
+
+	proc = subprocess.run(
+		[sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--reference-sample", "40x10"],
+		capture_output=True, text=True, timeout=300,
+	)
+
+	assert proc.returncode == 0, proc.stderr[-2000:]
+
+	lines = [line for line in proc.stdout.splitlines() if line.strip()]
+	assert len(lines) == 1
+
+	line = json.loads(lines[0])
+
+	assert line["impl"] == "reference" and line["unit"] == "DOF/s" and line["value"] > 0
+	assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 1
+	assert line["e2e"] == {"value": line["value"], "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+	assert line["config"]["n_dofs"] == 50025002 and line["higher_is_better"] is True
