@@ -347,3 +347,43 @@ def test_coarse_level_is_deterministic(lib, monkeypatch):
 		outs.append(case.instance.effects.copy())
 
 	assert np.array_equal(outs[0], outs[1])
+
+
+# ---- the measurement harness itself ------------------------------------------------------------------------
+
+
+def test_bench_line_has_the_contract_keys(tmp_path):
+	"""bench.py on a small plate: one JSON line with value / e2e / roofline / cpu_baseline / clocks / gpu_launches"""
+
+	import json
+	import os
+	import subprocess
+	import sys
+
+	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	proc = subprocess.run(
+		[sys.executable, os.path.join(root, "bench.py"), "--cells", "400x100", "--steps", "2", "--warmup", "3", "--reference-sample", "40x10"],
+		capture_output=True, text=True, timeout=600,
+	)
+
+	assert proc.returncode == 0, proc.stderr[-3000:]
+
+	lines = [line for line in proc.stdout.splitlines() if line.strip()]
+	assert len(lines) == 1, lines
+
+	line = json.loads(lines[0])
+
+	assert line["unit"] == "DOF/s" and line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3
+	assert line["value"] > 0 and line["higher_is_better"] is True and line["dtype"] == "f64" and line["vs_baseline"] is None
+	assert line["config"]["n_dofs"] == 2 * 401 * 101 and line["cg_rel_residual"] <= 1e-12
+	assert line["gpu_launches"] > 100
+
+	roof = line["roofline"]
+	assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["achieved"] > 0 and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
+
+	e2e = line["e2e"]
+	assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] >= 16 * 401 * 101 and e2e["d2h_bytes_per_step"] == 16 * 401 * 101
+
+	cpu = line["cpu_baseline"]
+	assert cpu["kind"] == "reference" and cpu["cores"] == 1 and cpu["value"] > 0
+	assert "sm_mhz" in line["clocks"] and "reasons" in line["clocks"]
