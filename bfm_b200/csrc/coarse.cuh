@@ -502,25 +502,52 @@ __global__ void __launch_bounds__(1024) k_gj_row(int n, int k, double* __restric
 	tile[(size_t) i * n + j] = s;
 }
 
-/* trailing update: E[i, j] -= sum_t E[i, K_t] * E[K_t, j] for i, j outside K; 64 x 64 tile per CTA, 4 x 4 per thread.
+/* where the pivot row panel R = P E[K, :] (32 x n) and P (32 x 32) of a Gauss-Jordan step come from: the matrix
+ * itself on one GPU; this rank's mailbox when the inversion is distributed by row blocks (p2p.cuh, panel channel) */
+struct GjPanel {
+	bool dist;
+	int owner;        /* rank that owns pivot block k */
+	uint64_t round;   /* k + 1 */
+};
+
+__device__ __forceinline__ double const* gj_panel(Scalars const* S, GjPanel const& G) {
+	P2p const& X = S->X;
+	return (double const*) (X.box[X.me] + X.L.panel_val) + (G.round & 1) * (32 * (size_t) X.L.coarse_cap + 32 * 32 + 8);
+}
+
+/* trailing update: E[i, j] -= sum_t E[i, K_t] * R[t, j] for the rows i of [row_lo, row_hi) and all j, both outside K;
+ * 64 x 64 tile per CTA, 4 x 4 per thread.
  * (A 128 x 128 / 8 x 8-per-thread variant was measured SLOWER - 168 registers, one CTA per SM: 620 us against 380 us
  * per launch at n = 6304 - so the small tile stays.) */
-__global__ void __launch_bounds__(256) k_gj_update(int n, int k, double* __restrict__ E) {
+__global__ void __launch_bounds__(256) k_gj_update(int n, int k, double* __restrict__ E, int row_lo, int row_hi, GjPanel G, Scalars* S) {
 	__shared__ double col[64][kGjBlock + 1]; /* E[I, K] */
-	__shared__ double row[kGjBlock][64 + 1]; /* E[K, J] (already multiplied by P) */
+	__shared__ double row[kGjBlock][64 + 1]; /* R[K, J] */
 
-	int const i0 = blockIdx.y * 64;
+	int const i0 = row_lo + blockIdx.y * 64;
 	int const j0 = blockIdx.x * 64;
 	int const kb = k * kGjBlock;
 
+	double const* R = E + (size_t) kb * n;
+
+	if (G.dist) { /* the owner's panel lands in my mailbox: wait for this step's round */
+		P2p const& X = S->X;
+
+		if (threadIdx.x == 0) {
+			p2p_wait(X, p2p_seq(X, X.me, X.L.panel_seq, G.round, G.owner), G.round);
+		}
+
+		__syncthreads();
+		R = gj_panel(S, G);
+	}
+
 	for (int t = threadIdx.x; t < 64 * kGjBlock; t += 256) {
 		int const r = t / kGjBlock, c = t % kGjBlock;
-		col[r][c] = i0 + r < n ? E[(size_t) (i0 + r) * n + kb + c] : 0;
+		col[r][c] = i0 + r < row_hi ? E[(size_t) (i0 + r) * n + kb + c] : 0;
 	}
 
 	for (int t = threadIdx.x; t < kGjBlock * 64; t += 256) {
 		int const r = t / 64, c = t % 64;
-		row[r][c] = j0 + c < n ? E[(size_t) (kb + r) * n + j0 + c] : 0;
+		row[r][c] = j0 + c < n ? __ldcg(&R[(size_t) r * n + j0 + c]) : 0;
 	}
 
 	__syncthreads();
@@ -553,7 +580,7 @@ __global__ void __launch_bounds__(256) k_gj_update(int n, int k, double* __restr
 	for (int u = 0; u < 4; u++) {
 		int const i = i0 + ti + u;
 
-		if (i >= n || (i >= kb && i < kb + kGjBlock)) {
+		if (i >= row_hi || (i >= kb && i < kb + kGjBlock)) {
 			continue;
 		}
 
@@ -568,9 +595,11 @@ __global__ void __launch_bounds__(256) k_gj_update(int n, int k, double* __restr
 	}
 }
 
-/* column panel: E[I, K] = -E[I, K] * P for I != k;  E[K, K] = P; one CTA per I */
-__global__ void __launch_bounds__(1024) k_gj_col(int n, int k, double* __restrict__ E, double const* __restrict__ P) {
-	int const I = blockIdx.x;
+/* column panel: E[I, K] = -E[I, K] * P for the row blocks I != k of this rank;  E[K, K] = P where it owns K.
+ * One CTA per row block from row_lo on.  Distributed: P comes from the mailbox, the owner's "not positive
+ * definite" verdict is taken over, and the last CTA acknowledges the step to every peer. */
+__global__ void __launch_bounds__(1024) k_gj_col(int n, int k, double* __restrict__ E, double const* __restrict__ Plocal, int row_lo, GjPanel G, int32_t* bad, Scalars* S) {
+	int const I = row_lo / kGjBlock + blockIdx.x;
 
 	__shared__ double p[kGjBlock][kGjBlock + 1];
 	__shared__ double a[kGjBlock][kGjBlock + 1];
@@ -578,39 +607,163 @@ __global__ void __launch_bounds__(1024) k_gj_col(int n, int k, double* __restric
 	int const i = threadIdx.x / kGjBlock;
 	int const j = threadIdx.x % kGjBlock;
 
+	double const* P = Plocal;
+
+	if (G.dist) {
+		P = gj_panel(S, G) + 32 * (size_t) n; /* the round was awaited by k_gj_update, earlier in the stream */
+
+		if (blockIdx.x == 0 && threadIdx.x == 0 && __ldcg(&P[kGjBlock * kGjBlock]) != 0) {
+			*bad = 1;
+		}
+	}
+
 	double* const tile = E + (size_t) (I * kGjBlock) * n + k * kGjBlock;
 
-	p[i][j] = P[i * kGjBlock + j];
+	p[i][j] = __ldcg(&P[i * kGjBlock + j]);
 	a[i][j] = tile[(size_t) i * n + j];
 	__syncthreads();
 
 	if (I == k) {
 		tile[(size_t) i * n + j] = p[i][j];
+	}
+
+	else {
+		double s = 0;
+
+#pragma unroll
+		for (int t = 0; t < kGjBlock; t++) {
+			s = fma(a[i][t], p[t][j], s);
+		}
+
+		tile[(size_t) i * n + j] = -s;
+	}
+
+	if (!G.dist) {
 		return;
 	}
 
-	double s = 0;
+	/* acknowledge: this rank has finished step k (its panel buffer may be overwritten two steps from now) */
 
-#pragma unroll
-	for (int t = 0; t < kGjBlock; t++) {
-		s = fma(a[i][t], p[t][j], s);
+	__shared__ bool last;
+
+	__syncthreads();
+
+	if (threadIdx.x == 0) {
+		__threadfence();
+		last = atomicAdd(&S->ticket2, 1u) == gridDim.x - 1;
 	}
 
-	tile[(size_t) i * n + j] = -s;
+	__syncthreads();
+
+	if (last && threadIdx.x == 0) {
+		P2p const& X = S->X;
+
+		for (int r = 0; r < X.world; r++) {
+			p2p_store_u64((uint64_t*) (X.box[r] + X.L.gj_done) + X.me, G.round);
+		}
+
+		S->ticket2 = 0;
+	}
 }
 
-int coarse_invert(CoarseWork const& W) {
+/* distributed: the owner of pivot block k stores R = E[K, :] (already multiplied by P), P and its verdict into
+ * every rank's panel buffer of this round, then publishes the round */
+__global__ void __launch_bounds__(kBlock) k_gj_bcast(int n, int k, double const* __restrict__ E, double const* __restrict__ P, int32_t const* __restrict__ bad, GjPanel G, Scalars* S) {
+	P2p const& X = S->X;
+
+	/* the buffer of this parity was last read in step k - 2: every rank must have acknowledged it */
+
+	if (threadIdx.x < X.world && G.round >= 3) {
+		p2p_wait(X, (uint64_t const*) (X.box[X.me] + X.L.gj_done) + threadIdx.x, G.round - 2);
+	}
+
+	__syncthreads();
+
+	size_t const panel = 32 * (size_t) X.L.coarse_cap + 32 * 32 + 8;
+	size_t const count = 32 * (size_t) n + 32 * 32 + 1;
+	double const* const src = E + (size_t) k * kGjBlock * n;
+
+	for (size_t t = blockIdx.x * (size_t) blockDim.x + threadIdx.x; t < count; t += (size_t) gridDim.x * blockDim.x) {
+		double const v = t < 32 * (size_t) n ? src[t] : (t < 32 * (size_t) n + 32 * 32 ? P[t - 32 * (size_t) n] : (double) *bad);
+
+		for (int r = 0; r < X.world; r++) {
+			p2p_store_f64((double*) (X.box[r] + X.L.panel_val) + (G.round & 1) * panel + t, v);
+		}
+	}
+
+	__threadfence_system();
+
+	__shared__ bool last;
+
+	__syncthreads();
+
+	if (threadIdx.x == 0) {
+		__threadfence_system();
+		last = atomicAdd(&S->ticket2, 1u) == gridDim.x - 1;
+	}
+
+	__syncthreads();
+
+	if (last && threadIdx.x == 0) {
+		__threadfence_system();
+
+		for (int r = 0; r < X.world; r++) {
+			p2p_publish(X, r, X.L.panel_seq, G.round);
+		}
+
+		S->ticket2 = 0;
+	}
+}
+
+__global__ void k_gj_ack_all(uint64_t rounds, Scalars* S) {
+	P2p const& X = S->X;
+
+	if (threadIdx.x < X.world) {
+		p2p_store_u64((uint64_t*) (X.box[threadIdx.x] + X.L.gj_done) + X.me, rounds);
+	}
+}
+
+/* In place.  Replicated (one GPU, or NCCL exchanges): every rank inverts all of E.  Distributed (peer memory):
+ * rank r owns the row blocks [r * blocks_per, (r + 1) * blocks_per) - the rows of E^-1 it will apply - and only
+ * updates those; the pivot panel of each step comes from its owner through the mailboxes. */
+int coarse_invert(CoarseWork const& W, Scalars* S, bool dist, int rank, int blocks_per) {
 	int const n = W.C.nc;
 	int const blocks = n / kGjBlock;
-	dim3 const tiles((n + 63) / 64, (n + 63) / 64);
+
+	int const my_b0 = dist ? (rank * blocks_per < blocks ? rank * blocks_per : blocks) : 0;
+	int const my_b1 = dist ? ((rank + 1) * blocks_per < blocks ? (rank + 1) * blocks_per : blocks) : blocks;
+	int const row_lo = my_b0 * kGjBlock;
+	int const row_hi = my_b1 * kGjBlock;
+
+	dim3 const tiles((n + 63) / 64, (row_hi - row_lo + 63) / 64);
+
+	/* a rank without rows never reads a panel: it acknowledges every step up front */
+
+	if (dist && row_hi == row_lo && BFMG_LAUNCH(k_gj_ack_all, 1, kWarp, 0, (uint64_t) blocks + 2, S) < 0) {
+		return -1;
+	}
 
 	for (int k = 0; k < blocks; k++) {
-		if (
+		GjPanel G;
+
+		G.dist = dist;
+		G.owner = dist ? k / blocks_per : 0;
+		G.round = (uint64_t) k + 1;
+
+		bool const mine = !dist || G.owner == rank;
+
+		if (mine && (
 			BFMG_LAUNCH(k_gj_diag, 1, 1024, 0, n, k, W.E, W.P, W.bad) < 0 ||
 			BFMG_LAUNCH(k_gj_row, blocks, 1024, 0, n, k, W.E, W.P) < 0 ||
-			BFMG_LAUNCH(k_gj_update, tiles, 256, 0, n, k, W.E) < 0 ||
-			BFMG_LAUNCH(k_gj_col, blocks, 1024, 0, n, k, W.E, W.P) < 0
-		) {
+			(dist && BFMG_LAUNCH(k_gj_bcast, 64, kBlock, 0, n, k, W.E, W.P, W.bad, G, S) < 0)
+		)) {
+			return -1;
+		}
+
+		if (row_hi > row_lo && (
+			BFMG_LAUNCH(k_gj_update, tiles, 256, 0, n, k, W.E, row_lo, row_hi, G, S) < 0 ||
+			BFMG_LAUNCH(k_gj_col, my_b1 - my_b0, 1024, 0, n, k, W.E, W.P, row_lo, G, W.bad, S) < 0
+		)) {
 			return -1;
 		}
 	}

@@ -11,6 +11,9 @@
  *   mu        each rank applies ITS rows of E^-1 and stores its part of mu into every peer
  *   halo      k_halo_post packs the interface entries of p straight into the neighbour's staging area;
  *             k_halo_take waits for the neighbours' rounds and copies them into the ghost range of p
+ *   panel     set-up only: the Gauss-Jordan inversion of the coarse operator is distributed by row blocks;
+ *             the owner of a pivot block stores its row panel into every peer, and every rank acknowledges
+ *             each finished step so that the two panel buffers can be reused safely
  *
  * Protocol (per channel): data stores, __threadfence_system(), then a store of the round number into
  * seq[buffer][me] on the receiver; the receiver polls its LOCAL seq words (volatile) and reads the data
@@ -34,10 +37,13 @@ struct P2pLayout {
 	size_t coarse_seq;  /* uint64 [2][kP2pMaxRanks] */
 	size_t mu_seq;      /* uint64 [2][kP2pMaxRanks] */
 	size_t halo_seq;    /* uint64 [2][kP2pMaxRanks] */
+	size_t panel_seq;   /* uint64 [2][kP2pMaxRanks]  distributed Gauss-Jordan: pivot panels, by owner */
+	size_t gj_done;     /* uint64 [kP2pMaxRanks]     ... steps every rank has finished (flow control) */
 	size_t error;       /* int32 */
 	size_t coarse_val;  /* double [2][world][coarse_cap] */
 	size_t mu_val;      /* double [2][coarse_cap] */
 	size_t halo_val;    /* double2 [2][world][halo_cap] */
+	size_t panel_val;   /* double [2][32 * coarse_cap + 32 * 32 + 8]: row panel, inverse of the pivot block, bad flag */
 	size_t total;
 	int32_t coarse_cap; /* doubles per rank in the coarse channel (n_c + 8 must fit) */
 	int32_t halo_cap;   /* node entries per neighbour in the halo channel */

@@ -736,9 +736,14 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 			: BFMG_LAUNCH((k_coarse_apply<FIRST, false>), coarse_grid, kBlock, 0, nc, 0, CW.E, CW.g, CW.mu, partials, S) == 0) && \
 		BFMG_LAUNCH(k_update_p_coarse, G.vec, kBlock, 0, n_own, lo, CW.C, CW.wrow, CW.mu, r, p, S, (obey)) == 0)
 
-	/* with peer memory each rank applies its own block of rows of E^-1 (an even number of rows each) */
-	int const my_rows = shared ? ((nc + world - 1) / world + 1) / 2 * 2 : nc;
-	int const my_row0 = shared ? bfmg_dist_rank() * my_rows : 0;
+	/* with peer memory each rank inverts and applies its own row blocks of the coarse operator: blocks of 32
+	 * rows, blocks_per of them per rank (coarse_invert) */
+	int const gj_blocks = nc / kGjBlock;
+	int const blocks_per = shared ? (gj_blocks + world - 1) / world : gj_blocks;
+	int const my_b0 = shared ? (bfmg_dist_rank() * blocks_per < gj_blocks ? bfmg_dist_rank() * blocks_per : gj_blocks) : 0;
+	int const my_b1 = shared ? ((bfmg_dist_rank() + 1) * blocks_per < gj_blocks ? (bfmg_dist_rank() + 1) * blocks_per : gj_blocks) : gj_blocks;
+	int const my_row0 = my_b0 * kGjBlock;
+	int const my_rows = (my_b1 - my_b0) * kGjBlock;
 	int const my_coarse_grid = my_rows / kCoarseRows > 0 ? my_rows / kCoarseRows : 1;
 
 	/* exchanges over NVLink peer memory when every rank's halo and coarse vectors fit the mailboxes */
@@ -831,16 +836,37 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		int32_t bad = 0;
 
 		if (
-			coarse_invert(CW) < 0 ||
+			coarse_invert(CW, S, p2p, shared ? bfmg_dist_rank() : 0, blocks_per) < 0 ||
 			BFMG_CHECK(cudaMemcpyAsync(&bad, CW.bad, sizeof bad, cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
 			BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0
 		) {
 			goto out;
 		}
 
+		if (p2p) {
+			/* distributed inversion: a rank only sees the verdicts of the pivot blocks it took part in (none at
+			 * all if it owns no rows): agree over the communicator so that every rank takes the same path */
+
+			double const mine = bad ? 1 : 0;
+			double everyone[BFMG_DIST_MAX_RANKS] = {};
+
+			if (
+				BFMG_CHECK(cudaMemcpyAsync(CW.gpart, &mine, sizeof mine, cudaMemcpyHostToDevice, bfmg_stream())) < 0 ||
+				bfmg_dist_allgather_f64(CW.gpart, CW.ggath, 1) < 0 ||
+				BFMG_CHECK(cudaMemcpyAsync(everyone, CW.ggath, sizeof(double) * world, cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
+				BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0
+			) {
+				goto out;
+			}
+
+			for (int r = 0; r < world; r++) {
+				bad |= everyone[r] != 0;
+			}
+		}
+
 		if (bad) {
-			/* E came out not positive definite (degenerate aggregates): solve with the diagonal
-			 * preconditioner alone.  Identical on every rank: E is replicated bit for bit. */
+			/* E came out not positive definite (degenerate aggregates): solve with the diagonal preconditioner
+			 * alone.  The same on every rank: replicated E is bit-identical, distributed verdicts are shared. */
 			use_coarse = false;
 		}
 
