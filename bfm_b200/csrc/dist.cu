@@ -132,7 +132,7 @@ P2pLayout mailbox_layout(int world) {
 	L.error = at, at += 64;
 	at = align_up(at, 256);
 
-	L.coarse_cap = 3 * 4096 + 64;          /* n_c + 8 doubles per rank: the binning may exceed its 2048-aggregate target */
+	L.coarse_cap = 3 * 6144 + 64;          /* n_c + 8 doubles per rank: up to 2048 x 16^(1/3) aggregates, and the binning may exceed its target */
 	L.halo_cap = 1 << 16;                  /* interface nodes per neighbour */
 
 	L.coarse_val = at, at += align_up((size_t) 2 * world * L.coarse_cap * sizeof(double), 256);

@@ -867,15 +867,25 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 	/* coarse level of the solver for meshes the one-CTA path does not take.  Aggregates: about sqrt(nodes)
 	 * - iterations fall like 1 / sqrt(n_agg) while inverting E grows like n_agg^3 and applying E^-1 like
 	 * n_agg^2 per iteration (measured optimum: ~500 at 0.25 M nodes, ~2000 at 4 M) - at least 32 nodes
-	 * each, at most 2048 (the dense E^-1 is replicated on every rank).
+	 * each, at most 2048 x world^(1/3) (see the cap below).
 	 * BFM_COARSE_AGGREGATES overrides; 0 switches the coarse level off. */
 
 	if (!takes_one_cta(job)) {
 		char const* const env = getenv("BFM_COARSE_AGGREGATES");
 		int64_t target = (int64_t) floor(sqrt((double) mesh->n_nodes) + 0.5);
 
+		/* the cap: on one GPU (or with NCCL exchanges) E^-1 is inverted and applied by every rank in full; with
+		 * peer memory both are split by row blocks over the ranks (coarse.cuh), so the same per-rank set-up time
+		 * (~ n_agg^3 / world) affords world^(1/3) times more aggregates */
+
+		int64_t cap = 2048;
+
+		if (job->part != NULL && bfmg_dist_p2p_status()[0] == 0) {
+			cap = (int64_t) floor(2048 * cbrt((double) job->part->world));
+		}
+
 		target = target > (int64_t) (mesh->n_nodes / 32) ? (int64_t) (mesh->n_nodes / 32) : target;
-		target = target > 2048 ? 2048 : target;
+		target = target > cap ? cap : target;
 
 		if (env != NULL) {
 			target = atoll(env);
