@@ -114,20 +114,137 @@ static int32_t aggregate_nodes(bfm_mesh_t const* mesh, int32_t target, int32_t* 
 		count[node_agg[a]]++;
 	}
 
-	/* bins too small to carry three independent modes join the fullest neighbour (growing rings) */
+	/* Aggregates = the connected pieces of each bin: nodes of one bin joined through elements that lie inside
+	 * it.  On a solid mesh a bin is one piece; on truss-like geometry (bridge-dam.obj) a bin can cut through
+	 * several members that do not touch, and one set of rigid-body modes for all of them is a poor coarse
+	 * function (measured: 535 iterations with plain bins).  Union-find, smaller root wins, so the
+	 * result does not depend on traversal order. */
 
-	for (int64_t b = 0; b < n_bins; b++) {
-		remap[b] = (int32_t) b;
+	size_t const kind = mesh->kind;
+	int32_t* const parent = malloc((nn + 1) * sizeof *parent);
+	int32_t* const size = calloc(nn + 1, sizeof *size);
+
+	if (parent == NULL || size == NULL) {
+		free(parent);
+		free(size);
+		free(count);
+		free(remap);
+		return 0;
 	}
 
+	for (size_t a = 0; a < nn; a++) {
+		parent[a] = (int32_t) a;
+	}
+
+#define FIND(v, out)                               \
+	do {                                           \
+		int32_t r_ = (v);                          \
+		while (parent[r_] != r_) {                 \
+			parent[r_] = parent[parent[r_]];       \
+			r_ = parent[r_];                       \
+		}                                          \
+		(out) = r_;                                \
+	} while (0)
+
+#define UNION(u, v)                                \
+	do {                                           \
+		int32_t ru_, rv_;                          \
+		FIND((u), ru_);                            \
+		FIND((v), rv_);                            \
+		if (ru_ != rv_) {                          \
+			if (ru_ < rv_) parent[rv_] = ru_;      \
+			else parent[ru_] = rv_;                \
+		}                                          \
+	} while (0)
+
+	for (size_t e = 0; e < mesh->n_elems; e++) {
+		size_t const* const el = &mesh->elems[e * kind];
+
+		for (size_t j = 1; j < kind; j++) {
+			for (size_t k = 0; k < j; k++) {
+				if (el[j] < nn && el[k] < nn && node_agg[el[j]] == node_agg[el[k]]) {
+					UNION((int32_t) el[j], (int32_t) el[k]);
+				}
+			}
+		}
+	}
+
+	/* pieces too small to carry three independent modes join a piece they touch through an element (a few
+	 * passes: a chain of tiny pieces needs more than one); what is still small afterwards - isolated nodes,
+	 * islands of one or two nodes - joins the largest piece of its bin, or of the nearest bin that has one */
+
+	for (int pass = 0; pass < 4; pass++) {
+		memset(size, 0, (nn + 1) * sizeof *size);
+
+		for (size_t a = 0; a < nn; a++) {
+			int32_t r;
+			FIND((int32_t) a, r);
+			size[r]++;
+		}
+
+		bool changed = false;
+
+		for (size_t e = 0; e < mesh->n_elems; e++) {
+			size_t const* const el = &mesh->elems[e * kind];
+
+			for (size_t j = 1; j < kind; j++) {
+				int32_t r0, rj;
+
+				if (el[0] >= nn || el[j] >= nn) {
+					continue;
+				}
+
+				FIND((int32_t) el[0], r0);
+				FIND((int32_t) el[j], rj);
+
+				if (r0 != rj && (size[r0] < MIN_NODES_PER_AGGREGATE || size[rj] < MIN_NODES_PER_AGGREGATE)) {
+					int32_t const total = size[r0] + size[rj];
+
+					UNION(r0, rj);
+					FIND(r0, r0);
+					size[r0] = total;
+					changed = true;
+				}
+			}
+		}
+
+		if (!changed) {
+			break;
+		}
+	}
+
+	memset(size, 0, (nn + 1) * sizeof *size);
+
+	for (size_t a = 0; a < nn; a++) {
+		int32_t r;
+		FIND((int32_t) a, r);
+		size[r]++;
+	}
+
+	/* largest piece of every bin (root node id; -1: the bin has no piece of three nodes) */
+
 	for (int64_t b = 0; b < n_bins; b++) {
-		if (count[b] == 0 || count[b] >= MIN_NODES_PER_AGGREGATE) {
+		remap[b] = -1;
+	}
+
+	for (size_t a = 0; a < nn; a++) {
+		if (parent[a] == (int32_t) a && size[a] >= MIN_NODES_PER_AGGREGATE) {
+			int32_t const b = node_agg[a];
+
+			if (remap[b] < 0 || size[a] > size[remap[b]]) {
+				remap[b] = (int32_t) a;
+			}
+		}
+	}
+
+	for (size_t a = 0; a < nn; a++) {
+		if (parent[a] != (int32_t) a || size[a] >= MIN_NODES_PER_AGGREGATE) {
 			continue;
 		}
 
-		int64_t const bx = b % nbx;
-		int64_t const by = b / nbx;
-		int64_t best = -1;
+		int64_t const bx = node_agg[a] % nbx;
+		int64_t const by = node_agg[a] / nbx;
+		int32_t best = remap[node_agg[a]];
 
 		for (int64_t ring = 1; best < 0 && ring < nbx + nby; ring++) {
 			for (int64_t dy = -ring; dy <= ring; dy++) {
@@ -139,49 +256,47 @@ static int32_t aggregate_nodes(bfm_mesh_t const* mesh, int32_t target, int32_t* 
 						continue;
 					}
 
-					int64_t const c = cy * nbx + cx;
+					int32_t const cand = remap[cy * nbx + cx];
 
-					if (count[c] >= MIN_NODES_PER_AGGREGATE && remap[c] == c && (best < 0 || count[c] > count[best])) {
-						best = c;
+					if (cand >= 0 && (best < 0 || size[cand] > size[best])) {
+						best = cand;
 					}
 				}
 			}
 		}
 
-		if (best < 0) { /* no bin of the mesh holds three nodes: no coarse level */
+		if (best < 0) { /* no piece of the whole mesh holds three nodes: no coarse level */
+			free(parent);
+			free(size);
 			free(count);
 			free(remap);
 			return 0;
 		}
 
-		remap[b] = (int32_t) best;
+		parent[a] = best; /* best is a root of a big piece and stays one: big roots are never re-parented here */
 	}
 
-	/* compact: ids follow bin order (deterministic); only bins that keep their own nodes get one */
+	/* compact: ids in order of each piece's smallest node (its root) - deterministic */
 
-	int32_t* const id = count; /* the counts are no longer needed */
 	int32_t n_agg = 0;
 
-	for (int64_t b = 0; b < n_bins; b++) {
-		id[b] = -1;
+	for (size_t a = 0; a < nn; a++) {
+		size[a] = parent[a] == (int32_t) a ? n_agg++ : -1;
 	}
+
+	bool const ok = n_agg > 0;
 
 	for (size_t a = 0; a < nn; a++) {
-		id[remap[node_agg[a]]] = -2; /* in use */
+		int32_t r;
+		FIND((int32_t) a, r);
+		node_agg[a] = size[r];
 	}
 
-	for (int64_t b = 0; b < n_bins; b++) {
-		if (id[b] == -2) {
-			id[b] = n_agg++;
-		}
-	}
+#undef FIND
+#undef UNION
 
-	bool const ok = true;
-
-	for (size_t a = 0; a < nn; a++) {
-		node_agg[a] = id[remap[node_agg[a]]];
-	}
-
+	free(parent);
+	free(size);
 	free(count);
 	free(remap);
 
