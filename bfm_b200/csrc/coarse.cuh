@@ -519,7 +519,7 @@ __device__ __forceinline__ double const* gj_panel(Scalars const* S, GjPanel cons
  * 64 x 64 tile per CTA, 4 x 4 per thread.
  * (A 128 x 128 / 8 x 8-per-thread variant was measured SLOWER - 168 registers, one CTA per SM: 620 us against 380 us
  * per launch at n = 6304 - so the small tile stays.) */
-__global__ void __launch_bounds__(256) k_gj_update(int n, int k, double* __restrict__ E, int row_lo, int row_hi, GjPanel G, Scalars* S) {
+__global__ void __launch_bounds__(256, 4) k_gj_update(int n, int k, double* __restrict__ E, int row_lo, int row_hi, GjPanel G, Scalars* S) {
 	__shared__ double col[64][kGjBlock + 1]; /* E[I, K] */
 	__shared__ double row[kGjBlock][64 + 1]; /* R[K, J] */
 
