@@ -21,7 +21,8 @@
  * can be at most one round ahead of a peer, because its next post needs that peer's current one.  Round
  * counters live on the device (Scalars) so that kernels skipped after convergence skip their rounds on
  * every rank alike; each solve starts from zeroed seq words behind a collective barrier.
- * Every spin has a time-out that raises the mailbox's error word instead of hanging the GPU.
+ * Every spin has a time-out (10 s) that raises the mailbox's error word instead of hanging the GPU; once raised,
+ * later waits of the same solve give up at once and the solve reports the failure.
  */
 #pragma once
 
@@ -78,10 +79,17 @@ __device__ __forceinline__ uint64_t p2p_now_ns() {
 	return t;
 }
 
-/* spin until the local word reaches `round`; false (and the error word set) after ~4 s */
+/* spin until the local word reaches `round`; false (and the error word set) after ~10 s, and at once when an
+ * earlier wait of this solve has already failed - a broken solve drains quickly instead of timing out per kernel */
 __device__ __forceinline__ bool p2p_wait(P2p const& X, uint64_t const* seq, uint64_t round) {
 	if (p2p_load_u64(seq) >= round) {
 		return true;
+	}
+
+	volatile int32_t* const error = (volatile int32_t*) (X.box[X.me] + X.L.error);
+
+	if (*error) {
+		return false;
 	}
 
 	uint64_t const t0 = p2p_now_ns();
@@ -91,8 +99,8 @@ __device__ __forceinline__ bool p2p_wait(P2p const& X, uint64_t const* seq, uint
 			return true;
 		}
 
-		if ((spins & 1023) == 1023 && p2p_now_ns() - t0 > 4000000000ull) {
-			*(volatile int32_t*) (X.box[X.me] + X.L.error) = 1;
+		if ((spins & 1023) == 1023 && (*error || p2p_now_ns() - t0 > 10000000000ull)) {
+			*error = 1;
 			return false;
 		}
 	}
