@@ -459,6 +459,11 @@ bfmi_coarse_t* bfmi_coarse_build(bfm_state_t* state, bfm_mesh_t const* gmesh, bf
 		n_pairs = uniq;
 	}
 
+	for (size_t i = 0; i < n_pairs; i++) {
+		int64_t const span = llabs((int64_t) (pairs[i] >> 32) - (int64_t) (pairs[i] & 0xffffffffu));
+		c->agg_span = span > c->agg_span ? (int32_t) span : c->agg_span;
+	}
+
 	/* CSR of the aggregate graph (both directions are present: the pair loop above is symmetric) */
 
 	int32_t* const adj_ptr = calloc((size_t) n_agg + 2, sizeof *adj_ptr);
@@ -586,6 +591,7 @@ int bfmi_coarse_upload(bfmi_coarse_t* c) {
 	d->n_agg = c->n_agg;
 	d->n_colors = c->n_colors;
 	d->nc = (3 * c->n_agg + 31) / 32 * 32;
+	d->half_bw = 3 * c->agg_span + 2;
 
 	if (
 		mirror((void**) &d->agg, c->agg, (size_t) c->n_local * sizeof(int32_t)) < 0 ||

@@ -473,10 +473,10 @@ __global__ void __launch_bounds__(1024) k_gj_diag(int n, int k, double const* __
 }
 
 /* row panel: E[K, J] = P * E[K, J] for every column block J != k; one CTA per J */
-__global__ void __launch_bounds__(1024) k_gj_row(int n, int k, double* __restrict__ E, double const* __restrict__ P) {
+__global__ void __launch_bounds__(1024) k_gj_row(int n, int k, int lim, double* __restrict__ E, double const* __restrict__ P) {
 	int const J = blockIdx.x;
 
-	if (J == k) {
+	if (J == k || J * kGjBlock >= lim) {
 		return;
 	}
 
@@ -519,13 +519,18 @@ __device__ __forceinline__ double const* gj_panel(Scalars const* S, GjPanel cons
  * 64 x 64 tile per CTA, 4 x 4 per thread.
  * (A 128 x 128 / 8 x 8-per-thread variant was measured SLOWER - 168 registers, one CTA per SM: 620 us against 380 us
  * per launch at n = 6304 - so the small tile stays.) */
-__global__ void __launch_bounds__(256, 4) k_gj_update(int n, int k, double* __restrict__ E, int row_lo, int row_hi, GjPanel G, Scalars* S) {
+__global__ void __launch_bounds__(256, 4) k_gj_update(int n, int k, int lim, double* __restrict__ E, int row_lo, int row_hi, GjPanel G, Scalars* S) {
 	__shared__ double col[64][kGjBlock + 1]; /* E[I, K] */
 	__shared__ double row[kGjBlock][64 + 1]; /* R[K, J] */
 
 	int const i0 = row_lo + blockIdx.y * 64;
 	int const j0 = blockIdx.x * 64;
 	int const kb = k * kGjBlock;
+
+	if (i0 >= lim || j0 >= lim) {
+		return; /* E[i, K] or R[K, j] is still all zero there: E is banded and pivots 0..k have filled rows and
+		         * columns below lim = 32 (k + 1) + half_bw only (see coarse_invert) */
+	}
 
 	double const* R = E + (size_t) kb * n;
 
@@ -598,7 +603,7 @@ __global__ void __launch_bounds__(256, 4) k_gj_update(int n, int k, double* __re
 /* column panel: E[I, K] = -E[I, K] * P for the row blocks I != k of this rank;  E[K, K] = P where it owns K.
  * One CTA per row block from row_lo on.  Distributed: P comes from the mailbox, the owner's "not positive
  * definite" verdict is taken over, and the last CTA acknowledges the step to every peer. */
-__global__ void __launch_bounds__(1024) k_gj_col(int n, int k, double* __restrict__ E, double const* __restrict__ Plocal, int row_lo, GjPanel G, int32_t* bad, Scalars* S) {
+__global__ void __launch_bounds__(1024) k_gj_col(int n, int k, int lim, double* __restrict__ E, double const* __restrict__ Plocal, int row_lo, GjPanel G, int32_t* bad, Scalars* S) {
 	int const I = row_lo / kGjBlock + blockIdx.x;
 
 	__shared__ double p[kGjBlock][kGjBlock + 1];
@@ -610,7 +615,16 @@ __global__ void __launch_bounds__(1024) k_gj_col(int n, int k, double* __restric
 	double const* P = Plocal;
 
 	if (G.dist) {
-		P = gj_panel(S, G) + 32 * (size_t) n; /* the round was awaited by k_gj_update, earlier in the stream */
+		/* k_gj_update waited for this round too, but its CTAs beyond lim return before they do */
+
+		if (threadIdx.x == 0) {
+			P2p const& X = S->X;
+			p2p_wait(X, p2p_seq(X, X.me, X.L.panel_seq, G.round, G.owner), G.round);
+		}
+
+		__syncthreads();
+
+		P = gj_panel(S, G) + 32 * (size_t) n;
 
 		if (blockIdx.x == 0 && threadIdx.x == 0 && __ldcg(&P[kGjBlock * kGjBlock]) != 0) {
 			*bad = 1;
@@ -627,7 +641,7 @@ __global__ void __launch_bounds__(1024) k_gj_col(int n, int k, double* __restric
 		tile[(size_t) i * n + j] = p[i][j];
 	}
 
-	else {
+	else if (I * kGjBlock < lim) { /* beyond lim the column panel is zero and stays zero */
 		double s = 0;
 
 #pragma unroll
@@ -752,17 +766,21 @@ int coarse_invert(CoarseWork const& W, Scalars* S, bool dist, int rank, int bloc
 
 		bool const mine = !dist || G.owner == rank;
 
+		/* E starts banded (adjacent aggregates have close numbers) and pivot blocks 0..k fill rows and columns
+		 * below lim only: everything at or beyond lim is still zero in both panels - a third of the n^3 work */
+		int const lim = (k + 1) * kGjBlock + W.C.half_bw < n ? (k + 1) * kGjBlock + W.C.half_bw : n;
+
 		if (mine && (
 			BFMG_LAUNCH(k_gj_diag, 1, 1024, 0, n, k, W.E, W.P, W.bad) < 0 ||
-			BFMG_LAUNCH(k_gj_row, blocks, 1024, 0, n, k, W.E, W.P) < 0 ||
+			BFMG_LAUNCH(k_gj_row, blocks, 1024, 0, n, k, lim, W.E, W.P) < 0 ||
 			(dist && BFMG_LAUNCH(k_gj_bcast, 64, kBlock, 0, n, k, W.E, W.P, W.bad, G, S) < 0)
 		)) {
 			return -1;
 		}
 
 		if (row_hi > row_lo && (
-			BFMG_LAUNCH(k_gj_update, tiles, 256, 0, n, k, W.E, row_lo, row_hi, G, S) < 0 ||
-			BFMG_LAUNCH(k_gj_col, my_b1 - my_b0, 1024, 0, n, k, W.E, W.P, row_lo, G, W.bad, S) < 0
+			BFMG_LAUNCH(k_gj_update, tiles, 256, 0, n, k, lim, W.E, row_lo, row_hi, G, S) < 0 ||
+			BFMG_LAUNCH(k_gj_col, my_b1 - my_b0, 1024, 0, n, k, lim, W.E, W.P, row_lo, G, W.bad, S) < 0
 		)) {
 			return -1;
 		}

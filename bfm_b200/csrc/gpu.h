@@ -135,6 +135,7 @@ typedef struct {
 	int32_t n_agg;
 	int32_t n_colors;
 	int32_t nc;          /* coarse dimension: 3 * n_agg rounded up to a multiple of 32 */
+	int32_t half_bw;     /* E[i][j] = 0 for |i - j| > half_bw: adjacent aggregates have close numbers (bins in grid order) */
 
 	int32_t* agg;        /* [nb] aggregate of every local block row (owned and ghost) */
 	double* wgeom;       /* [nb] double2: node position relative to its aggregate's centroid */

@@ -126,6 +126,7 @@ typedef struct bfmi_coarse {
 	int32_t n_agg;
 	int32_t n_colors;
 	int32_t n_local;     /* nodes of the mesh this rank assembles (owned + ghost) */
+	int32_t agg_span;    /* largest |g - h| over adjacent aggregates g, h */
 
 	int32_t* agg;        /* [n_local] */
 	double* wgeom;       /* [n_local][2] */
