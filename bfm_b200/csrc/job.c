@@ -867,15 +867,15 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 	/* coarse level of the solver for meshes the one-CTA path does not take.  How many aggregates: iterations fall
 	 * like 1 / sqrt(n_agg) while inverting E grows like n_agg^3 and applying E^-1 like n_agg^2 per iteration;
 	 * minimising  c sqrt(n / n_agg) (a n + b n_agg^2) + d n_agg^3  with the measured constants gives
-	 * n_agg ~ 2.6 n^(3/7): ~500 at 0.25 M nodes, ~1800 at 4 M, ~3900 at 25 M (measured there: 4.65 s with 2093
-	 * aggregates, 4.11 s with 3850).  At least 32 nodes per aggregate; at most 4096 (E^-1 is 1.2 GB then), 2048
-	 * when several GPUs exchange over NCCL and therefore each invert all of E.
+	 * n_agg ~ 3.4 n^(3/7): ~700 at 0.25 M nodes, ~2300 at 4 M, ~5000 at 25 M (measured there: 4.65 s with 2093
+	 * aggregates, 3.83 s with 3850; the optimum is flat).  At least 32 nodes per aggregate; at most 5120 (E^-1 is
+	 * 1.9 GB then), 2048 when several GPUs exchange over NCCL and therefore each invert all of E.
 	 * BFM_COARSE_AGGREGATES overrides; 0 switches the coarse level off. */
 
 	if (!takes_one_cta(job)) {
 		char const* const env = getenv("BFM_COARSE_AGGREGATES");
-		int64_t target = (int64_t) floor(2.6 * pow((double) mesh->n_nodes, 3.0 / 7.0) + 0.5);
-		int64_t const cap = job->part != NULL && bfmg_dist_p2p_status()[0] != 0 ? 2048 : 4096;
+		int64_t target = (int64_t) floor(3.4 * pow((double) mesh->n_nodes, 3.0 / 7.0) + 0.5);
+		int64_t const cap = job->part != NULL && bfmg_dist_p2p_status()[0] != 0 ? 2048 : 5120;
 
 		target = target > (int64_t) (mesh->n_nodes / 32) ? (int64_t) (mesh->n_nodes / 32) : target;
 		target = target > cap ? cap : target;
