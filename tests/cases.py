@@ -29,6 +29,8 @@ CASES = {
 	"plate_funky_20x5": True,   # FUNKY + LINEAR forces together (order of accumulation)
 	"plate_neumann_16x4": True, # Neumann tip load on generated edges
 	"gear60": False,            # config 3: irregular sparsity, mixed Dirichlet/Neumann (16 410 DOF)
+	"plate_jitter_40x10": True,     # interior nodes moved by +-0.2 h (seed 0): irregular geometry, no exact cancellations
+	"plate_q4_jitter_24x6": True,   # the same on quads: the Jacobian differs at every Gauss point; plane strain
 }
 
 HEAVY = {"gear60"}  # seconds-to-minutes on the dense reference
@@ -65,6 +67,25 @@ def plate_arrays(nx: int, ny: int, lx: float = 4.0, ly: float = 1.0, kind: int =
 		elems = np.stack([d, c, a, b], axis=1)
 
 	return coords, elems.astype(np.uint64)
+
+
+def jittered_plate_arrays(nx: int, ny: int, kind: int = 3, amplitude: float = 0.2, seed: int = 0):
+	"""the structured plate with every interior node moved by a uniform +-amplitude * h in x and y
+	(numpy RandomState(seed): the same numbers wherever the fixtures are regenerated)"""
+
+	coords, elems = plate_arrays(nx, ny, kind=kind)
+	hx, hy = 4.0 / nx, 1.0 / ny
+	rng = np.random.RandomState(seed)
+	shift = rng.uniform(-amplitude, amplitude, size=coords.shape) * np.array([hx, hy])
+
+	i = np.tile(np.arange(nx + 1), ny + 1)
+	j = np.repeat(np.arange(ny + 1), nx + 1)
+	interior = (i > 0) & (i < nx) & (j > 0) & (j < ny)
+
+	coords = coords.copy()
+	coords[interior] += shift[interior]
+
+	return coords, elems
 
 
 def _plate_mesh(binding, nx, ny, kind=3, edges=False):
@@ -165,6 +186,17 @@ def build(name: str, binding=None) -> Case:
 		mask = _lowest_nodes(mesh, 16 if name == "bridge" else 64)
 		conds = [(api.Condition.DIRICHLET_X, 0.0, mask), (api.Condition.DIRICHLET_Y, 0.0, mask)]
 		return _assemble_case(name, binding, mesh, api.CSim.PLANAR_STRESS, AA7075, [GRAVITY], conds)
+
+	if name.startswith("plate_") and "jitter" in name:
+		kind = 4 if "_q4_" in name else 3
+		nx, ny = (int(v) for v in name.rsplit("_", 1)[1].split("x"))
+		coords, elems = jittered_plate_arrays(nx, ny, kind)
+		mesh = api.Mesh.from_arrays(coords, elems, binding=binding)
+		left = coords[:, 0] == 0.0
+		conds = [(api.Condition.DIRICHLET_X, 0.0, left), (api.Condition.DIRICHLET_Y, 0.0, left)]
+		sim_kind = api.CSim.PLANAR_STRAIN if kind == 4 else api.CSim.PLANAR_STRESS
+
+		return _assemble_case(name, binding, mesh, sim_kind, STEEL, [GRAVITY], conds)
 
 	if name.startswith("plate_"):
 		kind = 4 if "_q4_" in name else 3
@@ -313,6 +345,15 @@ def build_oracle_only(name: str):
 		coords, elems, edges, domains = _read_lepl(os.path.join(GOLDEN, "meshes", ez[name][0]))
 		sim_kind, E, nu, rho, g, conds = _read_problem(os.path.join(GOLDEN, "problems", ez[name][1]), len(coords), edges, domains)
 		return orc.Problem(coords, elems, sim_kind, E, nu, rho, forces=[(0.0, g)] if g is not None else [], conditions=conds, edges=edges)
+
+	if name.startswith("plate_") and "jitter" in name:
+		kind = 4 if "_q4_" in name else 3
+		nx, ny = (int(v) for v in name.rsplit("_", 1)[1].split("x"))
+		coords, elems = jittered_plate_arrays(nx, ny, kind)
+		left = (coords[:, 0] == 0.0).astype(np.uint8)
+		E, nu, rho = STEEL
+
+		return orc.Problem(coords, elems, 1 if kind == 4 else 2, E, nu, rho, forces=[GRAVITY], conditions=[(0, 0.0, left), (1, 0.0, left)])
 
 	if name.startswith("plate_") and "neumann" not in name:
 		kind = 4 if "_q4_" in name else 3
