@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["lepl8", "lepl8_all_kinds", "bridge", "plate_80x20", "plate_q4_24x6", "plate_neumann_16x4", "plate_funky_20x5", "lepl8_axisym", "gear60"]
+CASES = ["lepl8", "lepl8_all_kinds", "bridge", "plate_80x20", "plate_q4_24x6", "plate_neumann_16x4", "plate_funky_20x5", "lepl8_axisym", "gear60", "plate_jitter_40x10"]
 
 
 def _gpu_count() -> int:
