@@ -1,13 +1,18 @@
 /*
- * solver.cu - FP64 Jacobi-preconditioned conjugate gradient on sm_100a.
+ * solver.cu - FP64 preconditioned conjugate gradient on sm_100a.
  *
  * The operator is the SELL-32 node-block matrix produced by assembly.cu.  Jacobi preconditioning is
  * applied once as a symmetric diagonal scaling  A^ = D^-1/2 A D^-1/2,  b^ = D^-1/2 b,  so the loop
- * is plain CG on A^ and never streams a preconditioner vector.  One iteration is three kernels:
+ * never streams a diagonal.  Without a coarse level one iteration is three kernels:
  *
  *   k_spmv_dot   q = A^ p          + partial p.q   -> last CTA: alpha = rho / p.q
  *   k_update_xr  x += alpha p, r -= alpha q + partial r.r -> last CTA: beta, rho, convergence flag
  *   k_update_p   p = r + beta p
+ *
+ * Meshes beyond the one-CTA solver (batch.cu) get the two-level preconditioner of coarse.cuh on top -
+ * z = r + W E^-1 W^T r with the rigid-body modes of node aggregates - which replaces k_update_p by
+ * k_restrict, k_coarse_apply and k_update_p_coarse and cuts the iteration count from ~12 L/h to
+ * ~30 H/h (46 429 -> 880 at 8 M DOF).  The stopping test stays on the unpreconditioned residual.
  *
  * Scalars never leave the device: each reducing kernel writes one partial per CTA and the last CTA
  * to finish (ticket counter) folds them in a fixed order - deterministic, no float atomics.  Once
@@ -19,6 +24,9 @@
  * reducing kernel leaves its partial in S->part, which an all-gather spreads to every rank; a one-thread
  * kernel then folds the world's partials in rank order and applies the same scalar update as the last
  * CTA does on one GPU.  Every rank computes bit-identical scalars, so all ranks stop together.
+ * With NVLink peer memory available (p2p.cuh) no collective is launched inside the loop at all: the
+ * reducing kernels store their shares straight into the peers' mailboxes, the halo is posted and taken
+ * by two small kernels, and - as on one GPU - a chunk of iterations is replayed as a CUDA graph.
  *
  * All three kernels are HBM-bound (FP64 SpMV ~ 0.25 flop/B): no tensor cores.  Algorithmic bytes per
  * block row (node) and iteration, structured P1 plate (7 blocks per row):
