@@ -89,8 +89,16 @@ static void half_edge_sort(bfm_edge_t* v, bfm_edge_t* tmp, size_t n) {
 
 	size_t const half = n / 2;
 
+	/* the two halves use disjoint scratch, so big ones can be sorted by different threads (OpenMP tasks, when
+	 * called from a parallel region); the merge keeps the result independent of who sorted what */
+
+#pragma omp task shared(v, tmp) if (n > ((size_t) 1 << 18))
 	half_edge_sort(v, tmp, half);
-	half_edge_sort(v + half, tmp, n - half);
+
+#pragma omp task shared(v, tmp) if (n > ((size_t) 1 << 18))
+	half_edge_sort(v + half, tmp + half, n - half);
+
+#pragma omp taskwait
 
 	size_t l = 0, r = half, o = 0;
 
@@ -133,6 +141,7 @@ int bfmx_mesh_compute_edges(bfm_mesh_t* mesh) {
 		return -1;
 	}
 
+#pragma omp parallel for schedule(static) if (n_half > ((size_t) 1 << 18))
 	for (size_t e = 0; e < mesh->n_elems; e++) {
 		for (size_t j = 0; j < sides; j++) {
 			bfm_edge_t* const he = &edges[e * sides + j];
@@ -144,7 +153,10 @@ int bfmx_mesh_compute_edges(bfm_mesh_t* mesh) {
 		}
 	}
 
+#pragma omp parallel if (n_half > ((size_t) 1 << 18))
+#pragma omp single
 	half_edge_sort(edges, tmp, n_half);
+
 	free(tmp);
 
 	size_t n_out = 0;
