@@ -440,7 +440,8 @@ def main():
 		# two-level preconditioner: restriction (index 4 B + r 16 B + W row 16 B per node), E^-1 g (dense, nc x nc doubles),
 		# prolongation fused in the p update (+ W row 16 B + aggregate id 4 B per node)
 		nc = (s["coarse_dim"] + 31) // 32 * 32
-		iter_bytes += (36 + 20) * (n_own // 2) + 8 * nc * nc
+		apply_rows = nc // world if s.get("uses_peer_memory") else nc  # over peer memory each rank applies its own rows of E^-1
+		iter_bytes += (36 + 20) * (n_own // 2) + 8 * nc * apply_rows
 
 	peaks = {}
 	peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
