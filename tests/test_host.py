@@ -550,3 +550,24 @@ def test_bench_reference_arm_prints_the_contract_line():
 	assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 1
 	assert line["e2e"] == {"value": line["value"], "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 	assert line["config"]["n_dofs"] == 50025002 and line["higher_is_better"] is True
+
+
+def test_edge_derivation_parallel_path_matches_live_reference(lib, ref, tmp_path):
+	"""above 2^18 half-edges the stable merge sort of bfmx_mesh_compute_edges runs as OpenMP tasks: the edge list
+	(order, node pairs, element pairs) must still be the reference reader's"""
+
+	nx, ny = 320, 150  # 96 000 triangles -> 288 000 half-edges
+	coords, elems = cases.plate_arrays(nx, ny)
+	path = tmp_path / "plate.obj"
+
+	with open(path, "w") as f:
+		np.savetxt(f, np.c_[coords, np.zeros(len(coords))], fmt="v %.17g %.17g %g")
+		np.savetxt(f, elems.astype(np.int64) + 1, fmt="f %d %d %d")
+
+	want = api.Mesh_wavefront(str(path), binding=ref).edges_array
+	got_reader = api.Mesh_wavefront(str(path), binding=lib).edges_array
+	got_generator = ext.plate(nx, ny, binding=lib, with_edges=True).edges_array
+
+	assert len(want) > (1 << 17)
+	assert np.array_equal(got_reader, want)
+	assert np.array_equal(got_generator, want)
