@@ -130,3 +130,86 @@ def test_two_rank_gloo_pcg(tmp_path):
 
 	err, iters = out.read_text().split()
 	assert float(err) <= 1e-9 and int(iters) > 10
+
+
+def test_emulated_partitioned_two_level_pcg(lib, golden):
+	"""the distributed form of the coarse level (coarse.cuh): every rank restricts over its OWNED rows only, the
+	partial W^T r are summed over the ranks, E^-1 is applied, and each rank prolongs to its own rows - with the
+	aggregates the library computes on the global mesh.  Same answer as the reference, far fewer iterations."""
+
+	import ctypes as C
+
+	import scipy.sparse as sp
+
+	name, world = "plate_80x20", 3
+	case = cases.build(name, lib)
+	oracle = cases.oracle_problem(case).system()
+	A, b = oracle.scipy(), oracle.b.copy()
+	nn = case.mesh.n_nodes
+	coords = case.mesh.coords_array
+
+	n_agg, n_colors = C.c_int32(), C.c_int32()
+	agg = np.zeros(nn, np.int32)
+	color = np.zeros(4 * 40 + 16, np.int32)
+	assert not lib.lib.bfmx_coarse_plan(case.mesh.c_mesh, 40, C.byref(n_agg), C.byref(n_colors), agg.ctypes.data_as(ext.c_int32_p), color.ctypes.data_as(ext.c_int32_p))
+	n_agg = n_agg.value
+	assert n_agg >= 16
+
+	# W in the Jacobi-scaled variables: rows S_a R_a (coarse.cuh)
+	d = 1 / np.sqrt(np.abs(A.diagonal()))
+	Ah = (sp.diags(d) @ A @ sp.diags(d)).tocsr()
+	bh = d * b
+	count = np.bincount(agg, minlength=n_agg)
+	cx = np.bincount(agg, coords[:, 0], n_agg) / count
+	cy = np.bincount(agg, coords[:, 1], n_agg) / count
+	a = np.arange(nn)
+	w = 1 / d
+	W = sp.csr_matrix((
+		np.concatenate([w[2 * a], w[2 * a + 1], -w[2 * a] * (coords[:, 1] - cy[agg]), w[2 * a + 1] * (coords[:, 0] - cx[agg])]),
+		(np.concatenate([2 * a, 2 * a + 1, 2 * a, 2 * a + 1]), np.concatenate([3 * agg, 3 * agg + 1, 3 * agg + 2, 3 * agg + 2])),
+	), shape=(2 * nn, 3 * n_agg))
+	Einv = np.linalg.inv((W.T @ Ah @ W).toarray())
+
+	parts = [ext.partition(case.mesh, r, world) for r in range(world)]
+	rows = [np.arange(2 * int(p["first_node"]), 2 * int(p["end_node"])) for p in parts]
+
+	def precondition(r_full):
+		g = sum(W[rows[k]].T @ r_full[rows[k]] for k in range(world))  # per-rank partial restrictions, folded in rank order
+		mu = Einv @ g
+		z = r_full.copy()
+
+		for k in range(world):
+			z[rows[k]] += W[rows[k]] @ mu  # each rank prolongs to its own rows
+
+		return z
+
+	def pcg(M):
+		x = np.zeros_like(bh)
+		r = bh.copy()
+		z = M(r)
+		p = z.copy()
+		rz = r @ z
+
+		for it in range(1, 5000):
+			q = np.concatenate([Ah[rows[k]] @ p for k in range(world)])  # owned rows of the SpMV
+			alpha = rz / (p @ q)
+			x += alpha * p
+			r -= alpha * q
+
+			if r @ r <= 1e-24 * (bh @ bh):
+				return d * x, it
+
+			z = M(r)
+			new = r @ z
+			p = z + (new / rz) * p
+			rz = new
+
+		raise AssertionError("no convergence")
+
+	x_two, it_two = pcg(precondition)
+	_, it_plain = pcg(lambda r: r)
+
+	want = golden[f"{name}/effects"].reshape(-1)
+
+	assert np.linalg.norm(x_two - want) / np.linalg.norm(want) <= 1e-9
+	assert it_two * 3 < it_plain, (it_two, it_plain)
