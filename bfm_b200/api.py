@@ -564,13 +564,15 @@ class System:
 	def get(self, i: int, j: int) -> float:
 		return self.binding.lib.bfm_matrix_get(C.byref(self.c_system.A), i, j)
 
-	def dense(self) -> np.ndarray:
-		"""whole matrix through bfm_matrix_get (small systems only)"""
+	def dense(self, copy: bool = True) -> np.ndarray:
+		"""whole matrix through bfm_matrix_get (small systems only); copy=False: a view of a FULL row-major
+		matrix's own storage (valid until the system changes), for systems too large to hold twice"""
 
 		A = self.c_system.A
 
 		if A.kind == abi.MATRIX_KIND_FULL and A.major == abi.MATRIX_MAJOR_ROW:
-			return np.ctypeslib.as_array(A.full.data, shape=(self.n, self.n)).copy()
+			view = np.ctypeslib.as_array(A.full.data, shape=(self.n, self.n))
+			return view.copy() if copy else view
 
 		get = self.binding.lib.bfm_matrix_get
 		ref = C.byref(A)

@@ -25,6 +25,8 @@ CASES = {
 	"bridge_dam": True,         # the mesh examples/deformation.py actually loads, 64 clamped nodes
 	"plate_40x10": True,        # config 4 at oracle sizes
 	"plate_80x20": True,
+	"plate_160x40": True,       # SURVEY.md 8(d) parity size: 13 202 DOF (the reference arm's sample in bench.py)
+	"plate_300x75": False,      # 45 752 DOF, just under the dense reference's ceiling of 46 340
 	"plate_q4_24x6": True,      # quads
 	"plate_funky_20x5": True,   # FUNKY + LINEAR forces together (order of accumulation)
 	"plate_neumann_16x4": True, # Neumann tip load on generated edges
@@ -33,7 +35,7 @@ CASES = {
 	"plate_q4_jitter_24x6": True,   # the same on quads: the Jacobian differs at every Gauss point; plane strain
 }
 
-HEAVY = {"gear60"}  # seconds-to-minutes on the dense reference
+HEAVY = {"gear60", "plate_300x75"}  # seconds-to-minutes on the dense reference
 
 
 @dataclass

@@ -206,6 +206,51 @@ def test_large_plate_properties(nx, ny, kind, lib):
 	assert -1.55e-4 < tip < -1.45e-4
 
 
+def _sparse_direct_reference(oracle):
+	"""displacements of the oracle's sparse system by SuperLU (scipy.sparse.linalg.splu) + one step of
+	iterative refinement: a direct solver that shares no code with this repository (the matrix comes from
+	oracle/bfm_oracle.c, itself pinned bit for bit to the compiled reference)"""
+
+	import scipy.sparse.linalg as spl
+
+	A = oracle.scipy().tocsc()
+	lu = spl.splu(A, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+	x = lu.solve(oracle.b.copy())
+
+	# at 2 M DOF the factorisation's own forward error is ~3e-10 (eps * cond): refine twice, report the last step
+	for _ in range(2):
+		dx = lu.solve(oracle.b - A @ x)
+		x += dx
+
+	return x, float(np.linalg.norm(dx) / np.linalg.norm(x))
+
+
+@pytest.mark.parametrize("nx,ny,kind,jitter", [(448, 112, 3, True), (1000, 250, 3, False), (600, 150, 4, False), (2000, 500, 3, False)])
+def test_displacements_match_independent_sparse_direct_solve(nx, ny, kind, jitter, lib):
+	"""above the dense reference's ceiling (46 340 DOF): 0.1 M, 0.5 M and 2 M DOF against SuperLU on the
+	oracle's matrix - relative L2 <= 1e-9, the north star's bar, where no band LU of the reference can go"""
+
+	if jitter:
+		coords, elems = cases.jittered_plate_arrays(nx, ny, kind)
+		mesh = api.Mesh.from_arrays(coords, elems, binding=lib)
+	else:
+		mesh = ext.plate(nx, ny, kind=kind, binding=lib)
+
+	left = mesh.coords_array[:, 0] == 0.0
+	conds = [(api.Condition.DIRICHLET_X, 0.0, left), (api.Condition.DIRICHLET_Y, 0.0, left)]
+	case = cases._assemble_case("big", lib, mesh, api.CSim.PLANAR_STRESS, cases.STEEL, [cases.GRAVITY], conds)
+
+	case.sim.run()
+	stats = ext.last_stats(lib)
+
+	assert stats["cg_converged"] == 1 and stats["cg_rel_residual"] <= 1e-12
+
+	want, last_refinement = _sparse_direct_reference(cases.oracle_problem(case).system())
+
+	assert last_refinement <= 1e-11  # the checker itself has converged
+	assert rel_l2(case.instance.effects.reshape(-1), want) <= REL_L2, (stats, last_refinement)
+
+
 # ---- small systems: the one-CTA solver and batches (BASELINE.json configs[4]) ---------------------------
 
 
