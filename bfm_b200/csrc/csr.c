@@ -295,7 +295,7 @@ void bfmi_pcg_options(size_t n, bfmg_pcg_opts_t* opts) {
 
 	opts->tol = 1e-12; /* BASELINE.json north_star: CG stopped at a relative residual <= 1e-12 */
 	opts->max_iter = (int32_t) (100 * sqrt((double) n) + 10000);
-	opts->chunk = 64;
+	opts->chunk = 0; /* the solver's default: 64, or 8 with the multilevel preconditioner */
 	opts->verify = 1;
 	opts->true_tol = 1e-10; /* normwise backward error, see solver.cu */
 	opts->max_restarts = 0;
@@ -395,7 +395,7 @@ int bfmi_csr_solve(bfm_matrix_t* matrix, bfm_vec_t* y) {
 	}
 
 	else {
-		solved = bfmg_pcg(&csr->plan->dev, csr->d_val, d_b, d_x, &opts, &res, NULL, NULL);
+		solved = bfmg_pcg(&csr->plan->dev, csr->d_val, d_b, d_x, &opts, &res, NULL, NULL, NULL);
 	}
 
 	if (solved < 0) {

@@ -145,6 +145,41 @@ typedef struct {
 	int32_t* color_nbr;  /* [n_agg * n_colors] the aggregate of colour c equal or adjacent to g, or -1 */
 } bfmg_coarse_t;
 
+/* ---- multilevel preconditioner: aggregation hierarchy on the device (hier.c builds it, mg.cuh uses it) ----- */
+
+#define BFMG_MG_MAX_LEVELS 12
+
+typedef struct {
+	int32_t n;           /* nodes of this level */
+	int32_t dofs;        /* unknowns per node: 2 on level 0, 3 above */
+	int32_t n_slices;
+	int64_t n_slots;
+	int32_t* slice_off;  /* SELL-32 node pattern of the level's operator */
+	int32_t* scol;
+	int32_t* diag_pos;
+	int32_t* row_len;
+
+	/* towards the next level (unused on the last) */
+	int32_t n_coarse;
+	int32_t n_p;
+	int32_t n_colors;
+	int32_t* agg;        /* [n] aggregate, -1: none */
+	float* geom;         /* [n] float2 */
+	int32_t* p_ptr;      /* prolongator entries by fine node */
+	int32_t* p_col;
+	int32_t* r_ptr;      /* ... and by coarse node */
+	int32_t* r_ent;
+	int32_t* r_node;
+	int32_t* color;      /* [n_coarse] */
+} bfmg_mg_level_t;
+
+typedef struct {
+	int32_t n_levels;    /* the last level is dense */
+	int32_t nc;          /* its dimension: 3 * nodes rounded up to a multiple of 32 */
+	int32_t half_bw;     /* band of the dense operator before inversion */
+	bfmg_mg_level_t level[BFMG_MG_MAX_LEVELS];
+} bfmg_mg_t;
+
 /* ---- FP64 conjugate gradient ----------------------------------------------------------------- */
 
 typedef struct {
@@ -166,6 +201,7 @@ typedef struct {
 	float ms;
 	float ms_setup;      /* of which: scaling + coarse-level setup (probing E, inverting it) */
 	int32_t coarse_dim;  /* 0 when the coarse level was not used */
+	int32_t mg_levels;   /* levels of the multilevel preconditioner (0: not used) */
 	int32_t peer_memory; /* 1 when the exchanges of the iteration went over NVLink peer memory, 0: NCCL or one GPU */
 	size_t launches;
 } bfmg_pcg_result_t;
@@ -173,7 +209,7 @@ typedef struct {
 /* solves A x = b over the rows [pat->row_lo, pat->row_hi); d_val is left untouched (a scaled copy is
  * made).  halo = NULL on one GPU; otherwise the vectors are local (owned + ghost rows), every rank
  * calls this collectively and d_x receives the owned rows (ghost rows of d_x are not meaningful) */
-int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res, bfmg_halo_t const* halo, bfmg_coarse_t const* coarse);
+int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res, bfmg_halo_t const* halo, bfmg_coarse_t const* coarse, bfmg_mg_t const* mg);
 
 /* ---- small systems: one CTA per system (batch.cu) ------------------------------------------------ */
 

@@ -149,6 +149,70 @@ BFMI_HIDDEN void bfmi_coarse_release(bfmi_coarse_t* coarse);
 BFMI_HIDDEN void bfmi_coarse_forget(bfm_mesh_t const* gmesh);
 
 /* ---------------------------------------------------------------------------------------------
+ * aggregation hierarchy of the multilevel preconditioner (hier.c), kernels in mg.cuh
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct bfmi_hier_level {
+	int32_t n;            /* nodes of this level (level 0: the nodes the plan covers) */
+	int32_t dofs;         /* unknowns per node: 2 on level 0, 3 above */
+
+	/* SELL-32 node pattern of the level's operator (level 0: the plan's arrays, borrowed) */
+	int32_t n_slices;
+	int64_t n_slots;
+	int32_t* slice_off;
+	int32_t* row_len;
+	int32_t* scol;
+	int32_t* diag_pos;
+	double* pos;          /* [n][2] reference points (level 0: the mesh coordinates, borrowed) */
+	bool owns_pattern;
+
+	int32_t const* owner; /* [n] rank of every node (NULL on one GPU); aggregates never straddle ranks */
+	bool owns_owner;
+
+	/* towards the next level (absent on the last) */
+	int32_t n_coarse;     /* nodes of the next level = aggregates of this one */
+	int32_t n_p;          /* entries of the prolongator */
+	int32_t n_colors;
+	int32_t* agg;         /* [n] aggregate of every node, -1: left out of the coarse space */
+	float* geom;          /* [n][2] node position relative to its aggregate's reference point */
+	int32_t* p_ptr;       /* [n + 1] prolongator by fine node */
+	int32_t* p_col;       /* [n_p] coarse node of every entry */
+	int32_t* r_ptr;       /* [n_coarse + 1] its transpose by coarse node */
+	int32_t* r_ent;       /* [n_p] entry index */
+	int32_t* r_node;      /* [n_p] fine node of that entry, ascending per coarse node */
+	int32_t* color;       /* [n_coarse] probing colour */
+
+	bfmg_mg_level_t dev;
+} bfmi_hier_level_t;
+
+typedef struct bfmi_hier {
+	int refs;
+
+	/* cache key */
+	struct bfmi_plan const* key_plan;
+	size_t key_nodes;
+	uint64_t elems_hash, coords_hash, settings;
+	int rank, world;
+	bool on_device;
+
+	int n_levels;         /* the last level is solved with a dense inverse */
+	int32_t dense_span;   /* largest |I - J| over coupled nodes of the last level */
+	bfmi_hier_level_t level[BFMG_MG_MAX_LEVELS];
+
+	bfmi_plan_t* plan;    /* retained: level 0 borrows its pattern */
+	bfmg_mg_t dev;
+} bfmi_hier_t;
+
+/* NULL when the mesh is too small or does not coarsen (not an error: the solver falls back) */
+BFMI_HIDDEN bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, int32_t const* owner);
+BFMI_HIDDEN int bfmi_hier_upload(bfmi_hier_t* hier, bfmg_pattern_t const* pat0, size_t* h2d_bytes);
+BFMI_HIDDEN void bfmi_hier_free(bfmi_hier_t* hier);
+/* cached (one entry, keyed by plan identity + coordinate hash + partition + settings), retained */
+BFMI_HIDDEN bfmi_hier_t* bfmi_hier_for_plan(bfmi_plan_t* plan, double const* coords, int32_t const* owner, int rank, int world);
+BFMI_HIDDEN void bfmi_hier_release(bfmi_hier_t* hier);
+BFMI_HIDDEN void bfmi_hier_forget(bfmi_plan_t const* plan);
+
+/* ---------------------------------------------------------------------------------------------
  * BFM_MATRIX_KIND_CSR implementation object (matrix->csr.impl)
  * ------------------------------------------------------------------------------------------- */
 

@@ -66,7 +66,8 @@ struct bfmx_job {
 	bfmg_pattern_t pat;      /* plan->dev with the owned row range */
 	bfmg_halo_t halo;
 	double* d_xg;            /* multi-GPU: the gathered global solution */
-	bfmi_coarse_t* coarse;   /* the solver's coarse level (NULL: small mesh, or disabled) */
+	bfmi_coarse_t* coarse;   /* the solver's single coarse level (NULL: small mesh, disabled, or superseded by hier) */
+	bfmi_hier_t* hier;       /* the solver's aggregation hierarchy (multilevel preconditioner), or NULL */
 	bfmg_asm_tables_t tab;
 
 	double* h_nforce; /* [n_forces][nb][2], FUNKY forces sampled at the nodes */
@@ -872,7 +873,33 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 	 * 1.9 GB then), 2048 when several GPUs exchange over NCCL and therefore each invert all of E.
 	 * BFM_COARSE_AGGREGATES overrides; 0 switches the coarse level off. */
 
-	if (!takes_one_cta(job)) {
+	/* the multilevel preconditioner (hier.c, mg.cuh) supersedes that single level on one GPU; BFM_MG=0 keeps
+	 * the single level */
+
+	if (!takes_one_cta(job) && job->part == NULL) {
+		char const* const env = getenv("BFM_MG");
+
+		if (env == NULL || atoi(env) != 0) {
+			double const t_h = now_ms();
+
+			job->hier = bfmi_hier_for_plan(job->plan, job->mesh->coords, NULL, 0, 1);
+
+			if (job->hier != NULL) {
+				bool const fresh_hier = !job->hier->on_device;
+
+				if (bfmi_hier_upload(job->hier, &job->plan->dev, &job->stats.h2d_bytes) < 0) {
+					BFMI_FAIL(state, "uploading the aggregation hierarchy failed: %s", bfmg_last_error());
+					goto fail;
+				}
+
+				if (fresh_hier) {
+					job->stats.ms_plan += (float) (now_ms() - t_h);
+				}
+			}
+		}
+	}
+
+	if (!takes_one_cta(job) && job->hier == NULL) {
 		char const* const env = getenv("BFM_COARSE_AGGREGATES");
 		int64_t target = (int64_t) floor(3.4 * pow((double) mesh->n_nodes, 3.0 / 7.0) + 0.5);
 		int64_t const cap = job->part != NULL && bfmg_dist_p2p_status()[0] != 0 ? 2048 : 5120;
@@ -1360,6 +1387,7 @@ int bfmx_job_destroy(bfmx_job_t* job) {
 	bfmg_free(job->d_cval);
 	bfmg_free(job->d_xg);
 	bfmi_coarse_release(job->coarse);
+	bfmi_hier_release(job->hier);
 	bfmg_free(job->d_tabs);
 	bfmg_free(job->d_slice_tab);
 
@@ -1551,7 +1579,7 @@ int bfmx_job_solve(bfmx_job_t* job) {
 		res.launches = bfmg_launch_count() - before;
 	}
 
-	else if (bfmg_pcg(&job->pat, job->d_val, job->d_b, job->d_x, &opts, &res, job->part != NULL ? &job->halo : NULL, job->coarse != NULL ? &job->coarse->dev : NULL) < 0) {
+	else if (bfmg_pcg(&job->pat, job->d_val, job->d_b, job->d_x, &opts, &res, job->part != NULL ? &job->halo : NULL, job->coarse != NULL ? &job->coarse->dev : NULL, job->hier != NULL ? &job->hier->dev : NULL) < 0) {
 		return BFMI_FAIL(job->state, "PCG failed: %s", bfmg_last_error());
 	}
 
@@ -1564,6 +1592,7 @@ int bfmx_job_solve(bfmx_job_t* job) {
 	job->stats.ms_solve = res.ms;
 	job->stats.ms_solve_setup = res.ms_setup;
 	job->stats.coarse_dim = (size_t) res.coarse_dim;
+	job->stats.mg_levels = res.mg_levels;
 	job->stats.uses_peer_memory = res.peer_memory;
 	job->stats.kernel_launches += res.launches;
 	job->solved = true;

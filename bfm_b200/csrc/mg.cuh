@@ -1,0 +1,948 @@
+/*
+ * mg.cuh - device side of the solver's multilevel preconditioner (included by solver.cu, after coarse.cuh).
+ *
+ * The reference's bfm_matrix_solve is a direct band LU (matrix.c:253-404, :531-541); here the system is solved
+ * by conjugate gradients, and what decides the cost is the iteration count.  With a diagonal preconditioner it
+ * grows like 1/h (46 000 iterations at 8 M DOF), with one additive coarse level of rigid-body modes like H/h
+ * (1 520 at 50 M DOF, round 1).  This file replaces that level by an aggregation multigrid cycle on the
+ * hierarchy of hier.c, used as a fixed symmetric positive definite preconditioner of plain PCG:
+ *
+ *   level 0   A^ = D^-1/2 A D^-1/2 (unit diagonal), SELL-32 2x2 node blocks - the assembled matrix
+ *   level l   A_l = P^T A_{l-1} P, 3x3 node blocks (two translations + one rotation per aggregate), also
+ *             scaled to a unit diagonal, SELL-32 with nine value planes
+ *   last      dense, inverted once per solve by coarse.cuh's blocked Gauss-Jordan
+ *
+ * P holds, per node of an aggregate, the aggregate's rigid-body modes seen from that node, in the scaled
+ * variables of both levels: P_a = D_a^1/2 [1 0 -dy; 0 1 dx; (0 0 1)] D_I^-1/2.  One cycle on level l for a
+ * right-hand side g (damped Jacobi, the diagonal being the identity):
+ *
+ *   z = w g                       pre-smoothing from a zero guess needs no product
+ *   t = g - A z                   one fused SpMV (k_spmv_mg<kPre> / k_blk_spmv<kPre>)
+ *   z += P cycle_{l+1}(P^T t)     restriction, recursion (gamma visits: V- or W-cycle), prolongation
+ *   z += w (g - A z)              one fused SpMV (kPost); on level 0 it also leaves r.z for CG
+ *
+ * with w = 1.6 / (largest absolute row sum): a Gershgorin bound of the largest eigenvalue, so w lambda_max < 2
+ * always holds and the smoother - hence the whole cycle - is symmetric positive definite.  The preconditioner
+ * changes how fast CG converges, not what it converges to: the stopping test stays on the true CG residual.
+ *
+ * Set-up, once per solve: P from the diagonal scaling; A_{l+1} = P^T A_l P column by column through colour
+ * probing (hier.c colours the coarse nodes so that the columns probed together never meet in a row): one
+ * plain SpMV + one restriction per (colour, mode); its diagonal, scaling and row-sum bound; at the end the
+ * dense inverse.  Everything is deterministic: fixed-order sums, no floating-point atomics (the row-sum bound
+ * is a maximum, taken with an integer atomicMax on the bit pattern of non-negative doubles).
+ *
+ * All kernels are HBM-bound streaming work.  Algorithmic bytes per mesh node and PCG iteration on the
+ * structured P1 plate (7 blocks per row), level 0:  k_spmv<kDot> 284 + k_update_xr 96 + k_spmv_mg<kPre> 284 +
+ * k_mg_restrict 48 + k_mg_prolong 64 + k_spmv_mg<kPost> 300 + k_update_p 48 = 1124 B; the coarser levels add
+ * about a quarter of that.
+ */
+#pragma once
+
+#include <cstring>
+
+namespace {
+
+enum MgMode { kMgPlain, kMgPre, kMgResid, kMgPost };
+
+constexpr int kMgGroup = 8;                       /* lanes that share one coarse node in k_mg_restrict */
+constexpr int kMgGroupsPerBlock = kBlock / kMgGroup;
+
+struct MgDev {
+	double omega[BFMG_MG_MAX_LEVELS];             /* damping of every level's Jacobi smoother */
+	unsigned long long gersh[BFMG_MG_MAX_LEVELS]; /* bit pattern of the largest absolute row sum */
+	int32_t bad;                                  /* a coarse operator came out with a non-positive diagonal */
+	int32_t pad;
+};
+
+/* ---- level 0: fused SpMV variants over the SELL-32 2x2 node blocks ----------------------------------------
+ *   kMgPre    out = g - w A^ g                 (v == g)
+ *   kMgResid  out = g - A^ v
+ *   kMgPost   out = v + w (g - A^ v),  + partial g.out; last CTA: rz -> beta, rho
+ * FIRST: the preconditioner is applied to the initial residual (beta = 0, ignores S->done) */
+template <MgMode MODE, bool FIRST>
+__global__ void __launch_bounds__(kBlock) k_spmv_mg(
+	const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ vtop, double2 const* __restrict__ vbot,
+	double2 const* __restrict__ v, double2 const* __restrict__ g, double2* __restrict__ out, double const* __restrict__ omega_p, double* __restrict__ partials, Scalars* S
+) {
+	if (!FIRST && S->done) {
+		return;
+	}
+
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+	int const n_warps = gridDim.x * blockDim.x / kWarp;
+	double const w = MODE == kMgResid ? 1.0 : *omega_p;
+
+	double acc = 0;
+
+	for (int slice = P.row_lo / kWarp + warp; slice < (P.row_hi + kWarp - 1) / kWarp; slice += n_warps) {
+		int const row = slice * kWarp + lane;
+		int const beg = __ldg(&P.slice_off[slice]);
+		int const end = __ldg(&P.slice_off[slice + 1]);
+
+		double y0 = 0, y1 = 0;
+
+#pragma unroll 4
+		for (int slot = beg + lane; slot < end; slot += kWarp) {
+			int const col = ld_stream(&P.scol[slot]);
+			double2 const t = ld_stream(&vtop[slot]);
+			double2 const u = ld_stream(&vbot[slot]);
+			double2 const xv = __ldg(&v[col]);
+
+			y0 = fma(t.x, xv.x, fma(t.y, xv.y, y0));
+			y1 = fma(u.x, xv.x, fma(u.y, xv.y, y1));
+		}
+
+		if (row >= P.row_lo && row < P.row_hi) {
+			double2 const gv = g[row];
+			double2 o;
+
+			if (MODE == kMgPost) {
+				double2 const vv = __ldg(&v[row]);
+
+				o.x = fma(w, gv.x - y0, vv.x);
+				o.y = fma(w, gv.y - y1, vv.y);
+				acc = fma(gv.x, o.x, fma(gv.y, o.y, acc));
+			}
+
+			else {
+				o.x = fma(-w, y0, gv.x);
+				o.y = fma(-w, y1, gv.y);
+			}
+
+			out[row] = o;
+		}
+	}
+
+	if (MODE != kMgPost) {
+		return;
+	}
+
+	double total;
+
+	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
+		/* r.z of a symmetric positive definite preconditioner is positive; anything else is a breakdown */
+		if (!(total > 0) || isinf(total)) {
+			S->done = S->done ? S->done : 2;
+			S->beta = 0;
+		}
+
+		else {
+			S->beta = FIRST ? 0 : total / S->rho;
+			S->rho = total;
+		}
+	}
+}
+
+/* largest absolute row sum of the scaled level-0 operator */
+__global__ void __launch_bounds__(kBlock) k_mg_gersh0(const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ vtop, double2 const* __restrict__ vbot, unsigned long long* __restrict__ gersh) {
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+	int const n_warps = gridDim.x * blockDim.x / kWarp;
+
+	double worst = 0;
+
+	for (int slice = P.row_lo / kWarp + warp; slice < (P.row_hi + kWarp - 1) / kWarp; slice += n_warps) {
+		int const beg = __ldg(&P.slice_off[slice]);
+		int const end = __ldg(&P.slice_off[slice + 1]);
+
+		double s0 = 0, s1 = 0;
+
+		for (int slot = beg + lane; slot < end; slot += kWarp) {
+			double2 const t = ld_stream(&vtop[slot]);
+			double2 const u = ld_stream(&vbot[slot]);
+
+			s0 += fabs(t.x) + fabs(t.y);
+			s1 += fabs(u.x) + fabs(u.y);
+		}
+
+		worst = fmax(worst, fmax(s0, s1));
+	}
+
+#pragma unroll
+	for (int off = kWarp / 2; off > 0; off >>= 1) {
+		worst = fmax(worst, __shfl_down_sync(0xffffffffu, worst, off));
+	}
+
+	if (lane == 0 && worst == worst) {
+		atomicMax(gersh, (unsigned long long) __double_as_longlong(worst)); /* non-negative doubles order like their bits */
+	}
+}
+
+__global__ void k_mg_omega(int n_levels, double factor, MgDev* D) {
+	int const l = threadIdx.x;
+
+	if (l < n_levels) {
+		double const bound = __longlong_as_double((long long) D->gersh[l]);
+		D->omega[l] = bound >= 1.0 ? factor / bound : factor; /* a unit diagonal makes every row sum >= 1 */
+	}
+}
+
+/* ---- prolongator ------------------------------------------------------------------------------------------
+ *
+ * Values by entry, planes [k * 3 + m][entry] (k: unknown of the fine node, m: mode of the coarse node); PT is
+ * float on level 0 (two thirds of the transfer traffic of an iteration is P, and its last digits only shape
+ * the preconditioner - every level's operator is built from the SAME rounded P, so the cycle stays symmetric
+ * positive definite), double above.  dsc = D^-1/2 of the FINE level (level 0: solver.cu's dscale). */
+template <int NB, typename PT>
+__global__ void k_mg_tentative(bfmg_mg_level_t L, double const* __restrict__ dsc, PT* __restrict__ pval) {
+	int const a = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (a >= L.n) {
+		return;
+	}
+
+	int const g = L.agg[a];
+	float2 const d = ((float2 const*) L.geom)[a];
+	size_t const np = (size_t) L.n_p;
+
+	for (int e = L.p_ptr[a]; e < L.p_ptr[a + 1]; e++) {
+		bool const own = L.p_col[e] == g;
+		double s[3];
+
+#pragma unroll
+		for (int k = 0; k < NB; k++) {
+			s[k] = own ? 1.0 / dsc[(size_t) NB * a + k] : 0.0;
+		}
+
+		/* rows of [1 0 -dy; 0 1 dx; 0 0 1] scaled by D_a^1/2 */
+		pval[0 * np + e] = (PT) s[0];
+		pval[1 * np + e] = (PT) 0;
+		pval[2 * np + e] = (PT) (-(double) d.y * s[0]);
+		pval[3 * np + e] = (PT) 0;
+		pval[4 * np + e] = (PT) s[1];
+		pval[5 * np + e] = (PT) ((double) d.x * s[1]);
+
+		if (NB == 3) {
+			pval[6 * np + e] = (PT) 0;
+			pval[7 * np + e] = (PT) 0;
+			pval[8 * np + e] = (PT) s[2];
+		}
+	}
+}
+
+/* P <- P D_c^-1/2 once the coarse level's scaling is known */
+template <int NB, typename PT>
+__global__ void k_mg_pscale(bfmg_mg_level_t L, double const* __restrict__ dsc_coarse, PT* __restrict__ pval) {
+	int const e = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (e >= L.n_p) {
+		return;
+	}
+
+	int const J = L.p_col[e];
+	size_t const np = (size_t) L.n_p;
+
+#pragma unroll
+	for (int m = 0; m < 3; m++) {
+		double const s = dsc_coarse[3 * (size_t) J + m];
+
+#pragma unroll
+		for (int k = 0; k < NB; k++) {
+			pval[(size_t) (k * 3 + m) * np + e] = (PT) ((double) pval[(size_t) (k * 3 + m) * np + e] * s);
+		}
+	}
+}
+
+/* v = sum over the coarse nodes J of colour `color` of column (J, mode) of P */
+template <int NB, typename PT>
+__global__ void k_mg_probe_vector(bfmg_mg_level_t L, PT const* __restrict__ pval, int color, int mode, double* __restrict__ v) {
+	int const a = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (a >= L.n) {
+		return;
+	}
+
+	size_t const np = (size_t) L.n_p;
+	double out[3] = {0, 0, 0};
+
+	for (int e = L.p_ptr[a]; e < L.p_ptr[a + 1]; e++) {
+		if (L.color[L.p_col[e]] == color) {
+#pragma unroll
+			for (int k = 0; k < NB; k++) {
+				out[k] += (double) pval[(size_t) (k * 3 + mode) * np + e];
+			}
+		}
+	}
+
+#pragma unroll
+	for (int k = 0; k < NB; k++) {
+		v[(size_t) NB * a + k] = out[k];
+	}
+}
+
+/* out = P^T v: kMgGroup lanes per coarse node walk its entry list (ascending fine nodes), then a fixed
+ * shuffle tree - deterministic.  n_out >= 3 * n_coarse: the padding up to it is zeroed (dense level). */
+template <int NB, typename PT>
+__global__ void __launch_bounds__(kBlock) k_mg_restrict(bfmg_mg_level_t L, PT const* __restrict__ pval, double const* __restrict__ v, double* __restrict__ out, int n_out, Scalars const* S, bool obey_done) {
+	if (obey_done && S->done) {
+		return;
+	}
+
+	int const sub = threadIdx.x & (kMgGroup - 1);
+	int const n_nodes_out = (n_out + 2) / 3;
+	size_t const np = (size_t) L.n_p;
+
+	/* the loop bound is the same for all lanes of a warp (its groups take consecutive coarse nodes), so the
+	 * full-mask shuffles below are always executed by all 32 lanes */
+	for (int base = blockIdx.x * kMgGroupsPerBlock + (threadIdx.x / kWarp) * (kWarp / kMgGroup); base < n_nodes_out; base += gridDim.x * kMgGroupsPerBlock) {
+		int const I = base + (threadIdx.x & (kWarp - 1)) / kMgGroup;
+		double s[3] = {0, 0, 0};
+
+		if (I < L.n_coarse) {
+			int const end = L.r_ptr[I + 1];
+
+			for (int at = L.r_ptr[I] + sub; at < end; at += kMgGroup) {
+				int const e = L.r_ent[at];
+				int const a = L.r_node[at];
+
+#pragma unroll
+				for (int k = 0; k < NB; k++) {
+					double const x = v[(size_t) NB * a + k];
+
+#pragma unroll
+					for (int m = 0; m < 3; m++) {
+						s[m] = fma((double) pval[(size_t) (k * 3 + m) * np + e], x, s[m]);
+					}
+				}
+			}
+		}
+
+#pragma unroll
+		for (int off = kMgGroup / 2; off > 0; off >>= 1) {
+#pragma unroll
+			for (int m = 0; m < 3; m++) {
+				s[m] += __shfl_down_sync(0xffffffffu, s[m], off, kMgGroup);
+			}
+		}
+
+		if (sub == 0 && I < n_nodes_out) {
+#pragma unroll
+			for (int m = 0; m < 3; m++) {
+				if (3 * I + m < n_out) {
+					out[3 * (size_t) I + m] = s[m];
+				}
+			}
+		}
+	}
+}
+
+/* z = w g + P mu (first visit of the coarse level), or z += P mu (later visits of a W-cycle) */
+template <int NB, typename PT, bool ADD>
+__global__ void __launch_bounds__(kBlock) k_mg_prolong(bfmg_mg_level_t L, int row0, int n_rows, PT const* __restrict__ pval, double const* __restrict__ mu, double const* __restrict__ g, double* __restrict__ z, double const* __restrict__ omega_p, Scalars const* S, bool obey_done) {
+	if (obey_done && S->done) {
+		return;
+	}
+
+	size_t const np = (size_t) L.n_p;
+	double const w = *omega_p;
+
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
+		int const a = row0 + i;
+		double acc[3] = {0, 0, 0};
+
+		for (int e = L.p_ptr[a]; e < L.p_ptr[a + 1]; e++) {
+			int const J = L.p_col[e];
+
+#pragma unroll
+			for (int m = 0; m < 3; m++) {
+				double const x = __ldg(&mu[3 * (size_t) J + m]);
+
+#pragma unroll
+				for (int k = 0; k < NB; k++) {
+					acc[k] = fma((double) pval[(size_t) (k * 3 + m) * np + e], x, acc[k]);
+				}
+			}
+		}
+
+#pragma unroll
+		for (int k = 0; k < NB; k++) {
+			size_t const at = (size_t) NB * a + k;
+			z[at] = ADD ? z[at] + acc[k] : fma(w, g[at], acc[k]);
+		}
+	}
+}
+
+/* the restricted probe g holds, for every coarse node I, column (J, mode) of P^T A P where J is the coarse node of
+ * colour `color` in row I of the next level's pattern (at most one by the colouring).  DENSE: into the row-major
+ * n_dense x n_dense matrix E instead of the SELL planes. */
+template <bool DENSE>
+__global__ void k_mg_scatter(bfmg_mg_level_t N, int32_t const* __restrict__ color_of, int color, int mode, double const* __restrict__ g, double* __restrict__ val, int n_dense) {
+	int const I = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (I >= N.n) {
+		return;
+	}
+
+	int const base = N.slice_off[I / kWarp] + I % kWarp;
+
+	for (int t = 0; t < N.row_len[I]; t++) {
+		int const slot = base + t * kWarp;
+		int const J = N.scol[slot];
+
+		if (color_of[J] != color) {
+			continue;
+		}
+
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			if (DENSE) {
+				val[(size_t) (3 * I + k) * n_dense + 3 * J + mode] = g[3 * (size_t) I + k];
+			}
+
+			else {
+				val[(size_t) (3 * k + mode) * N.n_slots + slot] = g[3 * (size_t) I + k];
+			}
+		}
+	}
+}
+
+/* ---- levels >= 1: 3x3 node blocks, SELL-32, value planes [3 k + m][slot] ---------------------------------- */
+
+/* dsc = 1 / sqrt(diagonal); a diagonal that is not positive marks the hierarchy unusable */
+__global__ void k_blk_diag(bfmg_mg_level_t N, double const* __restrict__ val, double* __restrict__ dsc, MgDev* D) {
+	int const I = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (I >= N.n) {
+		return;
+	}
+
+	int const slot = N.diag_pos[I];
+
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		double const d = val[(size_t) (4 * k) * N.n_slots + slot];
+
+		if (!(d > 0) || isinf(d)) {
+			D->bad = 1;
+			dsc[3 * (size_t) I + k] = 1;
+		}
+
+		else {
+			dsc[3 * (size_t) I + k] = 1.0 / sqrt(d);
+		}
+	}
+}
+
+/* A <- D^-1/2 A D^-1/2 in place, and the largest absolute row sum of the result */
+__global__ void __launch_bounds__(kBlock) k_blk_scale(bfmg_mg_level_t N, double* __restrict__ val, double const* __restrict__ dsc, unsigned long long* __restrict__ gersh) {
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+	int const n_warps = gridDim.x * blockDim.x / kWarp;
+
+	double worst = 0;
+
+	for (int slice = warp; slice < N.n_slices; slice += n_warps) {
+		int const row = slice * kWarp + lane;
+		int const end = N.slice_off[slice + 1];
+
+		double sr[3] = {0, 0, 0};
+		double sum[3] = {0, 0, 0};
+
+		if (row < N.n) {
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				sr[k] = dsc[3 * (size_t) row + k];
+			}
+		}
+
+		for (int slot = N.slice_off[slice] + lane; slot < end; slot += kWarp) {
+			int const col = N.scol[slot];
+
+#pragma unroll
+			for (int m = 0; m < 3; m++) {
+				double const sc = dsc[3 * (size_t) col + m];
+
+#pragma unroll
+				for (int k = 0; k < 3; k++) {
+					size_t const at = (size_t) (3 * k + m) * N.n_slots + slot;
+					double const x = val[at] * sr[k] * sc;
+
+					val[at] = x;
+					sum[k] += fabs(x);
+				}
+			}
+		}
+
+		worst = fmax(worst, fmax(sum[0], fmax(sum[1], sum[2])));
+	}
+
+#pragma unroll
+	for (int off = kWarp / 2; off > 0; off >>= 1) {
+		worst = fmax(worst, __shfl_down_sync(0xffffffffu, worst, off));
+	}
+
+	if (lane == 0 && worst == worst) {
+		atomicMax(gersh, (unsigned long long) __double_as_longlong(worst));
+	}
+}
+
+/* warp = slice, lane = node row; modes as k_spmv_mg (no dot product: the coarse levels feed no CG scalar) */
+template <MgMode MODE>
+__global__ void __launch_bounds__(kBlock) k_blk_spmv(bfmg_mg_level_t N, double const* __restrict__ val, double const* __restrict__ v, double const* __restrict__ g, double* __restrict__ out, double const* __restrict__ omega_p, Scalars const* S, bool obey_done) {
+	if (obey_done && S->done) {
+		return;
+	}
+
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+	int const n_warps = gridDim.x * blockDim.x / kWarp;
+	double const w = (MODE == kMgPre || MODE == kMgPost) ? *omega_p : 1.0;
+	size_t const ns = (size_t) N.n_slots;
+
+	for (int slice = warp; slice < N.n_slices; slice += n_warps) {
+		int const row = slice * kWarp + lane;
+		int const end = __ldg(&N.slice_off[slice + 1]);
+
+		double y0 = 0, y1 = 0, y2 = 0;
+
+#pragma unroll 2
+		for (int slot = __ldg(&N.slice_off[slice]) + lane; slot < end; slot += kWarp) {
+			int const col = ld_stream(&N.scol[slot]);
+			double const x0 = __ldg(&v[3 * (size_t) col + 0]);
+			double const x1 = __ldg(&v[3 * (size_t) col + 1]);
+			double const x2 = __ldg(&v[3 * (size_t) col + 2]);
+
+			y0 = fma(ld_stream(&val[0 * ns + slot]), x0, fma(ld_stream(&val[1 * ns + slot]), x1, fma(ld_stream(&val[2 * ns + slot]), x2, y0)));
+			y1 = fma(ld_stream(&val[3 * ns + slot]), x0, fma(ld_stream(&val[4 * ns + slot]), x1, fma(ld_stream(&val[5 * ns + slot]), x2, y1)));
+			y2 = fma(ld_stream(&val[6 * ns + slot]), x0, fma(ld_stream(&val[7 * ns + slot]), x1, fma(ld_stream(&val[8 * ns + slot]), x2, y2)));
+		}
+
+		if (row < N.n) {
+			size_t const at = 3 * (size_t) row;
+			double const y[3] = {y0, y1, y2};
+
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				double o;
+
+				if (MODE == kMgPlain) {
+					o = y[k];
+				}
+
+				else if (MODE == kMgPost) {
+					o = fma(w, g[at + k] - y[k], __ldg(&v[at + k]));
+				}
+
+				else {
+					o = fma(-w, y[k], g[at + k]);
+				}
+
+				out[at + k] = o;
+			}
+		}
+	}
+}
+
+/* mu = E^-1 g on the dense last level (the explicit inverse; kCoarseRows rows per CTA, four warps per row as in
+ * k_coarse_apply) */
+__global__ void __launch_bounds__(kBlock) k_dense_apply(int nc, double const* __restrict__ Einv, double const* __restrict__ g, double* __restrict__ mu, Scalars const* S, bool obey_done) {
+	if (obey_done && S->done) {
+		return;
+	}
+
+	__shared__ double quarter_sum[kWarpsPerBlock];
+
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = threadIdx.x / kWarp;
+	int const row = blockIdx.x * kCoarseRows + warp / 4;
+	int const span = ((nc + 3) / 4 + kWarp - 1) / kWarp * kWarp;
+	int const j_end = min(nc, (warp % 4 + 1) * span);
+
+	double t = 0;
+
+	if (row < nc) {
+		double const* const e = Einv + (size_t) row * nc;
+		double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+		int j = (warp % 4) * span + lane;
+
+		for (; j + 3 * kWarp < j_end; j += 4 * kWarp) {
+			t0 = fma(ld_stream(&e[j]), __ldg(&g[j]), t0);
+			t1 = fma(ld_stream(&e[j + kWarp]), __ldg(&g[j + kWarp]), t1);
+			t2 = fma(ld_stream(&e[j + 2 * kWarp]), __ldg(&g[j + 2 * kWarp]), t2);
+			t3 = fma(ld_stream(&e[j + 3 * kWarp]), __ldg(&g[j + 3 * kWarp]), t3);
+		}
+
+		for (; j < j_end; j += kWarp) {
+			t0 = fma(ld_stream(&e[j]), __ldg(&g[j]), t0);
+		}
+
+		t = warp_sum((t0 + t1) + (t2 + t3));
+	}
+
+	if (lane == 0) {
+		quarter_sum[warp] = t;
+	}
+
+	__syncthreads();
+
+	if (lane == 0 && warp % 4 == 0 && row < nc) {
+		mu[row] = (quarter_sum[warp] + quarter_sum[warp + 1]) + (quarter_sum[warp + 2] + quarter_sum[warp + 3]);
+	}
+}
+
+/* identity on the padding rows of the dense operator (3 n .. nc) */
+__global__ void k_mg_dense_pad(int n_real, int nc, double* __restrict__ E) {
+	int const i = n_real + blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (i < nc) {
+		E[(size_t) i * nc + i] = 1;
+	}
+}
+
+/* ---- one solve's multilevel state -------------------------------------------------------------------------- */
+
+struct MgLevelWork {
+	bfmg_mg_level_t L;
+	double* val;      /* levels >= 1 (sparse): nine planes of n_slots doubles */
+	double* dsc;      /* levels >= 1: D^-1/2, three per node */
+	void* pval;       /* prolongator to the next level: float [6][n_p] on level 0, double [9][n_p] above */
+	double *g, *va, *vb, *vt; /* levels >= 1: right-hand side and three work vectors, three per node */
+	int gamma;        /* visits of the next level per cycle */
+	int grid_rows;    /* grid of the per-slice kernels */
+	int grid_nodes;   /* grid of the per-node kernels */
+};
+
+struct MgRun {
+	bfmg_mg_t const* M = nullptr;
+	int n_levels = 0;
+	int nc = 0;
+	void* ws = nullptr;
+	MgDev* D = nullptr;
+	MgLevelWork W[BFMG_MG_MAX_LEVELS] = {};
+
+	/* dense last level */
+	double* E = nullptr;
+	double* Pblk = nullptr;
+	double* dg = nullptr;   /* its right-hand side [nc] */
+	double* dmu = nullptr;  /* its solution [nc] */
+	int32_t* bad = nullptr;
+
+	double omega_factor = 1.6;
+
+	static size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
+
+	int alloc(bfmg_mg_t const* mg) {
+		M = mg;
+		n_levels = mg->n_levels;
+		nc = mg->nc;
+
+		size_t total = align256(sizeof(MgDev));
+
+		for (int l = 0; l < n_levels; l++) {
+			bfmg_mg_level_t const& L = mg->level[l];
+			bool const last = l == n_levels - 1;
+
+			if (l >= 1 && !last) {
+				total += align256((size_t) L.n_slots * 9 * sizeof(double));
+			}
+
+			if (l >= 1) {
+				total += align256((size_t) L.n * 3 * sizeof(double));      /* dsc */
+				total += 4 * align256((size_t) L.n * 3 * sizeof(double));  /* g, va, vb, vt */
+			}
+
+			if (!last) {
+				total += align256((size_t) L.n_p * (l == 0 ? 6 * sizeof(float) : 9 * sizeof(double)));
+			}
+		}
+
+		total += align256((size_t) nc * nc * sizeof(double)) + align256(kGjBlock * kGjBlock * sizeof(double)) + 2 * align256(((size_t) nc + 8) * sizeof(double)) + 256;
+
+		if (bfmg_alloc(&ws, total) < 0) {
+			return -1;
+		}
+
+		char* at = (char*) ws;
+		auto take = [&](size_t bytes) { char* const p = at; at += align256(bytes); return (void*) p; };
+
+		D = (MgDev*) take(sizeof(MgDev));
+
+		for (int l = 0; l < n_levels; l++) {
+			bfmg_mg_level_t const& L = mg->level[l];
+			bool const last = l == n_levels - 1;
+			MgLevelWork& w = W[l];
+
+			w.L = L;
+			w.gamma = 1;
+			w.grid_rows = bfmg_grid((L.n_slices + kWarpsPerBlock - 1) / kWarpsPerBlock, 8);
+			w.grid_nodes = bfmg_grid(((int64_t) L.n + kBlock - 1) / kBlock, 8);
+
+			if (l >= 1 && !last) {
+				w.val = (double*) take((size_t) L.n_slots * 9 * sizeof(double));
+			}
+
+			if (l >= 1) {
+				w.dsc = (double*) take((size_t) L.n * 3 * sizeof(double));
+				w.g = (double*) take((size_t) L.n * 3 * sizeof(double));
+				w.va = (double*) take((size_t) L.n * 3 * sizeof(double));
+				w.vb = (double*) take((size_t) L.n * 3 * sizeof(double));
+				w.vt = (double*) take((size_t) L.n * 3 * sizeof(double));
+			}
+
+			if (!last) {
+				w.pval = take((size_t) L.n_p * (l == 0 ? 6 * sizeof(float) : 9 * sizeof(double)));
+			}
+		}
+
+		E = (double*) take((size_t) nc * nc * sizeof(double));
+		Pblk = (double*) take(kGjBlock * kGjBlock * sizeof(double));
+		dg = (double*) take(((size_t) nc + 8) * sizeof(double));
+		dmu = (double*) take(((size_t) nc + 8) * sizeof(double));
+		bad = (int32_t*) take(256);
+
+		/* cycle shape: BFM_MG_GAMMA visits of the next level on every sparse level above the mesh (W-cycle by
+		 * default: the piecewise-rigid interpolation of plain aggregation needs it to stay level-independent) */
+
+		char const* env = getenv("BFM_MG_GAMMA");
+
+		for (int l = 1; l < n_levels - 1; l++) { /* "2" or a list per level from level 1 on, "2,2,1": the last entry repeats */
+			int g = 2;
+
+			if (env != nullptr && env[0] != 0) {
+				char const* at = env;
+
+				for (int skip = 1; skip < l; skip++) {
+					char const* const comma = strchr(at, ',');
+
+					if (comma == nullptr) {
+						break;
+					}
+
+					at = comma + 1;
+				}
+
+				g = atoi(at);
+			}
+
+			W[l].gamma = g >= 1 && g <= 4 ? g : 2;
+		}
+
+		env = getenv("BFM_MG_OMEGA");
+
+		if (env != nullptr && atof(env) > 0 && atof(env) < 2) {
+			omega_factor = atof(env);
+		}
+
+		return 0;
+	}
+
+	void release() {
+		bfmg_free(ws);
+		ws = nullptr;
+	}
+
+	/* out = P_l^T v */
+	bool restrict_to(int l, double const* v, double* out, int n_out, Scalars* S, bool obey) {
+		MgLevelWork const& w = W[l];
+		int const grid = bfmg_grid(((int64_t) (n_out + 2) / 3 + kMgGroupsPerBlock - 1) / kMgGroupsPerBlock, 8);
+
+		return l == 0
+			? BFMG_LAUNCH((k_mg_restrict<2, float>), grid, kBlock, 0, w.L, (float const*) w.pval, v, out, n_out, S, obey) == 0
+			: BFMG_LAUNCH((k_mg_restrict<3, double>), grid, kBlock, 0, w.L, (double const*) w.pval, v, out, n_out, S, obey) == 0;
+	}
+
+	/* right-hand side / solution buffers of level l + 1 as seen from level l */
+	double* next_g(int l) { return l + 1 == n_levels - 1 ? dg : W[l + 1].g; }
+	int next_len(int l) { return l + 1 == n_levels - 1 ? nc : 3 * W[l + 1].L.n; }
+
+	/* set-up: prolongators, coarse operators by probing, scalings, damping factors, the dense inverse.
+	 * tmp_v / tmp_q: two level-0 work vectors (CG's p and q, free until k_cg_init); *usable = false when a coarse
+	 * operator is not positive definite (the caller then solves with the diagonal preconditioner alone) */
+	int setup(bfmg_pattern_t const* pat, double2 const* stop, double2 const* sbot, double2 const* dscale, double2* tmp_v, double2* tmp_q, int spmv_grid, Scalars* S, bool* usable) {
+		*usable = false;
+
+		if (
+			BFMG_CHECK(cudaMemsetAsync(D, 0, sizeof(MgDev), bfmg_stream())) < 0 ||
+			BFMG_CHECK(cudaMemsetAsync(bad, 0, sizeof(int32_t), bfmg_stream())) < 0 ||
+			BFMG_LAUNCH(k_mg_gersh0, spmv_grid, kBlock, 0, *pat, stop, sbot, &D->gersh[0]) < 0
+		) {
+			return -1;
+		}
+
+		for (int l = 0; l + 1 < n_levels; l++) {
+			MgLevelWork& w = W[l];
+			MgLevelWork& nx = W[l + 1];
+			bool const dense = l + 1 == n_levels - 1;
+			int const node_blocks = (w.L.n + kBlock - 1) / kBlock;
+			int const coarse_blocks = (nx.L.n + kBlock - 1) / kBlock;
+			double* const probe = l == 0 ? (double*) tmp_v : w.va;
+			double* const image = l == 0 ? (double*) tmp_q : w.vb;
+			double* const target = dense ? E : nx.val;
+			size_t const target_bytes = dense ? (size_t) nc * nc * sizeof(double) : (size_t) nx.L.n_slots * 9 * sizeof(double);
+
+			int rc = l == 0
+				? BFMG_LAUNCH((k_mg_tentative<2, float>), node_blocks, kBlock, 0, w.L, (double const*) dscale, (float*) w.pval)
+				: BFMG_LAUNCH((k_mg_tentative<3, double>), node_blocks, kBlock, 0, w.L, (double const*) w.dsc, (double*) w.pval);
+
+			if (rc < 0 || BFMG_CHECK(cudaMemsetAsync(target, 0, target_bytes, bfmg_stream())) < 0) {
+				return -1;
+			}
+
+			for (int c = 0; c < w.L.n_colors; c++) {
+				for (int m = 0; m < 3; m++) {
+					rc = l == 0
+						? BFMG_LAUNCH((k_mg_probe_vector<2, float>), node_blocks, kBlock, 0, w.L, (float const*) w.pval, c, m, probe)
+						: BFMG_LAUNCH((k_mg_probe_vector<3, double>), node_blocks, kBlock, 0, w.L, (double const*) w.pval, c, m, probe);
+
+					rc = rc < 0 ? rc : (l == 0
+						? BFMG_LAUNCH(k_spmv<kPlain>, spmv_grid, kBlock, 0, *pat, stop, sbot, (double2 const*) probe, (double2*) image, (double2 const*) nullptr, (double*) nullptr, S)
+						: BFMG_LAUNCH(k_blk_spmv<kMgPlain>, w.grid_rows, kBlock, 0, w.L, w.val, probe, (double const*) nullptr, image, (double const*) nullptr, S, false));
+
+					if (rc < 0 || !restrict_to(l, image, next_g(l), next_len(l), S, false)) {
+						return -1;
+					}
+
+					rc = dense
+						? BFMG_LAUNCH(k_mg_scatter<true>, coarse_blocks, kBlock, 0, nx.L, w.L.color, c, m, next_g(l), E, nc)
+						: BFMG_LAUNCH(k_mg_scatter<false>, coarse_blocks, kBlock, 0, nx.L, w.L.color, c, m, next_g(l), nx.val, nc);
+
+					if (rc < 0) {
+						return -1;
+					}
+				}
+			}
+
+			if (dense) {
+				if (3 * nx.L.n < nc && BFMG_LAUNCH(k_mg_dense_pad, 1, kBlock, 0, 3 * nx.L.n, nc, E) < 0) {
+					return -1;
+				}
+			}
+
+			else {
+				rc = BFMG_LAUNCH(k_blk_diag, coarse_blocks, kBlock, 0, nx.L, nx.val, nx.dsc, D);
+				rc = rc < 0 ? rc : BFMG_LAUNCH(k_blk_scale, nx.grid_rows, kBlock, 0, nx.L, nx.val, nx.dsc, &D->gersh[l + 1]);
+				rc = rc < 0 ? rc : (l == 0
+					? BFMG_LAUNCH((k_mg_pscale<2, float>), (w.L.n_p + kBlock - 1) / kBlock, kBlock, 0, w.L, nx.dsc, (float*) w.pval)
+					: BFMG_LAUNCH((k_mg_pscale<3, double>), (w.L.n_p + kBlock - 1) / kBlock, kBlock, 0, w.L, nx.dsc, (double*) w.pval));
+
+				if (rc < 0) {
+					return -1;
+				}
+			}
+		}
+
+		if (BFMG_LAUNCH(k_mg_omega, 1, kWarp, 0, n_levels, omega_factor, D) < 0) {
+			return -1;
+		}
+
+		/* dense inverse of the last level (in place, coarse.cuh) */
+
+		CoarseWork CW = {};
+
+		CW.C.nc = nc;
+		CW.C.half_bw = M->half_bw;
+		CW.E = E;
+		CW.P = Pblk;
+		CW.bad = bad;
+
+		int32_t flags[2] = {0, 0};
+
+		if (
+			coarse_invert(CW, S, false, 0, nc / kGjBlock) < 0 ||
+			BFMG_CHECK(cudaMemcpyAsync(&flags[0], bad, sizeof(int32_t), cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
+			BFMG_CHECK(cudaMemcpyAsync(&flags[1], &D->bad, sizeof(int32_t), cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
+			BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0
+		) {
+			return -1;
+		}
+
+		*usable = flags[0] == 0 && flags[1] == 0;
+		return 0;
+	}
+
+	/* one cycle on the sparse level l >= 1 for the right-hand side W[l].g; returns the vector holding the result */
+	double* cycle(int l, Scalars* S, bool obey) {
+		MgLevelWork& w = W[l];
+		bool const dense_next = l + 1 == n_levels - 1;
+		double const* const om = &D->omega[l];
+
+		if (BFMG_LAUNCH(k_blk_spmv<kMgPre>, w.grid_rows, kBlock, 0, w.L, w.val, w.g, w.g, w.vt, om, S, obey) < 0) {
+			return nullptr;
+		}
+
+		for (int visit = 0; visit < w.gamma; visit++) {
+			if (visit > 0 && BFMG_LAUNCH(k_blk_spmv<kMgResid>, w.grid_rows, kBlock, 0, w.L, w.val, w.va, w.g, w.vt, om, S, obey) < 0) {
+				return nullptr;
+			}
+
+			if (!restrict_to(l, w.vt, next_g(l), next_len(l), S, obey)) {
+				return nullptr;
+			}
+
+			double const* mu;
+
+			if (dense_next) {
+				if (BFMG_LAUNCH(k_dense_apply, (nc + kCoarseRows - 1) / kCoarseRows, kBlock, 0, nc, E, dg, dmu, S, obey) < 0) {
+					return nullptr;
+				}
+
+				mu = dmu;
+			}
+
+			else {
+				mu = cycle(l + 1, S, obey);
+
+				if (mu == nullptr) {
+					return nullptr;
+				}
+			}
+
+			int const rc = visit == 0
+				? BFMG_LAUNCH((k_mg_prolong<3, double, false>), w.grid_nodes, kBlock, 0, w.L, 0, w.L.n, (double const*) w.pval, mu, w.g, w.va, om, S, obey)
+				: BFMG_LAUNCH((k_mg_prolong<3, double, true>), w.grid_nodes, kBlock, 0, w.L, 0, w.L.n, (double const*) w.pval, mu, w.g, w.va, om, S, obey);
+
+			if (rc < 0) {
+				return nullptr;
+			}
+		}
+
+		if (BFMG_LAUNCH(k_blk_spmv<kMgPost>, w.grid_rows, kBlock, 0, w.L, w.val, w.va, w.g, w.vb, om, S, obey) < 0) {
+			return nullptr;
+		}
+
+		return w.vb;
+	}
+
+	/* z = M^-1 r on level 0: t (work) and z are level-0 vectors; the result lands in `out` (may alias t) together
+	 * with r.z -> beta, rho in S.  FIRST: initial residual (beta = 0, runs regardless of S->done). */
+	template <bool FIRST>
+	bool apply(bfmg_pattern_t const* pat, double2 const* stop, double2 const* sbot, double2 const* r, double2* t, double2* z, double2* out, double* partials, int spmv_grid, int vec_grid, Scalars* S) {
+		bool const obey = !FIRST;
+		bool const dense_next = n_levels == 2;
+		double const* const om = &D->omega[0];
+		int const lo = pat->row_lo;
+		int const n_own = pat->row_hi - pat->row_lo;
+
+		if (
+			BFMG_LAUNCH((k_spmv_mg<kMgPre, FIRST>), spmv_grid, kBlock, 0, *pat, stop, sbot, r, r, t, om, partials, S) < 0 ||
+			!restrict_to(0, (double const*) t, next_g(0), next_len(0), S, obey)
+		) {
+			return false;
+		}
+
+		double const* mu;
+
+		if (dense_next) {
+			if (BFMG_LAUNCH(k_dense_apply, (nc + kCoarseRows - 1) / kCoarseRows, kBlock, 0, nc, E, dg, dmu, S, obey) < 0) {
+				return false;
+			}
+
+			mu = dmu;
+		}
+
+		else {
+			mu = cycle(1, S, obey);
+
+			if (mu == nullptr) {
+				return false;
+			}
+		}
+
+		return
+			BFMG_LAUNCH((k_mg_prolong<2, float, false>), vec_grid, kBlock, 0, W[0].L, lo, n_own, (float const*) W[0].pval, mu, (double const*) r, (double*) z, om, S, obey) == 0 &&
+			BFMG_LAUNCH((k_spmv_mg<kMgPost, FIRST>), spmv_grid, kBlock, 0, *pat, stop, sbot, (double2 const*) z, r, out, om, partials, S) == 0;
+	}
+};
+
+} // namespace

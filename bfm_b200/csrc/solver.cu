@@ -588,6 +588,7 @@ __global__ void __launch_bounds__(kBlock) k_norm2(int n2, double2 const* __restr
 } // namespace
 
 #include "coarse.cuh"
+#include "mg.cuh"
 
 namespace {
 
@@ -629,7 +630,7 @@ int bfmg_scale_system(bfmg_pattern_t const* pat, double const* d_val, double con
 
 extern "C" {
 
-int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res, bfmg_halo_t const* halo, bfmg_coarse_t const* coarse) {
+int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, double* d_x, bfmg_pcg_opts_t const* opts, bfmg_pcg_result_t* res, bfmg_halo_t const* halo, bfmg_coarse_t const* coarse, bfmg_mg_t const* mg) {
 	if (!bfmg_ready()) {
 		return -1;
 	}
@@ -650,6 +651,15 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		return 0;
 	}
 
+	/* the multilevel preconditioner (mg.cuh) replaces the single coarse level where a hierarchy is given */
+	bool use_mg = mg != nullptr && !shared;
+
+	if (use_mg) {
+		coarse = nullptr;
+	}
+
+	MgRun MG;
+
 	Grids const G = grids_for(pat);
 	int const nc = coarse != nullptr ? coarse->nc : 0;
 	int const coarse_grid = (nc + kCoarseRows - 1) / kCoarseRows; /* k_coarse_apply: kCoarseRows rows per CTA */
@@ -658,7 +668,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 	/* workspace: scaled matrix, 6 vectors of nb double2, halo send buffer, partials, scalars, coarse level */
 
-	double2 *stop = nullptr, *sbot, *dscale, *bhat, *xhat, *r, *p, *q, *sendbuf;
+	double2 *stop = nullptr, *sbot, *dscale, *bhat, *xhat, *r, *p, *q, *zmg, *sendbuf;
 	double* partials;
 	Scalars* S;
 
@@ -666,7 +676,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	size_t const mat_bytes = (size_t) pat->n_slots * 2 * sizeof(double2);
 	size_t const send_bytes = shared ? ((size_t) halo->n_send + 1) * sizeof(double2) : 0;
 	size_t const coarse_bytes = coarse != nullptr ? vec_bytes + (((size_t) nc + 8) * (3 + world) + (size_t) nc * nc + kGjBlock * kGjBlock + 64) * sizeof(double) : 0;
-	size_t const total = mat_bytes + 6 * vec_bytes + send_bytes + (size_t) max_grid * sizeof(double) + sizeof(Scalars) + 512 + coarse_bytes;
+	size_t const total = mat_bytes + 7 * vec_bytes + send_bytes + (size_t) max_grid * sizeof(double) + sizeof(Scalars) + 512 + coarse_bytes;
 
 	CoarseWork CW = {};
 
@@ -687,6 +697,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		r = (double2*) at, at += vec_bytes;
 		p = (double2*) at, at += vec_bytes;
 		q = (double2*) at, at += vec_bytes;
+		zmg = (double2*) at, at += vec_bytes;
 		sendbuf = (double2*) at, at += send_bytes;
 		partials = (double*) at, at += (size_t) max_grid * sizeof(double);
 		at = (char*) (((uintptr_t) at + 127) & ~(uintptr_t) 127);
@@ -743,6 +754,11 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 			   BFMG_LAUNCH(k_coarse_finish<FIRST>, 1, kBlock, 0, nc, CW.g, CW.mu, S) == 0) \
 			: BFMG_LAUNCH((k_coarse_apply<FIRST, false>), coarse_grid, kBlock, 0, nc, 0, CW.E, CW.g, CW.mu, partials, S) == 0) && \
 		BFMG_LAUNCH(k_update_p_coarse, G.vec, kBlock, 0, n_own, lo, CW.C, CW.wrow, CW.mu, r, p, S, (obey)) == 0)
+
+	/* p = z + beta p with z = the multigrid cycle applied to r (mg.cuh); the cycle's last kernel leaves r.z, beta, rho */
+#define MG_PRECONDITION(FIRST) ( \
+		MG.apply<FIRST>(pat, stop, sbot, r, q, zmg, q, partials, G.spmv, G.vec, S) && \
+		BFMG_LAUNCH(k_update_p, G.vec, kBlock, 0, n_own, q + lo, p + lo, S) == 0)
 
 	/* with peer memory each rank inverts and applies its own row blocks of the coarse operator: blocks of 32
 	 * rows, blocks_per of them per rank (coarse_invert) */
@@ -812,6 +828,35 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		BFMG_LAUNCH(k_scale_matrix, G.spmv, kBlock, 0, *pat, vtop, vbot, dscale, stop, sbot) < 0
 	) {
 		goto out;
+	}
+
+	/* multilevel preconditioner: prolongators, coarse operators by probing, dense inverse of the last level
+	 * (p, q are free until k_cg_init) */
+
+	if (use_mg) {
+		bool usable = false;
+
+		if (MG.alloc(mg) < 0 || MG.setup(pat, stop, sbot, dscale, p, q, G.spmv, S, &usable) < 0) {
+			goto out;
+		}
+
+		if (!usable) {
+			use_mg = false; /* a coarse operator is not positive definite: diagonal preconditioner alone */
+		}
+
+		else {
+			int32_t const one = 1;
+
+			if (
+				BFMG_CHECK(cudaMemcpyAsync(&S->coarse, &one, sizeof one, cudaMemcpyHostToDevice, bfmg_stream())) < 0 ||
+				BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0
+			) {
+				goto out;
+			}
+
+			res->coarse_dim = 3 * mg->level[mg->n_levels - 1].n;
+			res->mg_levels = mg->n_levels;
+		}
 	}
 
 	/* coarse operator E = W^T A^ W by colour probing (p, q are free until k_cg_init), then E^-1 */
@@ -900,7 +945,8 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		if (
 			BFMG_LAUNCH(k_cg_init, G.vec, kBlock, 0, n_own, bhat + lo, xhat + lo, r + lo, p + lo, partials, S, opts->tol, opts->max_iter) < 0 ||
 			!SHARE(kFoldInit) ||
-			(use_coarse && !PRECONDITION(true, false, false))
+			(use_coarse && !PRECONDITION(true, false, false)) ||
+			(use_mg && !MG_PRECONDITION(true))
 		) {
 			goto out;
 		}
@@ -909,7 +955,9 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	}
 
 	{
-		int const chunk = opts->chunk > 0 ? opts->chunk : 64;
+		/* iterations per chunk: a chunk is replayed as one CUDA graph and the host learns about convergence one
+		 * chunk late, so launches after convergence are wasted - 64 cheap iterations, or 8 multigrid ones */
+		int const chunk = opts->chunk > 0 ? opts->chunk : (use_mg ? 8 : 64);
 		int restarts = 0;
 
 		{
@@ -946,7 +994,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 							BFMG_LAUNCH(k_spmv<kDot>, G.spmv, kBlock, 0, *pat, stop, sbot, p, q, bhat, partials, S) == 0 &&
 							SHARE(kFoldPq) &&
 							BFMG_LAUNCH(k_update_xr, G.vec, kBlock, 0, n_own, p + lo, q + lo, xhat + lo, r + lo, partials, S) == 0 &&
-							(use_coarse ? PRECONDITION(false, true, true) : (SHARE(kFoldRr) && BFMG_LAUNCH(k_update_p, G.vec, kBlock, 0, n_own, r + lo, p + lo, S) == 0));
+							(use_mg ? MG_PRECONDITION(false) : use_coarse ? PRECONDITION(false, true, true) : (SHARE(kFoldRr) && BFMG_LAUNCH(k_update_p, G.vec, kBlock, 0, n_own, r + lo, p + lo, S) == 0));
 					}
 
 					launches_per_chunk = bfmg_launch_count() - before;
@@ -1064,7 +1112,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 			/* residual replacement: restart CG from the true residual */
 
-			if (BFMG_LAUNCH(k_restart, G.vec, kBlock, 0, n_own, q + lo, r + lo, p + lo, S) < 0 || (use_coarse && !PRECONDITION(true, false, false))) {
+			if (BFMG_LAUNCH(k_restart, G.vec, kBlock, 0, n_own, q + lo, r + lo, p + lo, S) < 0 || (use_coarse && !PRECONDITION(true, false, false)) || (use_mg && !MG_PRECONDITION(true))) {
 				goto out;
 			}
 
@@ -1097,6 +1145,9 @@ out:
 #undef HALO
 #undef RESTRICT
 #undef PRECONDITION
+#undef MG_PRECONDITION
+
+	MG.release();
 
 	if (chunk_exec != nullptr) {
 		cudaGraphExecDestroy(chunk_exec);

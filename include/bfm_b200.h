@@ -71,6 +71,7 @@ typedef struct {
 	size_t coarse_dim;         /* dimension of the solver's coarse space (3 rigid-body modes per aggregate); 0 = none */
 	float ms_solve_setup;      /* part of ms_solve spent scaling the matrix and building the coarse operator */
 	int uses_peer_memory;      /* multi-GPU: 1 when the per-iteration exchanges went over NVLink peer memory (CUDA IPC), 0 when over NCCL */
+	int mg_levels;             /* levels of the solver's aggregation multigrid preconditioner (mesh level and dense last level included); 0 = not used */
 } bfmx_stats_t;
 
 /* stats of the most recent bfm_sim_run instance / bfm_matrix_solve / job stage in this process */
@@ -168,6 +169,25 @@ int bfmx_partition_copy(bfm_mesh_t* mesh, int rank, int world, size_t* local_to_
 /* the coarse level the solver would build for a mesh with `target` aggregates (host-only): aggregate of
  * every node, colour of every aggregate; *n_aggregates = 0 when the mesh gets none */
 int bfmx_coarse_plan(bfm_mesh_t* mesh, int target, int32_t* n_aggregates, int32_t* n_colors, int32_t* node_aggregate, int32_t* aggregate_color);
+
+/* the aggregation hierarchy the solver's multilevel preconditioner would use for a mesh (host-only, tests):
+ * level 0 = the mesh nodes, every further level the aggregates of the one below, the last one solved densely;
+ * n_levels = 0 when the mesh gets none (too small, or it does not coarsen) */
+#define BFMX_HIER_MAX_LEVELS 12
+
+typedef struct {
+	int32_t n_levels;
+	int32_t n_nodes[BFMX_HIER_MAX_LEVELS];
+	int32_t n_colors[BFMX_HIER_MAX_LEVELS];  /* probing colours of the aggregates of this level (0 on the last) */
+	int64_t n_slots[BFMX_HIER_MAX_LEVELS];   /* padded SELL-32 slots of the level's operator */
+} bfmx_hier_info_t;
+
+int bfmx_hier_info(bfm_mesh_t* mesh, bfmx_hier_info_t* info);
+/* per level (any pointer may be NULL): aggregate[n] of every node (-1: left out), geometry[2 n] of every node
+ * relative to its aggregate's reference point, color[n of level + 1] of every aggregate (not on the last
+ * level); pattern_rowptr[n + 1] / pattern_col: the level's operator pattern as CSR with ascending columns
+ * (call with pattern_col = NULL first to learn the length) */
+int bfmx_hier_level(bfm_mesh_t* mesh, int level, int32_t* aggregate, float* geometry, int32_t* color, int32_t* pattern_rowptr, int32_t* pattern_col);
 
 /* ---- matrices ---------------------------------------------------------------------------------------- */
 

@@ -361,6 +361,7 @@ def test_coarse_level_changes_speed_not_answers(name, lib, golden, monkeypatch):
 	the north star's tolerance, far fewer iterations with it"""
 
 	monkeypatch.setenv("BFM_ONE_CTA", "0")
+	monkeypatch.setenv("BFM_MG", "0")  # the single coarse level of round 1 (still what several GPUs over NCCL use)
 	case = cases.build(name, lib)
 	want = golden[f"{name}/effects"]
 	runs = {}
@@ -380,8 +381,53 @@ def test_coarse_level_changes_speed_not_answers(name, lib, golden, monkeypatch):
 	assert runs["24"]["cg_iterations"] * 1.6 < runs["0"]["cg_iterations"], (runs["0"]["cg_iterations"], runs["24"]["cg_iterations"])
 
 
+@pytest.mark.parametrize("name", ["gear60", "plate_160x40", "plate_300x75", "bridge_dam", "plate_q4_jitter_24x6", "lepl8_all_kinds"])
+def test_multilevel_preconditioner_changes_speed_not_answers(name, lib, golden, monkeypatch):
+	"""general path with the aggregation multigrid cycle (hier.c, mg.cuh) against the diagonal preconditioner
+	alone: the same displacements to the north star's tolerance, several times fewer iterations"""
+
+	monkeypatch.setenv("BFM_ONE_CTA", "0")
+	monkeypatch.setenv("BFM_COARSE_AGGREGATES", "0")
+
+	if case_is_small := name in ("bridge_dam", "plate_q4_jitter_24x6", "lepl8_all_kinds"):
+		monkeypatch.setenv("BFM_MG_RATIO0", "6")       # small meshes: small aggregates so that they still get levels
+		monkeypatch.setenv("BFM_MG_DENSE_NODES", "48")
+
+	case = cases.build(name, lib)
+	want = golden[f"{name}/effects"]
+	runs = {}
+
+	for mg in ("0", "1"):
+		monkeypatch.setenv("BFM_MG", mg)
+		case.sim.run()
+		stats = ext.last_stats(lib)
+
+		assert stats["cg_converged"] == 1 and stats["cg_rel_residual"] <= 1e-12
+		assert rel_l2(case.instance.effects, want) <= REL_L2, (name, mg)
+
+		runs[mg] = stats
+
+	assert runs["0"]["mg_levels"] == 0 and runs["1"]["mg_levels"] >= 2 and runs["1"]["coarse_dim"] > 0
+	assert runs["1"]["cg_iterations"] * (2 if case_is_small else 4) < runs["0"]["cg_iterations"], (runs["0"]["cg_iterations"], runs["1"]["cg_iterations"])
+
+
+def test_multilevel_preconditioner_is_deterministic(lib, monkeypatch):
+	monkeypatch.setenv("BFM_ONE_CTA", "0")
+
+	case = cases.build("gear60", lib)
+	outs = []
+
+	for _ in range(2):
+		case.sim.run()
+		outs.append(case.instance.effects.copy())
+
+	assert ext.last_stats(lib)["mg_levels"] >= 2
+	assert np.array_equal(outs[0], outs[1])
+
+
 def test_coarse_level_is_deterministic(lib, monkeypatch):
 	monkeypatch.setenv("BFM_ONE_CTA", "0")
+	monkeypatch.setenv("BFM_MG", "0")
 	monkeypatch.setenv("BFM_COARSE_AGGREGATES", "32")
 
 	case = cases.build("gear60", lib)

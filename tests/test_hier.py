@@ -1,0 +1,93 @@
+"""Host side of the multilevel preconditioner (bfm_b200/csrc/hier.c), on CPU: structural invariants of the
+aggregation hierarchy - every connected node has an aggregate, aggregates are big enough for three independent
+rigid-body modes, every level's pattern is the symbolic product P^T A P, the colouring lets the device probe that
+product column by column - and, through tests/mg_emulation.py, the numerics of the cycle the device runs on it."""
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import cases
+import mg_emulation
+
+
+def _pattern(level):
+	n = level["n"]
+	return sp.csr_matrix((np.ones(len(level["col"]), np.int8), level["col"].astype(np.int64), level["rowptr"].astype(np.int64)), shape=(n, n))
+
+
+@pytest.mark.parametrize("name", ["gear60", "plate_160x40", "plate_300x75", "plate_jitter_40x10", "bridge_dam"])
+def test_hierarchy_invariants(name, lib, monkeypatch):
+	if name == "bridge_dam":
+		monkeypatch.setenv("BFM_MG_RATIO0", "6")      # a small truss mesh: small aggregates so that it still gets levels
+		monkeypatch.setenv("BFM_MG_DENSE_NODES", "64")
+
+	case = cases.build(name, lib)
+	levels = mg_emulation.hierarchy(lib, case.mesh)
+
+	assert len(levels) >= 2 and levels[0]["n"] == case.mesh.n_nodes
+
+	for l, (fine, coarse) in enumerate(zip(levels[:-1], levels[1:])):
+		agg, color = fine["agg"], fine["color"]
+		sizes = np.bincount(agg[agg >= 0], minlength=coarse["n"])
+
+		assert agg.max() == coarse["n"] - 1 and sizes.min() >= (3 if l == 0 else 1)
+		assert coarse["n"] * 10 <= fine["n"] * 7                     # it coarsens
+		assert np.all(np.diff(np.unique(agg[agg >= 0], return_index=True)[1]) > 0)  # ids follow the smallest member
+
+		# nodes left out are isolated (coupled to nothing but themselves)
+		degree = np.diff(fine["rowptr"])
+		assert np.all(degree[agg < 0] <= 1)
+
+		# pattern of the next level == pattern of P^T A P, P the aggregate indicator
+		keep = np.flatnonzero(agg >= 0)
+		P = sp.csr_matrix((np.ones(len(keep), np.int8), (keep, agg[keep].astype(np.int64))), shape=(fine["n"], coarse["n"]))
+		want = (P.T @ _pattern(fine) @ P).tocsr()
+		want.sort_indices()
+		got = _pattern(coarse)
+
+		assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+		assert np.all(np.diff(coarse["col"].astype(np.int64))[np.setdiff1d(np.arange(len(coarse["col"]) - 1), coarse["rowptr"][1:-1] - 1)] > 0)  # ascending columns
+
+		# probing colours: no row of the next level's pattern meets a colour twice
+		assert color.min() == 0 and color.max() == fine["n_colors"] - 1
+
+		for I in range(coarse["n"]):
+			row = coarse["col"][coarse["rowptr"][I]:coarse["rowptr"][I + 1]]
+			assert len(set(color[row].tolist())) == len(row), (l, I)
+
+		# geometry: relative to the centroid of the aggregate
+		for k in range(2):
+			sums = np.bincount(agg[keep], fine["geom"][keep, k], coarse["n"])
+			scale = np.abs(fine["geom"]).max() + 1e-300
+			assert np.abs(sums / sizes).max() <= 1e-5 * scale
+
+	# deterministic
+	again = mg_emulation.hierarchy(lib, case.mesh)
+	assert all(np.array_equal(a["agg"], b["agg"]) and np.array_equal(a["color"], b["color"]) for a, b in zip(levels, again))
+
+
+def test_no_hierarchy_for_tiny_meshes(lib):
+	from bfm_b200 import ext
+
+	assert mg_emulation.hierarchy(lib, ext.plate(4, 2, kind=3, binding=lib)) == []   # 15 nodes: nothing to coarsen
+	assert len(mg_emulation.hierarchy(lib, cases.build("lepl8", lib).mesh)) == 2     # 335 nodes: mesh level + dense level
+
+
+@pytest.mark.parametrize("name,most", [("gear60", 320), ("plate_160x40", 80), ("plate_jitter_40x10", 60)])
+def test_emulated_cycle_converges_to_the_reference(name, most, lib, golden):
+	"""the W-cycle of mg.cuh as a PCG preconditioner, emulated in numpy on the library's own hierarchy: converges
+	to 1e-12 in a mesh-independent handful of iterations and lands on the reference's displacements"""
+
+	case = cases.build(name, lib)
+	levels = mg_emulation.hierarchy(lib, case.mesh)
+	system = cases.oracle_problem(case).system()
+
+	emu = mg_emulation.Emulation(system.scipy().tocsr(), levels)
+	x, iterations = emu.solve(system.b.copy())
+
+	assert iterations <= most, iterations
+	assert all(0 < w * 1.0 < 1.6 for w in emu.omega)
+
+	want = golden[f"{name}/effects"].reshape(-1)
+	assert np.linalg.norm(x - want) / np.linalg.norm(want) <= 1e-9
