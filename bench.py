@@ -166,7 +166,17 @@ def reference_arm(args, rank: int):
 		return
 
 	nx, ny = parse_cells(args.cells)
+	sx, sy = parse_cells(args.reference_sample)
 	base = time_reference(args.reference_sample, args.steps, args.warmup)
+
+	# the dense reference cannot hold the GPU arm's plate (8 n^2 bytes, int index: n <= 46 340), so its line
+	# describes the plate it really ran; the GPU arm reports its own figure at this same size as `same_size`
+	config = workload_config(sx, sy, 1)
+	config["solver"] = "reference libbfm: dense assembly, RCM, band LU (unmodified, oracle/_ref)"
+	config["partition"] = "none (single-threaded CPU code)"
+	config["l2"] = "n/a (CPU)"
+	config["reference_sample"] = base["sample"]
+	config["gpu_arm_workload"] = workload_config(nx, ny, args.gpus)["workload"]
 
 	print(json.dumps({
 		"impl": "reference",
@@ -182,23 +192,77 @@ def reference_arm(args, rank: int):
 		"vs_baseline": None,
 		"dtype": "f64",
 		"data": "synthetic",
-		"config": workload_config(nx, ny, args.gpus) | {"reference_sample": base["sample"]},
+		"config": config,
+		"same_config": False,  # a cross-size ratio: the reference's DOF/s falls like 1/n, see `same_size` on the GPU arm's line
 		"cpu_baseline": base,
 		"e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
 		"gpu_launches": 0,
 	}), flush=True)
 
 
-def workload_config(nx: int, ny: int, gpus: int) -> dict:
+def workload_config(nx: int, ny: int, gpus: int, stats: dict | None = None) -> dict:
+	solver = "FP64 PCG to a relative residual of 1e-12, Jacobi scaling"
+
+	if stats and stats.get("mg_levels", 0):
+		solver += f" + aggregation multigrid W-cycle preconditioner ({stats['mg_levels']} levels, rigid-body modes per aggregate, damped-Jacobi smoothing fused into the SpMVs, dense last level of dimension {stats.get('coarse_dim', 0)})"
+	elif stats and stats.get("coarse_dim", 0):
+		solver += f" + one additive coarse level of rigid-body modes ({stats['coarse_dim'] // 3} aggregates, dense inverse)"
+
 	return {
 		"workload": f"synthetic structured triangulated plate {nx}x{ny} cells, {2 * (nx + 1) * (ny + 1)} DOF, plane stress, steel, gravity, left edge clamped (BASELINE.json configs[3])",
 		"cells": f"{nx}x{ny}",
 		"n_dofs": 2 * (nx + 1) * (ny + 1),
 		"element": "P1 triangle, 3-point Gauss",
-		"solver": "FP64 PCG, Jacobi scaling + rigid-body-mode coarse level (<= 2048 aggregates), relative residual 1e-12",
+		"solver": solver,
 		"partition": "none" if gpus == 1 else f"{gpus} contiguous node-row blocks, halo exchange + dot-product reductions over NVLink",
 		"l2": "inputs larger than L2 (matrix 6.3 GB at the default size, 126 MB of L2); no flush needed",
 	}
+
+
+
+# ---- algorithmic bytes of one multigrid-preconditioned PCG iteration (mg.cuh header) ----
+
+
+def mg_gammas(n_levels: int) -> list[int]:
+	"""visits of the next level per cycle on the sparse levels 1 .. n_levels - 2 (mg.cuh: BFM_MG_GAMMA, default 2)"""
+
+	env = os.environ.get("BFM_MG_GAMMA", "")
+	out = []
+
+	for l in range(1, n_levels - 1):
+		g = 2
+
+		if env:
+			parts = env.split(",")
+			g = int(parts[min(l - 1, len(parts) - 1)] or 2)
+
+		out.append(g if 1 <= g <= 4 else 2)
+
+	return out
+
+
+def mg_iteration_bytes(levels: list[dict], coarse_dim: int) -> dict:
+	"""levels: [{n, n_slots}] from bfmx_hier_info.  Stored-format bytes every kernel of one iteration must move:
+	level 0 (2x2 blocks, 36 B per slot): k_spmv<kDot> 36 S + 32 n, k_update_xr 96 n, k_spmv_mg<kPre> 36 S + 32 n,
+	k_mg_restrict 48 n (t 16 + P 24 in FP32 + 2 indices), k_mg_prolong 64 n, k_spmv_mg<kPost> 36 S + 48 n, k_update_p
+	48 n; level l >= 1 (3x3 blocks, 76 B per slot, gamma visits of the next level): (gamma + 1) fused SpMVs of
+	76 S + 72 n, gamma restrictions of 104 n and prolongations of 128 n (+ 24 n when adding); the dense last level
+	8 nc^2 per visit."""
+
+	n0, s0 = levels[0]["n"], levels[0]["n_slots"]
+	per_level = [3 * (36 * s0) + (32 + 96 + 32 + 48 + 64 + 48 + 48) * n0]
+	gammas = mg_gammas(len(levels))
+	visits = 1
+
+	for l in range(1, len(levels) - 1):
+		n, sl, g = levels[l]["n"], levels[l]["n_slots"], gammas[l - 1]
+		per_level.append(visits * ((g + 1) * (76 * sl + 72 * n) + g * (104 + 128) * n + (g - 1) * 24 * n + g * 24 * levels[l + 1]["n"]))
+		visits *= g
+
+	nc = (coarse_dim + 31) // 32 * 32
+	per_level.append(visits * 8 * nc * nc)
+
+	return {"total": sum(per_level), "per_level": per_level, "gammas": gammas, "dense_visits": visits}
 
 
 # ---- configs[4]: 1024 batched small systems ---------------------------------------------------------
@@ -436,7 +500,19 @@ def main():
 	canonical_bytes = 12 * 4 * s["n_blocks"] + 20 * n_own + 4        # scalar CSR, 12 B/nnz + 20 B/row
 	iter_bytes = stored_bytes + 72 * n_own                           # + update_xr (6 x 8 B/DOF) + update_p (3 x 8 B/DOF)
 
-	if s.get("coarse_dim", 0):
+	mg_model = None
+
+	if s.get("mg_levels", 0) and world == 1:
+		import ctypes
+
+		info = ext.HierInfo()
+		assert not lib.bfmx_hier_info(case.mesh.c_mesh, ctypes.byref(info))
+		levels = [{"n": info.n_nodes[l], "n_slots": info.n_slots[l]} for l in range(info.n_levels)]
+		mg_model = mg_iteration_bytes(levels, s["coarse_dim"])
+		mg_model["levels"] = levels
+		iter_bytes = mg_model["total"]
+
+	elif s.get("coarse_dim", 0):
 		# two-level preconditioner: restriction (index 4 B + r 16 B + W row 16 B per node), E^-1 g (dense, nc x nc doubles),
 		# prolongation fused in the p update (+ W row 16 B + aggregate id 4 B per node)
 		nc = (s["coarse_dim"] + 31) // 32 * 32
@@ -482,8 +558,29 @@ def main():
 			"bytes": iter_bytes,
 			"achieved": iter_bytes / (us_iter * 1e-6) / 1e9,
 			"frac": iter_bytes / (us_iter * 1e-6) / 1e9 / peak,
-			"note": "whole PCG iteration (SpMV + fused vector kernels + coarse-level restrict / apply / prolong) over the timed region: (solve ms - set-up ms) / iterations",
+			"note": "whole PCG iteration (CG SpMV + vector kernels + the preconditioner's fused SpMVs, restrictions, prolongations and coarser levels) over the timed region: (solve ms - set-up ms) / iterations",
+			"model": mg_model,
 		},
+	}
+
+	# assembly: one launch of k_assemble + the boundary-condition kernels.  Algorithmic bytes: connectivity
+	# 4 B x kind x elements, coordinates 16 B per node, contributor map 4 B per contribution (9 per P1 element) + 4 B per
+	# slot of list bounds, 32 B written per 2x2 block slot, 16 B of load vector per node
+	n_nodes_own = n_own // 2
+	n_elems = 2 * nx * ny // world
+	asm_bytes = 4 * 3 * n_elems + 16 * n_nodes_own + 4 * 9 * n_elems + 4 * s["n_slots"] + 32 * s["n_slots"] + 16 * n_nodes_own
+	ms_asm_kernel = statistics.mean(p["ms_assemble"] for p in per_step)
+
+	roofline_assembly = {
+		"kernel": "k_assemble<3,0,0> (one lane per 2x2 block walks its contributor list in the reference's order)",
+		"bound": "hbm",
+		"achieved": asm_bytes / (ms_asm_kernel * 1e-3) / 1e9,
+		"peak": peak,
+		"unit": "GB/s",
+		"frac": asm_bytes / (ms_asm_kernel * 1e-3) / 1e9 / peak,
+		"bytes_per_launch": asm_bytes,
+		"us_per_launch": ms_asm_kernel * 1e3,
+		"note": "latency- and FP64-bound rather than HBM-bound: every block recomputes its elements' geometry (bit-for-bit reference arithmetic, -fmad=false, true divisions); 1 % of a step",
 	}
 
 	# ---- end to end: bfm_sim_run on host buffers (the call pybfm makes), copies inside the timed region
@@ -549,7 +646,7 @@ def main():
 			"vs_baseline": None,  # the reference publishes no number for this metric
 			"dtype": "f64",
 			"data": "synthetic",
-			"config": workload_config(nx, ny, world),
+			"config": workload_config(nx, ny, world, s),
 			"assembly_ms": ms_asm,
 			"solve_ms": ms_solve,
 			"symbolic_setup_ms_once_per_mesh": symbolic_ms,
@@ -557,9 +654,13 @@ def main():
 		"coarse_dim": s.get("coarse_dim", 0),
 		"exchange": ("NVLink peer memory (CUDA IPC mailboxes), posted from inside the kernels" if s.get("uses_peer_memory") else "NCCL") if world > 1 else "none",
 		"solve_setup_ms": s.get("ms_solve_setup", 0.0),
-			"cg_rel_residual": s["cg_rel_residual"],
-			"cg_true_rel_residual": s["cg_true_rel_residual"],
+			"mg_levels": s.get("mg_levels", 0),
+			"cg_rel_residual": s["cg_rel_residual"],            # recursive residual CG stops on (<= 1e-12)
+			"cg_true_rel_residual": s["cg_true_rel_residual"],  # recomputed b - A x: floors at ~eps * cond(A) in FP64 for any solver
+			"cg_backward_error": s["cg_backward_error"],        # ||b - A x|| / (||x|| + ||b||), scaled norm: what a backward-stable solve guarantees
+			"cg_restarts": s["cg_restarts"],
 			"roofline": roofline,
+			"roofline_assembly": roofline_assembly,
 			"cpu_baseline": cpu,
 			"e2e": e2e,
 			"gpu_launches": launches,

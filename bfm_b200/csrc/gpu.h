@@ -159,10 +159,21 @@ typedef struct {
 	int32_t* diag_pos;
 	int32_t* row_len;
 
+	/* several GPUs (hier.c): rows [row_lo, row_hi) are this rank's; a distributed level refreshes its ghosts before
+	 * every product with its operator; one GPU: row_lo = 0, row_hi = n */
+	int32_t row_lo, row_hi;
+	int32_t distributed;
+	int32_t gather_first, gather_count; /* level below a replicated one: where this rank's aggregates sit in it */
+	int32_t n_nbr, n_send;
+	int32_t nbr[BFMG_DIST_MAX_RANKS];
+	int32_t recv_begin[BFMG_DIST_MAX_RANKS];
+	int32_t recv_count[BFMG_DIST_MAX_RANKS];
+	int32_t send_ptr[BFMG_DIST_MAX_RANKS + 1];
+	int32_t* send_idx;   /* device */
+
 	/* towards the next level (unused on the last) */
 	int32_t n_coarse;
 	int32_t n_p;
-	int32_t n_colors;
 	int32_t* agg;        /* [n] aggregate, -1: none */
 	float* geom;         /* [n] float2 */
 	int32_t* p_ptr;      /* prolongator entries by fine node */
@@ -170,7 +181,6 @@ typedef struct {
 	int32_t* r_ptr;      /* ... and by coarse node */
 	int32_t* r_ent;
 	int32_t* r_node;
-	int32_t* color;      /* [n_coarse] */
 } bfmg_mg_level_t;
 
 typedef struct {

@@ -15,12 +15,20 @@
  * (pieces too small to carry three independent modes join a neighbour).  Between two levels sits the
  * prolongator P, stored by its sparsity structure (CSR by fine node + its transpose by coarse node); its
  * values are computed on the device for every solve because they carry the matrix's diagonal scaling.  The
- * next level's operator P^T A P is computed on the device by probing: coarse nodes that share no row of
- * P^T A P get the same colour, so one product with the sum of one mode over one colour yields one column
- * per coarse node of that colour.  Pattern of P^T A P and the colouring are computed here, symbolically.
+ * next level's operator P^T A P is computed on the device too (k_mg_rap); its sparsity pattern is computed
+ * here, symbolically, as the same product.
  *
- * Everything is deterministic: ids follow the smallest member, sets are sorted, colours are greedy in id
- * order.
+ * Several GPUs (one rank per GPU, partition.c): every rank builds the hierarchy of ITS rows.  Aggregates are formed
+ * from owned nodes only, so they never straddle two ranks: restriction and prolongation stay local and only the
+ * products with a level's operator need a halo exchange, exactly as on the mesh level.  A level is DISTRIBUTED
+ * (local numbering: owned nodes first, then the ghosts of each neighbour, ascending by the owner's numbering)
+ * while it is large; from the first level of at most BFM_MG_REPLICATED_NODES nodes on it is REPLICATED: every
+ * rank holds all of it (global numbering, rank after rank) and runs it redundantly - cheaper than exchanging
+ * halos of a few hundred nodes several times per cycle.  What the ranks must tell each other while building -
+ * aggregate counts, the aggregates of ghost nodes, the rows of the first replicated level - goes through the
+ * communicator of dist.cu (a handful of small collectives, once per mesh).
+ *
+ * Everything is deterministic: ids follow the smallest member, sets are sorted.
  */
 #include "internal.h"
 
@@ -48,9 +56,8 @@ static void level_free(bfmi_hier_level_t* L) {
 		free(L->pos);
 	}
 
-	if (L->owns_owner) {
-		free((void*) L->owner);
-	}
+	free(L->send_idx);
+	bfmg_free(L->dev.send_idx);
 
 	free(L->agg);
 	free(L->geom);
@@ -59,7 +66,6 @@ static void level_free(bfmi_hier_level_t* L) {
 	free(L->r_ptr);
 	free(L->r_ent);
 	free(L->r_node);
-	free(L->color);
 
 	bfmg_mg_level_t* const d = &L->dev;
 
@@ -77,7 +83,6 @@ static void level_free(bfmi_hier_level_t* L) {
 	bfmg_free(d->r_ptr);
 	bfmg_free(d->r_ent);
 	bfmg_free(d->r_node);
-	bfmg_free(d->color);
 }
 
 void bfmi_hier_free(bfmi_hier_t* h) {
@@ -102,9 +107,15 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 	int32_t const n = L->n;
 	double const* const pos = L->pos;
 
-	double x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
+	int32_t const lo = L->row_lo, hi = L->row_hi; /* the nodes this rank aggregates: all of them on one GPU */
 
 	for (int32_t a = 0; a < n; a++) {
+		agg[a] = -1;
+	}
+
+	double x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
+
+	for (int32_t a = lo; a < hi; a++) {
 		double const x = pos[2 * (size_t) a + 0];
 		double const y = pos[2 * (size_t) a + 1];
 
@@ -153,8 +164,13 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 		return 0;
 	}
 
-#pragma omp parallel for schedule(static) if (n > 100000)
 	for (int32_t a = 0; a < n; a++) {
+		bin[a] = -1;
+		parent[a] = a;
+	}
+
+#pragma omp parallel for schedule(static) if (hi - lo > 100000)
+	for (int32_t a = lo; a < hi; a++) {
 		int64_t bx = (int64_t) ((pos[2 * (size_t) a + 0] - x0) / wx * (double) nbx);
 		int64_t by = (int64_t) ((pos[2 * (size_t) a + 1] - y0) / wy * (double) nby);
 
@@ -179,11 +195,11 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 	 * root wins, so the result does not depend on traversal order; on a solid mesh a bin is one piece, on
 	 * truss-like geometry a bin can cut through members that do not touch and each becomes its own aggregate */
 
-	for (int32_t a = 0; a < n; a++) {
+	for (int32_t a = lo; a < hi; a++) {
 		for (int32_t t = 0; t < L->row_len[a]; t++) {
 			int32_t const b = L->scol[slot_of(L->slice_off, a, t)];
 
-			if (b < a && bin[b] == bin[a] && (L->owner == NULL || L->owner[a] == L->owner[b])) {
+			if (b < a && b >= lo && bin[b] == bin[a]) {
 				int32_t ra, rb;
 
 				FIND(a, ra);
@@ -208,7 +224,7 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 	for (int pass = 0; pass < 4 && min_nodes > 1; pass++) {
 		memset(size, 0, ((size_t) n + 1) * sizeof *size);
 
-		for (int32_t a = 0; a < n; a++) {
+		for (int32_t a = lo; a < hi; a++) {
 			int32_t r;
 			FIND(a, r);
 			size[r]++;
@@ -216,7 +232,7 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 
 		bool changed = false;
 
-		for (int32_t a = 0; a < n; a++) {
+		for (int32_t a = lo; a < hi; a++) {
 			int32_t ra;
 			FIND(a, ra);
 
@@ -228,7 +244,7 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 				int32_t const b = L->scol[slot_of(L->slice_off, a, t)];
 				int32_t rb;
 
-				if (b == a || (L->owner != NULL && L->owner[a] != L->owner[b])) {
+				if (b == a || b < lo || b >= hi) {
 					continue;
 				}
 
@@ -254,7 +270,7 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 
 	memset(size, 0, ((size_t) n + 1) * sizeof *size);
 
-	for (int32_t a = 0; a < n; a++) {
+	for (int32_t a = lo; a < hi; a++) {
 		int32_t r;
 		FIND(a, r);
 		size[r]++;
@@ -264,13 +280,13 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 
 	int32_t n_agg = 0;
 
-	for (int32_t a = 0; a < n; a++) {
+	for (int32_t a = lo; a < hi; a++) {
 		if (parent[a] == a) {
 			bin[a] = size[a] >= min_nodes ? n_agg++ : -1; /* bin[] is free now: reuse as root -> id */
 		}
 	}
 
-	for (int32_t a = 0; a < n; a++) {
+	for (int32_t a = lo; a < hi; a++) {
 		int32_t r;
 		FIND(a, r);
 		agg[a] = bin[r];
@@ -287,7 +303,8 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 
 /* ---- the structures between level l and level l + 1 -------------------------------------------------------- */
 
-/* CSR of the prolongator (one entry per node: its aggregate) and its transpose */
+/* CSR of the prolongator (one entry per node that has an aggregate - ghosts included, the Galerkin product needs
+ * their rows) and its transpose over the nodes this rank owns (restriction sums over owned nodes only) */
 static int build_transfer(bfmi_hier_level_t* L) {
 	int32_t const n = L->n;
 	int32_t const nc = L->n_coarse;
@@ -320,7 +337,10 @@ static int build_transfer(bfmi_hier_level_t* L) {
 	for (int32_t a = 0; a < n; a++) {
 		if (L->agg[a] >= 0) {
 			L->p_col[L->p_ptr[a]] = L->agg[a];
-			L->r_ptr[L->agg[a] + 2]++;
+
+			if (a >= L->row_lo && a < L->row_hi) {
+				L->r_ptr[L->agg[a] + 2]++;
+			}
 		}
 	}
 
@@ -328,7 +348,7 @@ static int build_transfer(bfmi_hier_level_t* L) {
 		L->r_ptr[g + 2] += L->r_ptr[g + 1];
 	}
 
-	for (int32_t a = 0; a < n; a++) { /* ascending nodes inside every coarse node's list */
+	for (int32_t a = L->row_lo; a < L->row_hi; a++) { /* ascending nodes inside every coarse node's list */
 		for (int32_t e = L->p_ptr[a]; e < L->p_ptr[a + 1]; e++) {
 			int32_t const at = L->r_ptr[L->p_col[e] + 1]++;
 
@@ -346,36 +366,28 @@ static int cmp_i32(void const* a, void const* b) {
 	return x < y ? -1 : x > y;
 }
 
-/* pattern of P^T A P as a SELL-32 node pattern of the next level: coarse node I couples to J when some node in
- * the support of column I of P is coupled (through A) to a node in the support of column J */
-static int build_coarse_pattern(bfmi_hier_level_t const* L, bfmi_hier_level_t* N) {
+static int cmp_i64(void const* a, void const* b) {
+	int64_t const x = *(int64_t const*) a;
+	int64_t const y = *(int64_t const*) b;
+	return x < y ? -1 : x > y;
+}
+
+/* rows [first, first + count) of the pattern of P^T A P: coarse node I couples to J when some node in the support of
+ * column I of P is coupled (through A) to a node in the support of column J.  rows[i] (malloc'd, ascending) and
+ * lens[i] for i = I - first. */
+static int coarse_rows(bfmi_hier_level_t const* L, int32_t first, int32_t count, int32_t** rows, int32_t* lens) {
 	int32_t const nc = L->n_coarse;
-
-	N->n = nc;
-	N->owns_pattern = true;
-	N->row_len = calloc((size_t) nc + 1, sizeof *N->row_len);
-
-	int64_t* const row_ptr = calloc((size_t) nc + 2, sizeof *row_ptr);
-
-	if (N->row_len == NULL || row_ptr == NULL) {
-		free(row_ptr);
-		return -1;
-	}
 
 	int const n_threads =
 #ifdef _OPENMP
-		nc > 20000 ? omp_get_max_threads() : 1;
+		count > 20000 ? omp_get_max_threads() : 1;
 #else
 		1;
 #endif
 
 	int32_t* const marks = malloc((size_t) n_threads * ((size_t) nc + 1) * sizeof *marks);
-	int32_t** const rows = calloc((size_t) nc + 1, sizeof *rows); /* per coarse node: its sorted column list */
 
-	if (marks == NULL || rows == NULL) {
-		free(marks);
-		free(rows);
-		free(row_ptr);
+	if (marks == NULL) {
 		return -1;
 	}
 
@@ -394,7 +406,8 @@ static int build_coarse_pattern(bfmi_hier_level_t const* L, bfmi_hier_level_t* N
 		int32_t* buf = malloc((size_t) cap * sizeof *buf);
 
 #pragma omp for schedule(dynamic, 256)
-		for (int32_t I = 0; I < nc; I++) {
+		for (int32_t i = 0; i < count; i++) {
+			int32_t const I = first + i;
 			int32_t cnt = 0;
 
 			if (buf == NULL) {
@@ -437,62 +450,62 @@ static int build_coarse_pattern(bfmi_hier_level_t const* L, bfmi_hier_level_t* N
 
 			qsort(buf, (size_t) cnt, sizeof *buf, cmp_i32);
 
-			rows[I] = malloc((size_t) cnt * sizeof **rows);
+			rows[i] = malloc((size_t) cnt * sizeof **rows);
 
-			if (rows[I] == NULL) {
+			if (rows[i] == NULL) {
 				failed = true;
 				continue;
 			}
 
-			memcpy(rows[I], buf, (size_t) cnt * sizeof *buf);
-			N->row_len[I] = cnt;
+			memcpy(rows[i], buf, (size_t) cnt * sizeof *buf);
+			lens[i] = cnt;
 		}
 
 		free(buf);
 	}
 
 	free(marks);
+	return failed ? -1 : 0;
+}
 
-	int rv = -1;
-
-	if (failed) {
-		goto done;
-	}
-
-	N->n_slices = (nc + SLICE - 1) / SLICE;
+/* SELL-32 layout of n_rows pattern rows (N->n vector entries: the columns may reach beyond the rows - ghosts) */
+static int layout_level(bfmi_hier_level_t* N, int32_t n_rows, int32_t* const* rows, int32_t const* lens) {
+	N->owns_pattern = true;
+	N->row_len = calloc((size_t) n_rows + 1, sizeof *N->row_len);
+	N->n_slices = (n_rows + SLICE - 1) / SLICE;
 	N->slice_off = malloc(((size_t) N->n_slices + 1) * sizeof *N->slice_off);
 
-	if (N->slice_off == NULL) {
-		goto done;
+	if (N->row_len == NULL || N->slice_off == NULL) {
+		return -1;
 	}
 
-	{
-		int64_t off = 0;
+	memcpy(N->row_len, lens, (size_t) n_rows * sizeof *lens);
 
-		for (int32_t s = 0; s < N->n_slices; s++) {
-			int32_t longest = 0;
+	int64_t off = 0;
 
-			for (int32_t a = s * SLICE; a < nc && a < (s + 1) * SLICE; a++) {
-				longest = N->row_len[a] > longest ? N->row_len[a] : longest;
-			}
+	for (int32_t s = 0; s < N->n_slices; s++) {
+		int32_t longest = 0;
 
-			N->slice_off[s] = (int32_t) off;
-			off += (int64_t) longest * SLICE;
-
-			if (off > INT32_MAX / 9) { /* nine value planes are indexed with 32-bit slots */
-				goto done;
-			}
+		for (int32_t a = s * SLICE; a < n_rows && a < (s + 1) * SLICE; a++) {
+			longest = lens[a] > longest ? lens[a] : longest;
 		}
 
-		N->slice_off[N->n_slices] = (int32_t) off;
-		N->n_slots = off;
+		N->slice_off[s] = (int32_t) off;
+		off += (int64_t) longest * SLICE;
+
+		if (off > INT32_MAX / 9) { /* nine value planes are indexed with 32-bit slots */
+			return -1;
+		}
 	}
 
+	N->slice_off[N->n_slices] = (int32_t) off;
+	N->n_slots = off;
+
 	N->scol = malloc(((size_t) N->n_slots + 1) * sizeof *N->scol);
-	N->diag_pos = malloc(((size_t) nc + 1) * sizeof *N->diag_pos);
+	N->diag_pos = malloc(((size_t) n_rows + 1) * sizeof *N->diag_pos);
 
 	if (N->scol == NULL || N->diag_pos == NULL) {
-		goto done;
+		return -1;
 	}
 
 	/* padding slots point at their own row (clamped) and carry zeros */
@@ -500,12 +513,12 @@ static int build_coarse_pattern(bfmi_hier_level_t const* L, bfmi_hier_level_t* N
 	for (int32_t s = 0; s < N->n_slices; s++) {
 		for (int32_t slot = N->slice_off[s]; slot < N->slice_off[s + 1]; slot++) {
 			int32_t const a = s * SLICE + (slot - N->slice_off[s]) % SLICE;
-			N->scol[slot] = a < nc ? a : nc - 1;
+			N->scol[slot] = a < n_rows ? a : n_rows - 1;
 		}
 	}
 
-	for (int32_t I = 0; I < nc; I++) {
-		for (int32_t t = 0; t < N->row_len[I]; t++) {
+	for (int32_t I = 0; I < n_rows; I++) {
+		for (int32_t t = 0; t < lens[I]; t++) {
 			int64_t const slot = slot_of(N->slice_off, I, t);
 
 			N->scol[slot] = rows[I][t];
@@ -516,69 +529,124 @@ static int build_coarse_pattern(bfmi_hier_level_t const* L, bfmi_hier_level_t* N
 		}
 	}
 
-	rv = 0;
+	return 0;
+}
 
-done:
+/* ---- what the ranks tell each other while building (device-staged: the communicator lives in dist.cu) ------- */
 
-	for (int32_t I = 0; I < nc; I++) {
-		free(rows[I]);
+static int comm_allgather(double const* mine, size_t count, double* all) {
+	int const world = bfmg_dist_world();
+	double *d_send = NULL, *d_recv = NULL;
+	int rv = -1;
+
+	if (
+		bfmg_alloc((void**) &d_send, (count + 1) * sizeof(double)) == 0 &&
+		bfmg_alloc((void**) &d_recv, ((size_t) world * count + 1) * sizeof(double)) == 0 &&
+		bfmg_upload(d_send, mine, count * sizeof(double)) == 0 &&
+		bfmg_dist_allgather_f64(d_send, d_recv, (int) count) == 0 &&
+		bfmg_download(all, d_recv, (size_t) world * count * sizeof(double)) == 0
+	) {
+		rv = 0;
 	}
 
-	free(rows);
-	free(row_ptr);
+	bfmg_free(d_send);
+	bfmg_free(d_recv);
 
 	return rv;
 }
 
-/* greedy distance-2 colouring of the next level's pattern: I differs from every J that shares a row with it
- * (J in row K and I in row K for some K; the pattern is symmetric), so that the columns probed together never
- * meet in a row */
-static int color_level(bfmi_hier_level_t* L, bfmi_hier_level_t const* N) {
-	int32_t const nc = N->n;
+/* every rank's variable-length list, one after the other in rank order: *out (malloc'd), counts[world] */
+static int comm_allgather_v(double const* mine, size_t count, double** out, size_t* counts) {
+	int const world = bfmg_dist_world();
+	double const my_count = (double) count;
+	double all_counts[BFMG_DIST_MAX_RANKS];
 
-	L->color = malloc(((size_t) nc + 1) * sizeof *L->color);
-
-	int32_t* const mark = malloc(((size_t) nc + 1) * sizeof *mark); /* indexed by colour: never more colours than nodes */
-
-	if (L->color == NULL || mark == NULL) {
-		free(mark);
+	if (comm_allgather(&my_count, 1, all_counts) < 0) {
 		return -1;
 	}
 
-	for (int32_t I = 0; I < nc; I++) {
-		L->color[I] = -1;
-		mark[I] = -1;
+	size_t longest = 1, total = 0;
+
+	for (int r = 0; r < world; r++) {
+		counts[r] = (size_t) all_counts[r];
+		longest = counts[r] > longest ? counts[r] : longest;
+		total += counts[r];
 	}
 
-	int32_t n_colors = 0;
+	double* const padded = calloc(longest, sizeof *padded);
+	double* const all = malloc((size_t) world * longest * sizeof *all);
 
-	for (int32_t I = 0; I < nc; I++) {
-		for (int32_t t = 0; t < N->row_len[I]; t++) {
-			int32_t const K = N->scol[slot_of(N->slice_off, I, t)];
+	*out = malloc((total + 1) * sizeof **out);
 
-			for (int32_t u = 0; u < N->row_len[K]; u++) {
-				int32_t const J = N->scol[slot_of(N->slice_off, K, u)];
-
-				if (J != I && L->color[J] >= 0) {
-					mark[L->color[J]] = I;
-				}
-			}
-		}
-
-		int32_t col = 0;
-
-		while (mark[col] == I) {
-			col++;
-		}
-
-		L->color[I] = col;
-		n_colors = col + 1 > n_colors ? col + 1 : n_colors;
+	if (padded == NULL || all == NULL || *out == NULL) {
+		free(padded);
+		free(all);
+		free(*out);
+		*out = NULL;
+		return -1;
 	}
 
-	L->n_colors = n_colors;
+	memcpy(padded, mine, count * sizeof *mine);
 
-	free(mark);
-	return 0;
+	int const rv = comm_allgather(padded, longest, all);
+
+	if (rv == 0) {
+		size_t at = 0;
+
+		for (int r = 0; r < world; r++) {
+			memcpy(*out + at, all + (size_t) r * longest, counts[r] * sizeof(double));
+			at += counts[r];
+		}
+	}
+
+	else {
+		free(*out);
+		*out = NULL;
+	}
+
+	free(padded);
+	free(all);
+
+	return rv;
+}
+
+/* ghost entries of vec (two doubles per node of level L) from their owners */
+static int comm_halo(bfmi_hier_level_t const* L, double* vec) {
+	if (L->n_nbr == 0) {
+		return 0;
+	}
+
+	bfmg_halo_t halo = {0};
+	double *d_vec = NULL, *d_buf = NULL;
+	int32_t* d_idx = NULL;
+	int rv = -1;
+
+	halo.n_nbr = L->n_nbr;
+	halo.nbr = L->nbr;
+	halo.recv_begin = L->recv_begin;
+	halo.recv_count = L->recv_count;
+	halo.send_ptr = L->send_ptr;
+	halo.n_send = L->n_send;
+
+	if (
+		bfmg_alloc((void**) &d_vec, ((size_t) L->n + 1) * 2 * sizeof(double)) == 0 &&
+		bfmg_alloc((void**) &d_buf, ((size_t) L->n_send + 1) * 2 * sizeof(double)) == 0 &&
+		bfmg_alloc((void**) &d_idx, ((size_t) L->n_send + 1) * sizeof(int32_t)) == 0 &&
+		bfmg_upload(d_vec, vec, (size_t) L->n * 2 * sizeof(double)) == 0 &&
+		(L->n_send == 0 || bfmg_upload(d_idx, L->send_idx, (size_t) L->n_send * sizeof(int32_t)) == 0)
+	) {
+		halo.d_send_idx = d_idx;
+
+		if (bfmg_dist_halo(&halo, d_vec, d_buf) == 0 && bfmg_download(vec, d_vec, (size_t) L->n * 2 * sizeof(double)) == 0) {
+			rv = 0;
+		}
+	}
+
+	bfmg_free(d_vec);
+	bfmg_free(d_buf);
+	bfmg_free(d_idx);
+
+	return rv;
 }
 
 /* ---- the hierarchy ---------------------------------------------------------------------------------------- */
@@ -588,15 +656,75 @@ static int64_t env_i64(char const* name, int64_t fallback) {
 	return env != NULL && env[0] != 0 ? atoll(env) : fallback;
 }
 
-bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, int32_t const* owner) {
+/* reference points of the aggregates of L (centroids over the nodes this rank aggregated) into cen[2 * n_agg], and
+ * the geometry of the owned nodes relative to them (ghosts: filled by the exchange, or unused) */
+static int centroids(bfmi_hier_level_t* L, int32_t n_agg, int32_t id_shift, double* cen) {
+	int32_t* const count = calloc((size_t) n_agg + 1, sizeof *count);
+
+	L->geom = calloc(((size_t) L->n + 1) * 2, sizeof *L->geom);
+
+	if (count == NULL || L->geom == NULL) {
+		free(count);
+		return -1;
+	}
+
+	for (int32_t a = L->row_lo; a < L->row_hi; a++) { /* fixed order: identical wherever it is computed */
+		int32_t const g = L->agg[a] - id_shift;
+
+		if (L->agg[a] >= 0) {
+			cen[2 * (size_t) g + 0] += L->pos[2 * (size_t) a + 0];
+			cen[2 * (size_t) g + 1] += L->pos[2 * (size_t) a + 1];
+			count[g]++;
+		}
+	}
+
+	for (int32_t g = 0; g < n_agg; g++) {
+		cen[2 * (size_t) g + 0] /= (double) count[g];
+		cen[2 * (size_t) g + 1] /= (double) count[g];
+	}
+
+	free(count);
+
+	for (int32_t a = L->row_lo; a < L->row_hi; a++) {
+		int32_t const g = L->agg[a] - id_shift;
+
+		if (L->agg[a] >= 0) {
+			L->geom[2 * (size_t) a + 0] = (float) (L->pos[2 * (size_t) a + 0] - cen[2 * (size_t) g + 0]);
+			L->geom[2 * (size_t) a + 1] = (float) (L->pos[2 * (size_t) a + 1] - cen[2 * (size_t) g + 1]);
+		}
+	}
+
+	return 0;
+}
+
+/* the rank that owns ghost node b of a distributed level (index into L->nbr), or -1 */
+static int ghost_owner(bfmi_hier_level_t const* L, int32_t b) {
+	for (int k = 0; k < L->n_nbr; k++) {
+		if (b >= L->recv_begin[k] && b < L->recv_begin[k] + L->recv_count[k]) {
+			return k;
+		}
+	}
+
+	return -1;
+}
+
+bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, bfmi_part_t const* part) {
 	/* aggregate sizes: nodes per aggregate on the mesh level and on the levels above; the last level is solved by
 	 * a dense inverse and may hold this many nodes (three unknowns each) */
 	int64_t const ratio0 = env_i64("BFM_MG_RATIO0", 12);
 	int64_t const ratio = env_i64("BFM_MG_RATIO", 6);
-	int64_t const dense_nodes = env_i64("BFM_MG_DENSE_NODES", 640);
+	int64_t const dense_nodes = env_i64("BFM_MG_DENSE_NODES", 1024);
 	int64_t const dense_limit = 2 * dense_nodes; /* pieces of bins can exceed the target */
+	int64_t replicated_nodes = env_i64("BFM_MG_REPLICATED_NODES", 65536);
 
-	if (ratio0 < 2 || ratio < 2 || plan->nb < 4 * ratio0) {
+	int const world = part != NULL ? part->world : 1;
+	int const rank = part != NULL ? part->rank : 0;
+
+	replicated_nodes = replicated_nodes < dense_limit ? dense_limit : replicated_nodes; /* the dense level is always replicated */
+
+	int64_t n_glob = part != NULL ? (int64_t) part->n_nodes : plan->nb; /* nodes of the current level over all ranks */
+
+	if (ratio0 < 2 || ratio < 2 || n_glob < 4 * ratio0 || world > BFMG_DIST_MAX_RANKS) {
 		return NULL;
 	}
 
@@ -620,8 +748,34 @@ bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, int3
 	L->scol = plan->scol;
 	L->diag_pos = plan->diag_pos;
 	L->pos = (double*) coords;
-	L->owner = owner;
 	L->owns_pattern = false;
+	L->row_lo = 0;
+	L->row_hi = plan->nb;
+
+	if (part != NULL) {
+		L->distributed = true;
+		L->row_lo = part->own_begin;
+		L->row_hi = part->own_end;
+		L->n_nbr = part->n_nbr;
+		L->n_send = part->n_send;
+
+		if (part->n_nbr > BFMG_DIST_MAX_RANKS) {
+			goto fail;
+		}
+
+		memcpy(L->nbr, part->nbr, (size_t) part->n_nbr * sizeof(int32_t));
+		memcpy(L->recv_begin, part->recv_begin, (size_t) part->n_nbr * sizeof(int32_t));
+		memcpy(L->recv_count, part->recv_count, (size_t) part->n_nbr * sizeof(int32_t));
+		memcpy(L->send_ptr, part->send_ptr, ((size_t) part->n_nbr + 1) * sizeof(int32_t));
+
+		L->send_idx = malloc(((size_t) part->n_send + 1) * sizeof(int32_t));
+
+		if (L->send_idx == NULL) {
+			goto fail;
+		}
+
+		memcpy(L->send_idx, part->send_idx, (size_t) part->n_send * sizeof(int32_t));
+	}
 
 	h->n_levels = 1;
 
@@ -632,7 +786,8 @@ bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, int3
 			goto fail;
 		}
 
-		int64_t target = L->n / (l == 0 ? ratio0 : ratio);
+		int32_t const n_own = L->row_hi - L->row_lo;
+		int64_t target = n_glob / (l == 0 ? ratio0 : ratio);
 
 		/* close to the dense level: aim straight at it instead of leaving a tiny level in between */
 		if (target <= 2 * dense_nodes) {
@@ -640,7 +795,12 @@ bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, int3
 		}
 
 		if (target < 4) {
-			goto fail;
+			goto fail; /* the same decision on every rank: n_glob is global */
+		}
+
+		if (L->distributed) { /* this rank's share of the aggregates */
+			target = (int64_t) ((double) target * (double) n_own / (double) n_glob + 0.5);
+			target = target < 1 ? 1 : target;
 		}
 
 		L->agg = malloc(((size_t) L->n + 1) * sizeof *L->agg);
@@ -651,79 +811,405 @@ bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, int3
 
 		int32_t const n_agg = aggregate_level(L, target, l == 0 ? MIN_NODES_LEVEL0 : 1, L->agg);
 
-		if (n_agg < 4 || (int64_t) n_agg * 10 > (int64_t) L->n * 7) {
-			goto fail; /* no coarsening to speak of (or nothing to aggregate): the caller falls back */
-		}
-
-		L->n_coarse = n_agg;
-
 		bfmi_hier_level_t* const N = &h->level[l + 1];
 
 		N->dofs = 3;
+		N->owns_pattern = true;
 		h->n_levels = l + 2;
 
-		/* reference points of the next level: centroids of the aggregates; geometry of P relative to them */
+		int64_t n_glob_next = n_agg;
 
-		N->pos = calloc((size_t) n_agg * 2 + 2, sizeof *N->pos);
-		L->geom = malloc(((size_t) L->n + 1) * 2 * sizeof *L->geom);
+		if (!L->distributed) {
+			/* one GPU, or a replicated level: everything is here */
 
-		int32_t* const count = calloc((size_t) n_agg + 1, sizeof *count);
+			if (n_agg < 4 || (int64_t) n_agg * 10 > n_glob * 7) {
+				goto fail; /* no coarsening to speak of (or nothing to aggregate): the caller falls back */
+			}
 
-		if (N->pos == NULL || L->geom == NULL || count == NULL) {
-			free(count);
-			N->owns_pattern = true; /* so that level_free releases N->pos */
-			goto fail;
-		}
+			L->n_coarse = n_agg;
+			N->n = n_agg;
+			N->row_lo = 0;
+			N->row_hi = n_agg;
+			N->pos = calloc((size_t) n_agg * 2 + 2, sizeof *N->pos);
 
-		N->owns_pattern = true;
+			int32_t** const rows = calloc((size_t) n_agg + 1, sizeof *rows);
+			int32_t* const lens = calloc((size_t) n_agg + 1, sizeof *lens);
 
-		for (int32_t a = 0; a < L->n; a++) { /* fixed order: identical wherever it is computed */
-			int32_t const g = L->agg[a];
+			int rv = N->pos != NULL && rows != NULL && lens != NULL ? 0 : -1;
 
-			if (g >= 0) {
-				N->pos[2 * (size_t) g + 0] += L->pos[2 * (size_t) a + 0];
-				N->pos[2 * (size_t) g + 1] += L->pos[2 * (size_t) a + 1];
-				count[g]++;
+			rv = rv < 0 ? rv : centroids(L, n_agg, 0, N->pos);
+			rv = rv < 0 ? rv : build_transfer(L);
+			rv = rv < 0 ? rv : coarse_rows(L, 0, n_agg, rows, lens);
+			rv = rv < 0 ? rv : layout_level(N, n_agg, rows, lens);
+
+			for (int32_t I = 0; rows != NULL && I < n_agg; I++) {
+				free(rows[I]);
+			}
+
+			free(rows);
+			free(lens);
+
+			if (rv < 0) {
+				goto fail;
 			}
 		}
 
-		for (int32_t g = 0; g < n_agg; g++) {
-			N->pos[2 * (size_t) g + 0] /= (double) count[g];
-			N->pos[2 * (size_t) g + 1] /= (double) count[g];
-		}
+		else {
+			/* several GPUs, distributed level: every rank has aggregated its own nodes */
 
-		free(count);
+			double const mine = n_agg;
+			double counts[BFMG_DIST_MAX_RANKS];
 
-		for (int32_t a = 0; a < L->n; a++) {
-			int32_t const g = L->agg[a];
-
-			L->geom[2 * (size_t) a + 0] = g >= 0 ? (float) (L->pos[2 * (size_t) a + 0] - N->pos[2 * (size_t) g + 0]) : 0;
-			L->geom[2 * (size_t) a + 1] = g >= 0 ? (float) (L->pos[2 * (size_t) a + 1] - N->pos[2 * (size_t) g + 1]) : 0;
-		}
-
-		if (owner != NULL) {
-			/* an aggregate belongs to the rank of its members (they all share one) */
-			int32_t* const up = malloc(((size_t) n_agg + 1) * sizeof *up);
-
-			if (up == NULL) {
+			if (comm_allgather(&mine, 1, counts) < 0) {
 				goto fail;
 			}
 
-			for (int32_t a = L->n - 1; a >= 0; a--) {
-				if (L->agg[a] >= 0) {
-					up[L->agg[a]] = L->owner[a];
+			int64_t first = 0; /* global id of this rank's first aggregate */
+
+			n_glob_next = 0;
+
+			for (int r = 0; r < world; r++) {
+				first += r < rank ? (int64_t) counts[r] : 0;
+				n_glob_next += (int64_t) counts[r];
+			}
+
+			if (n_glob_next < 4 || n_glob_next * 10 > n_glob * 7 || n_glob_next > INT32_MAX / 4) {
+				goto fail; /* the same decision on every rank */
+			}
+
+			bool const replicate = n_glob_next <= replicated_nodes;
+
+			/* aggregate ids of the next level's numbering: global when it is replicated, owner-local otherwise */
+
+			int32_t const shift = replicate ? (int32_t) first : 0;
+
+			for (int32_t a = L->row_lo; a < L->row_hi && shift > 0; a++) {
+				L->agg[a] += L->agg[a] >= 0 ? shift : 0;
+			}
+
+			double* const cen = calloc((size_t) n_agg * 2 + 2, sizeof *cen);
+			double* const ids = calloc(((size_t) L->n + 1) * 2, sizeof *ids);
+			double* const geo = calloc(((size_t) L->n + 1) * 2, sizeof *geo);
+
+			int rv = cen != NULL && ids != NULL && geo != NULL ? 0 : -1;
+
+			rv = rv < 0 ? rv : centroids(L, n_agg, shift, cen);
+
+			for (int32_t a = L->row_lo; rv == 0 && a < L->row_hi; a++) {
+				ids[2 * (size_t) a] = L->agg[a];
+				geo[2 * (size_t) a + 0] = L->geom[2 * (size_t) a + 0];
+				geo[2 * (size_t) a + 1] = L->geom[2 * (size_t) a + 1];
+			}
+
+			/* the aggregates and geometry of the ghost nodes come from their owners */
+
+			rv = rv < 0 ? rv : comm_halo(L, ids);
+			rv = rv < 0 ? rv : comm_halo(L, geo);
+
+			if (rv < 0) {
+				free(cen);
+				free(ids);
+				free(geo);
+				goto fail;
+			}
+
+			for (int32_t b = 0; b < L->n; b++) {
+				if (b < L->row_lo || b >= L->row_hi) {
+					L->geom[2 * (size_t) b + 0] = (float) geo[2 * (size_t) b + 0];
+					L->geom[2 * (size_t) b + 1] = (float) geo[2 * (size_t) b + 1];
 				}
 			}
 
-			N->owner = up;
-			N->owns_owner = true;
+			free(geo);
+
+			if (replicate) {
+				/* the next level is held by every rank in full, numbered globally (rank after rank) */
+
+				for (int32_t b = 0; b < L->n; b++) {
+					if (b < L->row_lo || b >= L->row_hi) {
+						L->agg[b] = ghost_owner(L, b) >= 0 ? (int32_t) ids[2 * (size_t) b] : -1;
+					}
+				}
+
+				free(ids);
+
+				L->n_coarse = (int32_t) n_glob_next;
+				L->gather_first = (int32_t) first;
+				L->gather_count = n_agg;
+
+				N->n = (int32_t) n_glob_next;
+				N->row_lo = 0;
+				N->row_hi = N->n;
+
+				/* reference points and pattern rows of everybody's aggregates */
+
+				double* all_pos = NULL;
+				size_t per_rank[BFMG_DIST_MAX_RANKS];
+
+				rv = comm_allgather_v(cen, (size_t) n_agg * 2, &all_pos, per_rank);
+				free(cen);
+
+				if (rv < 0 || build_transfer(L) < 0) {
+					free(all_pos);
+					goto fail;
+				}
+
+				N->pos = all_pos;
+
+				int32_t** const rows = calloc((size_t) n_agg + 1, sizeof *rows);
+				int32_t* const lens = calloc((size_t) n_agg + 1, sizeof *lens);
+
+				rv = rows != NULL && lens != NULL ? coarse_rows(L, (int32_t) first, n_agg, rows, lens) : -1;
+
+				size_t packed_len = 0;
+
+				for (int32_t i = 0; rv == 0 && i < n_agg; i++) {
+					packed_len += 1 + (size_t) lens[i];
+				}
+
+				double* const packed = malloc((packed_len + 1) * sizeof *packed);
+				double* all_rows = NULL;
+
+				if (rv == 0 && packed != NULL) {
+					size_t at = 0;
+
+					for (int32_t i = 0; i < n_agg; i++) {
+						packed[at++] = lens[i];
+
+						for (int32_t t = 0; t < lens[i]; t++) {
+							packed[at++] = rows[i][t];
+						}
+					}
+
+					rv = comm_allgather_v(packed, packed_len, &all_rows, per_rank);
+				}
+
+				else {
+					rv = -1;
+				}
+
+				for (int32_t i = 0; rows != NULL && i < n_agg; i++) {
+					free(rows[i]);
+				}
+
+				free(rows);
+				free(lens);
+				free(packed);
+
+				if (rv < 0) {
+					free(all_rows);
+					goto fail;
+				}
+
+				/* unpack: rows arrive in global order (rank after rank, each rank's in its own order) */
+
+				int32_t** const grows = calloc((size_t) N->n + 1, sizeof *grows);
+				int32_t* const glens = calloc((size_t) N->n + 1, sizeof *glens);
+
+				rv = grows != NULL && glens != NULL ? 0 : -1;
+
+				size_t at = 0, total = 0;
+
+				for (int r = 0; r < world; r++) {
+					total += per_rank[r];
+				}
+
+				for (int32_t I = 0; rv == 0 && I < N->n; I++) {
+					if (at >= total) {
+						rv = -1;
+						break;
+					}
+
+					glens[I] = (int32_t) all_rows[at++];
+					grows[I] = malloc(((size_t) glens[I] + 1) * sizeof **grows);
+
+					if (grows[I] == NULL || at + (size_t) glens[I] > total) {
+						rv = -1;
+						break;
+					}
+
+					for (int32_t t = 0; t < glens[I]; t++) {
+						grows[I][t] = (int32_t) all_rows[at++];
+					}
+				}
+
+				rv = rv < 0 ? rv : layout_level(N, N->n, grows, glens);
+
+				for (int32_t I = 0; grows != NULL && I < N->n; I++) {
+					free(grows[I]);
+				}
+
+				free(grows);
+				free(glens);
+				free(all_rows);
+
+				if (rv < 0) {
+					goto fail;
+				}
+			}
+
+			else {
+				/* the next level stays distributed: owned aggregates first, then the ghosts' aggregates grouped by
+				 * owner (ascending rank), each group ascending by the owner's numbering - the order in which the
+				 * owner will send them */
+
+				int64_t* const keys = malloc(((size_t) L->n + 1) * sizeof *keys);
+				size_t n_keys = 0;
+
+				if (keys == NULL) {
+					free(cen);
+					free(ids);
+					goto fail;
+				}
+
+				for (int32_t b = 0; b < L->n; b++) {
+					if ((b < L->row_lo || b >= L->row_hi) && ids[2 * (size_t) b] >= 0) {
+						int const k = ghost_owner(L, b);
+
+						if (k >= 0) {
+							keys[n_keys++] = (int64_t) k << 32 | (int64_t) ids[2 * (size_t) b];
+						}
+					}
+				}
+
+				qsort(keys, n_keys, sizeof *keys, cmp_i64);
+
+				size_t uniq = 0;
+
+				for (size_t i = 0; i < n_keys; i++) {
+					if (i == 0 || keys[i] != keys[i - 1]) {
+						keys[uniq++] = keys[i];
+					}
+				}
+
+				n_keys = uniq;
+
+				for (int32_t b = 0; b < L->n; b++) {
+					if (b < L->row_lo || b >= L->row_hi) {
+						int const k = ghost_owner(L, b);
+
+						L->agg[b] = -1;
+
+						if (k >= 0 && ids[2 * (size_t) b] >= 0) {
+							int64_t const key = (int64_t) k << 32 | (int64_t) ids[2 * (size_t) b];
+							int64_t const* const hit = bsearch(&key, keys, n_keys, sizeof *keys, cmp_i64);
+
+							L->agg[b] = hit != NULL ? n_agg + (int32_t) (hit - keys) : -1;
+						}
+					}
+				}
+
+				free(ids);
+
+				L->n_coarse = n_agg + (int32_t) n_keys;
+
+				N->distributed = true;
+				N->n = L->n_coarse;
+				N->row_lo = 0;
+				N->row_hi = n_agg;
+				N->pos = calloc((size_t) N->n * 2 + 2, sizeof *N->pos);
+
+				if (N->pos == NULL) {
+					free(cen);
+					free(keys);
+					goto fail;
+				}
+
+				memcpy(N->pos, cen, (size_t) n_agg * 2 * sizeof *cen);
+				free(cen);
+
+				/* halo plan of the next level: what a neighbour ghosts of mine are the aggregates of the nodes it
+				 * ghosts of mine; what I ghost of its are the aggregates of my ghosts of its */
+
+				int32_t* const send = malloc(((size_t) L->n_send + 1) * sizeof *send);
+
+				if (send == NULL) {
+					free(keys);
+					goto fail;
+				}
+
+				int32_t n_send = 0;
+
+				N->n_nbr = 0;
+
+				for (int k = 0; k < L->n_nbr; k++) {
+					int32_t const begin = n_send;
+
+					for (int32_t i = L->send_ptr[k]; i < L->send_ptr[k + 1]; i++) {
+						int32_t const g = L->agg[L->send_idx[i]];
+
+						if (g >= 0) {
+							send[n_send++] = g;
+						}
+					}
+
+					qsort(send + begin, (size_t) (n_send - begin), sizeof *send, cmp_i32);
+
+					int32_t kept = begin;
+
+					for (int32_t i = begin; i < n_send; i++) {
+						if (i == begin || send[i] != send[i - 1]) {
+							send[kept++] = send[i];
+						}
+					}
+
+					n_send = kept;
+
+					int32_t recv_first = -1, recv_count = 0;
+
+					for (size_t i = 0; i < n_keys; i++) {
+						if ((int) (keys[i] >> 32) == k) {
+							recv_first = recv_first < 0 ? n_agg + (int32_t) i : recv_first;
+							recv_count++;
+						}
+					}
+
+					if (n_send == begin && recv_count == 0) {
+						continue; /* no longer neighbours on the next level */
+					}
+
+					int const j = N->n_nbr++;
+
+					N->nbr[j] = L->nbr[k];
+					N->recv_begin[j] = recv_first < 0 ? n_agg : recv_first;
+					N->recv_count[j] = recv_count;
+					N->send_ptr[j] = begin;
+					N->send_ptr[j + 1] = n_send;
+				}
+
+				N->n_send = n_send;
+				N->send_idx = send;
+
+				free(keys);
+
+				int32_t** const rows = calloc((size_t) n_agg + 1, sizeof *rows);
+				int32_t* const lens = calloc((size_t) n_agg + 1, sizeof *lens);
+
+				rv = rows != NULL && lens != NULL ? 0 : -1;
+				rv = rv < 0 ? rv : build_transfer(L);
+				rv = rv < 0 ? rv : coarse_rows(L, 0, n_agg, rows, lens);
+				rv = rv < 0 ? rv : layout_level(N, n_agg, rows, lens);
+
+				for (int32_t I = 0; rows != NULL && I < n_agg; I++) {
+					free(rows[I]);
+				}
+
+				free(rows);
+				free(lens);
+
+				if (rv < 0) {
+					goto fail;
+				}
+			}
 		}
 
-		if (build_transfer(L) < 0 || build_coarse_pattern(L, N) < 0 || color_level(L, N) < 0) {
-			goto fail;
-		}
+		n_glob = n_glob_next;
 
-		if (n_agg <= dense_limit) {
+		if (n_glob <= dense_limit) {
+			if (N->distributed) {
+				goto fail; /* cannot happen: replicated_nodes >= dense_limit */
+			}
+
 			break; /* N is the dense level */
 		}
 	}
@@ -783,6 +1269,25 @@ int bfmi_hier_upload(bfmi_hier_t* h, bfmg_pattern_t const* pat0, size_t* h2d_byt
 		d->dofs = L->dofs;
 		d->n_slices = L->n_slices;
 		d->n_slots = L->n_slots;
+		d->row_lo = L->row_lo;
+		d->row_hi = L->row_hi;
+		d->distributed = L->distributed;
+		d->gather_first = L->gather_first;
+		d->gather_count = L->gather_count;
+		d->n_nbr = L->n_nbr;
+		d->n_send = L->n_send;
+
+		for (int k = 0; k < L->n_nbr; k++) {
+			d->nbr[k] = L->nbr[k];
+			d->recv_begin[k] = L->recv_begin[k];
+			d->recv_count[k] = L->recv_count[k];
+			d->send_ptr[k] = L->send_ptr[k];
+			d->send_ptr[k + 1] = L->send_ptr[k + 1];
+		}
+
+		if (L->distributed && mirror((void**) &d->send_idx, L->send_idx, (size_t) L->n_send * sizeof(int32_t), &bytes) < 0) {
+			return -1;
+		}
 
 		if (l == 0) { /* the plan's pattern is on the device already */
 			d->slice_off = pat0->slice_off;
@@ -794,8 +1299,8 @@ int bfmi_hier_upload(bfmi_hier_t* h, bfmg_pattern_t const* pat0, size_t* h2d_byt
 		else if (
 			mirror((void**) &d->slice_off, L->slice_off, ((size_t) L->n_slices + 1) * sizeof(int32_t), &bytes) < 0 ||
 			mirror((void**) &d->scol, L->scol, (size_t) L->n_slots * sizeof(int32_t), &bytes) < 0 ||
-			mirror((void**) &d->diag_pos, L->diag_pos, (size_t) L->n * sizeof(int32_t), &bytes) < 0 ||
-			mirror((void**) &d->row_len, L->row_len, (size_t) L->n * sizeof(int32_t), &bytes) < 0
+			mirror((void**) &d->diag_pos, L->diag_pos, (size_t) L->row_hi * sizeof(int32_t), &bytes) < 0 ||
+			mirror((void**) &d->row_len, L->row_len, (size_t) L->row_hi * sizeof(int32_t), &bytes) < 0
 		) {
 			return -1;
 		}
@@ -803,7 +1308,6 @@ int bfmi_hier_upload(bfmi_hier_t* h, bfmg_pattern_t const* pat0, size_t* h2d_byt
 		if (l + 1 < h->n_levels) {
 			d->n_coarse = L->n_coarse;
 			d->n_p = L->n_p;
-			d->n_colors = L->n_colors;
 
 			if (
 				mirror((void**) &d->agg, L->agg, (size_t) L->n * sizeof(int32_t), &bytes) < 0 ||
@@ -812,8 +1316,7 @@ int bfmi_hier_upload(bfmi_hier_t* h, bfmg_pattern_t const* pat0, size_t* h2d_byt
 				mirror((void**) &d->p_col, L->p_col, (size_t) L->n_p * sizeof(int32_t), &bytes) < 0 ||
 				mirror((void**) &d->r_ptr, L->r_ptr, ((size_t) L->n_coarse + 1) * sizeof(int32_t), &bytes) < 0 ||
 				mirror((void**) &d->r_ent, L->r_ent, (size_t) L->n_p * sizeof(int32_t), &bytes) < 0 ||
-				mirror((void**) &d->r_node, L->r_node, (size_t) L->n_p * sizeof(int32_t), &bytes) < 0 ||
-				mirror((void**) &d->color, L->color, (size_t) L->n_coarse * sizeof(int32_t), &bytes) < 0
+				mirror((void**) &d->r_node, L->r_node, (size_t) L->n_p * sizeof(int32_t), &bytes) < 0
 			) {
 				return -1;
 			}
@@ -861,7 +1364,7 @@ static uint64_t hash_coords(double const* coords, size_t count) {
 }
 
 static uint64_t settings_hash(void) {
-	return (uint64_t) env_i64("BFM_MG_RATIO0", 12) * 1000003u + (uint64_t) env_i64("BFM_MG_RATIO", 6) * 10007u + (uint64_t) env_i64("BFM_MG_DENSE_NODES", 640);
+	return (uint64_t) env_i64("BFM_MG_RATIO0", 12) * 1000003u + (uint64_t) env_i64("BFM_MG_RATIO", 6) * 10007u + (uint64_t) env_i64("BFM_MG_DENSE_NODES", 1024) + (uint64_t) env_i64("BFM_MG_REPLICATED_NODES", 65536) * 7919u;
 }
 
 static bool same_key(bfmi_hier_t const* h, bfmi_plan_t const* plan, uint64_t coords_hash, int rank, int world) {
@@ -884,7 +1387,9 @@ void bfmi_hier_release(bfmi_hier_t* h) {
 	}
 }
 
-bfmi_hier_t* bfmi_hier_for_plan(bfmi_plan_t* plan, double const* coords, int32_t const* owner, int rank, int world) {
+bfmi_hier_t* bfmi_hier_for_plan(bfmi_plan_t* plan, double const* coords, bfmi_part_t const* part) {
+	int const rank = part != NULL ? part->rank : 0;
+	int const world = part != NULL ? part->world : 1;
 	uint64_t const coords_hash = hash_coords(coords, (size_t) plan->nb * 2);
 
 	if (cached != NULL && same_key(cached, plan, coords_hash, rank, world)) {
@@ -896,7 +1401,7 @@ bfmi_hier_t* bfmi_hier_for_plan(bfmi_plan_t* plan, double const* coords, int32_t
 		return NULL;
 	}
 
-	bfmi_hier_t* const h = bfmi_hier_build(plan, coords, owner);
+	bfmi_hier_t* const h = bfmi_hier_build(plan, coords, part);
 
 	if (h == NULL) {
 		cached_none = true;
@@ -934,7 +1439,7 @@ static bfmi_hier_t* hier_of(bfm_mesh_t* mesh, bfmi_plan_t** plan_out) {
 		return NULL;
 	}
 
-	bfmi_hier_t* const h = bfmi_hier_for_plan(plan, mesh->coords, NULL, 0, 1);
+	bfmi_hier_t* const h = bfmi_hier_for_plan(plan, mesh->coords, NULL);
 
 	*plan_out = plan;
 	return h;
@@ -951,7 +1456,6 @@ int bfmx_hier_info(bfm_mesh_t* mesh, bfmx_hier_info_t* info) {
 
 		for (int l = 0; l < h->n_levels; l++) {
 			info->n_nodes[l] = h->level[l].n;
-			info->n_colors[l] = l + 1 < h->n_levels ? h->level[l].n_colors : 0;
 			info->n_slots[l] = h->level[l].n_slots;
 		}
 	}
@@ -962,7 +1466,7 @@ int bfmx_hier_info(bfm_mesh_t* mesh, bfmx_hier_info_t* info) {
 	return plan != NULL ? 0 : -1;
 }
 
-int bfmx_hier_level(bfm_mesh_t* mesh, int level, int32_t* aggregate, float* geometry, int32_t* color, int32_t* pattern_rowptr, int32_t* pattern_col) {
+int bfmx_hier_level(bfm_mesh_t* mesh, int level, int32_t* aggregate, float* geometry, int32_t* pattern_rowptr, int32_t* pattern_col) {
 	bfmi_plan_t* plan = NULL;
 	bfmi_hier_t* const h = hier_of(mesh, &plan);
 	int rv = -1;
@@ -981,12 +1485,9 @@ int bfmx_hier_level(bfm_mesh_t* mesh, int level, int32_t* aggregate, float* geom
 				memcpy(geometry, L->geom, (size_t) L->n * 2 * sizeof *geometry);
 			}
 
-			if (color != NULL) {
-				memcpy(color, L->color, (size_t) L->n_coarse * sizeof *color);
-			}
 		}
 
-		else if (aggregate != NULL || geometry != NULL || color != NULL) {
+		else if (aggregate != NULL || geometry != NULL) {
 			rv = -1; /* the last level has nothing above it */
 		}
 

@@ -166,13 +166,23 @@ typedef struct bfmi_hier_level {
 	double* pos;          /* [n][2] reference points (level 0: the mesh coordinates, borrowed) */
 	bool owns_pattern;
 
-	int32_t const* owner; /* [n] rank of every node (NULL on one GPU); aggregates never straddle ranks */
-	bool owns_owner;
+	/* several GPUs: the nodes [row_lo, row_hi) are this rank's (it has their pattern rows and aggregates them);
+	 * a distributed level also holds ghosts, refreshed by a halo exchange before every product with its operator;
+	 * a replicated level is held in full by every rank.  One GPU: row_lo = 0, row_hi = n. */
+	int32_t row_lo, row_hi;
+	bool distributed;
+	int32_t n_nbr;
+	int32_t nbr[BFMG_DIST_MAX_RANKS];        /* neighbour ranks, ascending */
+	int32_t recv_begin[BFMG_DIST_MAX_RANKS]; /* per neighbour: its ghosts are the nodes [recv_begin, recv_begin + recv_count) */
+	int32_t recv_count[BFMG_DIST_MAX_RANKS];
+	int32_t send_ptr[BFMG_DIST_MAX_RANKS + 1];
+	int32_t n_send;
+	int32_t* send_idx;                       /* [n_send] owned nodes each neighbour ghosts, in the order it expects them */
+	int32_t gather_first, gather_count;      /* distributed level below a replicated one: global ids of this rank's aggregates */
 
 	/* towards the next level (absent on the last) */
 	int32_t n_coarse;     /* nodes of the next level = aggregates of this one */
 	int32_t n_p;          /* entries of the prolongator */
-	int32_t n_colors;
 	int32_t* agg;         /* [n] aggregate of every node, -1: left out of the coarse space */
 	float* geom;          /* [n][2] node position relative to its aggregate's reference point */
 	int32_t* p_ptr;       /* [n + 1] prolongator by fine node */
@@ -180,7 +190,6 @@ typedef struct bfmi_hier_level {
 	int32_t* r_ptr;       /* [n_coarse + 1] its transpose by coarse node */
 	int32_t* r_ent;       /* [n_p] entry index */
 	int32_t* r_node;      /* [n_p] fine node of that entry, ascending per coarse node */
-	int32_t* color;       /* [n_coarse] probing colour */
 
 	bfmg_mg_level_t dev;
 } bfmi_hier_level_t;
@@ -204,11 +213,11 @@ typedef struct bfmi_hier {
 } bfmi_hier_t;
 
 /* NULL when the mesh is too small or does not coarsen (not an error: the solver falls back) */
-BFMI_HIDDEN bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, int32_t const* owner);
+BFMI_HIDDEN bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, bfmi_part_t const* part);
 BFMI_HIDDEN int bfmi_hier_upload(bfmi_hier_t* hier, bfmg_pattern_t const* pat0, size_t* h2d_bytes);
 BFMI_HIDDEN void bfmi_hier_free(bfmi_hier_t* hier);
 /* cached (one entry, keyed by plan identity + coordinate hash + partition + settings), retained */
-BFMI_HIDDEN bfmi_hier_t* bfmi_hier_for_plan(bfmi_plan_t* plan, double const* coords, int32_t const* owner, int rank, int world);
+BFMI_HIDDEN bfmi_hier_t* bfmi_hier_for_plan(bfmi_plan_t* plan, double const* coords, bfmi_part_t const* part); /* collective on several GPUs */
 BFMI_HIDDEN void bfmi_hier_release(bfmi_hier_t* hier);
 BFMI_HIDDEN void bfmi_hier_forget(bfmi_plan_t const* plan);
 

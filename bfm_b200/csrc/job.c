@@ -882,7 +882,7 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 		if (env == NULL || atoi(env) != 0) {
 			double const t_h = now_ms();
 
-			job->hier = bfmi_hier_for_plan(job->plan, job->mesh->coords, NULL, 0, 1);
+			job->hier = bfmi_hier_for_plan(job->plan, job->mesh->coords, NULL);
 
 			if (job->hier != NULL) {
 				bool const fresh_hier = !job->hier->on_device;

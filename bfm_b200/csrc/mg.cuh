@@ -25,10 +25,8 @@
  * always holds and the smoother - hence the whole cycle - is symmetric positive definite.  The preconditioner
  * changes how fast CG converges, not what it converges to: the stopping test stays on the true CG residual.
  *
- * Set-up, once per solve: P from the diagonal scaling; A_{l+1} = P^T A_l P column by column through colour
- * probing (hier.c colours the coarse nodes so that the columns probed together never meet in a row): one
- * plain SpMV + one restriction per (colour, mode); its diagonal, scaling and row-sum bound; at the end the
- * dense inverse.  Everything is deterministic: fixed-order sums, no floating-point atomics (the row-sum bound
+ * Set-up, once per solve: P from the diagonal scaling; A_{l+1} = P^T A_l P by k_mg_rap (one warp per coarse
+ * node, one pass over A_l); its diagonal, scaling and row-sum bound; at the end the dense inverse.  Everything is deterministic: fixed-order sums, no floating-point atomics (the row-sum bound
  * is a maximum, taken with an integer atomicMax on the bit pattern of non-negative doubles).
  *
  * All kernels are HBM-bound streaming work.  Algorithmic bytes per mesh node and PCG iteration on the
@@ -46,6 +44,13 @@ enum MgMode { kMgPlain, kMgPre, kMgResid, kMgPost };
 
 constexpr int kMgGroup = 8;                       /* lanes that share one coarse node in k_mg_restrict */
 constexpr int kMgGroupsPerBlock = kBlock / kMgGroup;
+
+/* vector reads: through L1 (ld.global.nc) where a vector never changes during a launch; from L2 (ld.global.cg)
+ * where a kernel reads what another SM - or a peer GPU - may have written while it runs */
+template <bool CG>
+__device__ __forceinline__ double ldv(double const* p) {
+	return CG ? __ldcg(p) : __ldg(p);
+}
 
 struct MgDev {
 	double omega[BFMG_MG_MAX_LEVELS];             /* damping of every level's Jacobi smoother */
@@ -244,41 +249,10 @@ __global__ void k_mg_pscale(bfmg_mg_level_t L, double const* __restrict__ dsc_co
 	}
 }
 
-/* v = sum over the coarse nodes J of colour `color` of column (J, mode) of P */
-template <int NB, typename PT>
-__global__ void k_mg_probe_vector(bfmg_mg_level_t L, PT const* __restrict__ pval, int color, int mode, double* __restrict__ v) {
-	int const a = blockIdx.x * blockDim.x + threadIdx.x;
-
-	if (a >= L.n) {
-		return;
-	}
-
-	size_t const np = (size_t) L.n_p;
-	double out[3] = {0, 0, 0};
-
-	for (int e = L.p_ptr[a]; e < L.p_ptr[a + 1]; e++) {
-		if (L.color[L.p_col[e]] == color) {
-#pragma unroll
-			for (int k = 0; k < NB; k++) {
-				out[k] += (double) pval[(size_t) (k * 3 + mode) * np + e];
-			}
-		}
-	}
-
-#pragma unroll
-	for (int k = 0; k < NB; k++) {
-		v[(size_t) NB * a + k] = out[k];
-	}
-}
-
 /* out = P^T v: kMgGroup lanes per coarse node walk its entry list (ascending fine nodes), then a fixed
  * shuffle tree - deterministic.  n_out >= 3 * n_coarse: the padding up to it is zeroed (dense level). */
-template <int NB, typename PT>
-__global__ void __launch_bounds__(kBlock) k_mg_restrict(bfmg_mg_level_t L, PT const* __restrict__ pval, double const* __restrict__ v, double* __restrict__ out, int n_out, Scalars const* S, bool obey_done) {
-	if (obey_done && S->done) {
-		return;
-	}
-
+template <int NB, typename PT, bool CG>
+__device__ __forceinline__ void d_mg_restrict(bfmg_mg_level_t const& L, PT const* __restrict__ pval, double const* __restrict__ v, double* __restrict__ out, int n_out) {
 	int const sub = threadIdx.x & (kMgGroup - 1);
 	int const n_nodes_out = (n_out + 2) / 3;
 	size_t const np = (size_t) L.n_p;
@@ -298,7 +272,7 @@ __global__ void __launch_bounds__(kBlock) k_mg_restrict(bfmg_mg_level_t L, PT co
 
 #pragma unroll
 				for (int k = 0; k < NB; k++) {
-					double const x = v[(size_t) NB * a + k];
+					double const x = ldv<CG>(&v[(size_t) NB * a + k]);
 
 #pragma unroll
 					for (int m = 0; m < 3; m++) {
@@ -327,15 +301,19 @@ __global__ void __launch_bounds__(kBlock) k_mg_restrict(bfmg_mg_level_t L, PT co
 	}
 }
 
-/* z = w g + P mu (first visit of the coarse level), or z += P mu (later visits of a W-cycle) */
-template <int NB, typename PT, bool ADD>
-__global__ void __launch_bounds__(kBlock) k_mg_prolong(bfmg_mg_level_t L, int row0, int n_rows, PT const* __restrict__ pval, double const* __restrict__ mu, double const* __restrict__ g, double* __restrict__ z, double const* __restrict__ omega_p, Scalars const* S, bool obey_done) {
+template <int NB, typename PT>
+__global__ void __launch_bounds__(kBlock) k_mg_restrict(bfmg_mg_level_t L, PT const* __restrict__ pval, double const* __restrict__ v, double* __restrict__ out, int n_out, Scalars const* S, bool obey_done) {
 	if (obey_done && S->done) {
 		return;
 	}
 
+	d_mg_restrict<NB, PT, false>(L, pval, v, out, n_out);
+}
+
+/* z = w g + P mu (first visit of the coarse level), or z += P mu (later visits of a W-cycle) */
+template <int NB, typename PT, bool ADD, bool CG>
+__device__ __forceinline__ void d_mg_prolong(bfmg_mg_level_t const& L, int row0, int n_rows, PT const* __restrict__ pval, double const* __restrict__ mu, double const* __restrict__ g, double* __restrict__ z, double w) {
 	size_t const np = (size_t) L.n_p;
-	double const w = *omega_p;
 
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
 		int const a = row0 + i;
@@ -346,7 +324,7 @@ __global__ void __launch_bounds__(kBlock) k_mg_prolong(bfmg_mg_level_t L, int ro
 
 #pragma unroll
 			for (int m = 0; m < 3; m++) {
-				double const x = __ldg(&mu[3 * (size_t) J + m]);
+				double const x = ldv<CG>(&mu[3 * (size_t) J + m]);
 
 #pragma unroll
 				for (int k = 0; k < NB; k++) {
@@ -358,40 +336,128 @@ __global__ void __launch_bounds__(kBlock) k_mg_prolong(bfmg_mg_level_t L, int ro
 #pragma unroll
 		for (int k = 0; k < NB; k++) {
 			size_t const at = (size_t) NB * a + k;
-			z[at] = ADD ? z[at] + acc[k] : fma(w, g[at], acc[k]);
+			z[at] = ADD ? ldv<CG>(&z[at]) + acc[k] : fma(w, ldv<CG>(&g[at]), acc[k]);
 		}
 	}
 }
 
-/* the restricted probe g holds, for every coarse node I, column (J, mode) of P^T A P where J is the coarse node of
- * colour `color` in row I of the next level's pattern (at most one by the colouring).  DENSE: into the row-major
- * n_dense x n_dense matrix E instead of the SELL planes. */
-template <bool DENSE>
-__global__ void k_mg_scatter(bfmg_mg_level_t N, int32_t const* __restrict__ color_of, int color, int mode, double const* __restrict__ g, double* __restrict__ val, int n_dense) {
-	int const I = blockIdx.x * blockDim.x + threadIdx.x;
-
-	if (I >= N.n) {
+template <int NB, typename PT, bool ADD>
+__global__ void __launch_bounds__(kBlock) k_mg_prolong(bfmg_mg_level_t L, int row0, int n_rows, PT const* __restrict__ pval, double const* __restrict__ mu, double const* __restrict__ g, double* __restrict__ z, double const* __restrict__ omega_p, Scalars const* S, bool obey_done) {
+	if (obey_done && S->done) {
 		return;
 	}
 
-	int const base = N.slice_off[I / kWarp] + I % kWarp;
+	d_mg_prolong<NB, PT, ADD, false>(L, row0, n_rows, pval, mu, g, z, *omega_p);
+}
 
-	for (int t = 0; t < N.row_len[I]; t++) {
-		int const slot = base + t * kWarp;
-		int const J = N.scol[slot];
+/* Galerkin operator of the next level, A_c = P^T A P, directly: one warp per coarse node I, lane = slot of row I in
+ * the next level's pattern (hier.c computed that pattern symbolically as the very same product).  The warp walks
+ * the fine nodes a of column I of P in ascending order and, for each, the blocks (a, b) of A's row in slot order;
+ * the lane whose coarse column J owns b adds P_a^T A_ab P_b.  Every entry is accumulated by one lane in a fixed
+ * order: deterministic, no atomics.  FINE: the operator of the fine level (level 0: the two planes of 2x2 blocks
+ * (a00,a01) / (a10,a11); above: nine planes).  DENSE: the result goes into the row-major n_dense x n_dense matrix. */
+template <int NB, typename PT, bool DENSE>
+__global__ void __launch_bounds__(kBlock) k_mg_rap(bfmg_mg_level_t L, bfmg_mg_level_t N, double const* __restrict__ fine, PT const* __restrict__ pval, double* __restrict__ val, int n_dense) {
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+	int const n_warps = gridDim.x * blockDim.x / kWarp;
+	size_t const np = (size_t) L.n_p;
+	size_t const ns = (size_t) L.n_slots;
 
-		if (color_of[J] != color) {
-			continue;
-		}
+	for (int I = warp; I < N.n; I += n_warps) {
+		int const base = N.slice_off[I / kWarp] + I % kWarp;
+		int const len = N.row_len[I];
+
+		for (int t0 = 0; t0 < len; t0 += kWarp) { /* rows longer than a warp: one pass per 32 columns */
+			int const my_slot = t0 + lane < len ? base + (t0 + lane) * kWarp : -1;
+			int const my_col = my_slot >= 0 ? N.scol[my_slot] : -1;
+
+			double c[3][3] = {};
+
+			for (int at = L.r_ptr[I]; at < L.r_ptr[I + 1]; at++) {
+				int const a = L.r_node[at];
+				int const ea = L.r_ent[at];
+				int const abase = L.slice_off[a / kWarp] + a % kWarp;
+				int const alen = L.row_len[a];
+
+				double pa[NB][3];
 
 #pragma unroll
-		for (int k = 0; k < 3; k++) {
-			if (DENSE) {
-				val[(size_t) (3 * I + k) * n_dense + 3 * J + mode] = g[3 * (size_t) I + k];
+				for (int k = 0; k < NB; k++) {
+#pragma unroll
+					for (int m = 0; m < 3; m++) {
+						pa[k][m] = (double) pval[(size_t) (k * 3 + m) * np + ea];
+					}
+				}
+
+				for (int u = 0; u < alen; u++) {
+					int const slot = abase + u * kWarp;
+					int const b = L.scol[slot];
+					int const eb = L.p_ptr[b];
+
+					if (eb == L.p_ptr[b + 1] || L.p_col[eb] != my_col) {
+						continue; /* b is outside the coarse space, or belongs to another lane's column */
+					}
+
+					double A[NB][NB];
+
+					if (NB == 2) {
+						double2 const top = ((double2 const*) fine)[slot];
+						double2 const bot = ((double2 const*) fine)[ns + slot];
+
+						A[0][0] = top.x, A[0][1] = top.y;
+						A[1][0] = bot.x, A[1][1] = bot.y;
+					}
+
+					else {
+#pragma unroll
+						for (int k = 0; k < NB; k++) {
+#pragma unroll
+							for (int j = 0; j < NB; j++) {
+								A[k][j] = fine[(size_t) (3 * k + j) * ns + slot];
+							}
+						}
+					}
+
+#pragma unroll
+					for (int m = 0; m < 3; m++) {
+						double t[NB];
+
+#pragma unroll
+						for (int k = 0; k < NB; k++) {
+							t[k] = 0;
+
+#pragma unroll
+							for (int j = 0; j < NB; j++) {
+								t[k] = fma(A[k][j], (double) pval[(size_t) (j * 3 + m) * np + eb], t[k]);
+							}
+						}
+
+#pragma unroll
+						for (int i = 0; i < 3; i++) {
+#pragma unroll
+							for (int k = 0; k < NB; k++) {
+								c[i][m] = fma(pa[k][i], t[k], c[i][m]);
+							}
+						}
+					}
+				}
 			}
 
-			else {
-				val[(size_t) (3 * k + mode) * N.n_slots + slot] = g[3 * (size_t) I + k];
+			if (my_slot >= 0) {
+#pragma unroll
+				for (int i = 0; i < 3; i++) {
+#pragma unroll
+					for (int m = 0; m < 3; m++) {
+						if (DENSE) {
+							val[(size_t) (3 * I + i) * n_dense + 3 * my_col + m] = c[i][m];
+						}
+
+						else {
+							val[(size_t) (3 * i + m) * N.n_slots + my_slot] = c[i][m];
+						}
+					}
+				}
 			}
 		}
 	}
@@ -478,16 +544,11 @@ __global__ void __launch_bounds__(kBlock) k_blk_scale(bfmg_mg_level_t N, double*
 }
 
 /* warp = slice, lane = node row; modes as k_spmv_mg (no dot product: the coarse levels feed no CG scalar) */
-template <MgMode MODE>
-__global__ void __launch_bounds__(kBlock) k_blk_spmv(bfmg_mg_level_t N, double const* __restrict__ val, double const* __restrict__ v, double const* __restrict__ g, double* __restrict__ out, double const* __restrict__ omega_p, Scalars const* S, bool obey_done) {
-	if (obey_done && S->done) {
-		return;
-	}
-
+template <MgMode MODE, bool CG>
+__device__ __forceinline__ void d_blk_spmv(bfmg_mg_level_t const& N, double const* __restrict__ val, double const* __restrict__ v, double const* __restrict__ g, double* __restrict__ out, double w) {
 	int const lane = threadIdx.x & (kWarp - 1);
 	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
 	int const n_warps = gridDim.x * blockDim.x / kWarp;
-	double const w = (MODE == kMgPre || MODE == kMgPost) ? *omega_p : 1.0;
 	size_t const ns = (size_t) N.n_slots;
 
 	for (int slice = warp; slice < N.n_slices; slice += n_warps) {
@@ -499,9 +560,9 @@ __global__ void __launch_bounds__(kBlock) k_blk_spmv(bfmg_mg_level_t N, double c
 #pragma unroll 2
 		for (int slot = __ldg(&N.slice_off[slice]) + lane; slot < end; slot += kWarp) {
 			int const col = ld_stream(&N.scol[slot]);
-			double const x0 = __ldg(&v[3 * (size_t) col + 0]);
-			double const x1 = __ldg(&v[3 * (size_t) col + 1]);
-			double const x2 = __ldg(&v[3 * (size_t) col + 2]);
+			double const x0 = ldv<CG>(&v[3 * (size_t) col + 0]);
+			double const x1 = ldv<CG>(&v[3 * (size_t) col + 1]);
+			double const x2 = ldv<CG>(&v[3 * (size_t) col + 2]);
 
 			y0 = fma(ld_stream(&val[0 * ns + slot]), x0, fma(ld_stream(&val[1 * ns + slot]), x1, fma(ld_stream(&val[2 * ns + slot]), x2, y0)));
 			y1 = fma(ld_stream(&val[3 * ns + slot]), x0, fma(ld_stream(&val[4 * ns + slot]), x1, fma(ld_stream(&val[5 * ns + slot]), x2, y1)));
@@ -521,11 +582,11 @@ __global__ void __launch_bounds__(kBlock) k_blk_spmv(bfmg_mg_level_t N, double c
 				}
 
 				else if (MODE == kMgPost) {
-					o = fma(w, g[at + k] - y[k], __ldg(&v[at + k]));
+					o = fma(w, ldv<CG>(&g[at + k]) - y[k], ldv<CG>(&v[at + k]));
 				}
 
 				else {
-					o = fma(-w, y[k], g[at + k]);
+					o = fma(-w, y[k], ldv<CG>(&g[at + k]));
 				}
 
 				out[at + k] = o;
@@ -534,51 +595,69 @@ __global__ void __launch_bounds__(kBlock) k_blk_spmv(bfmg_mg_level_t N, double c
 	}
 }
 
+template <MgMode MODE>
+__global__ void __launch_bounds__(kBlock) k_blk_spmv(bfmg_mg_level_t N, double const* __restrict__ val, double const* __restrict__ v, double const* __restrict__ g, double* __restrict__ out, double const* __restrict__ omega_p, Scalars const* S, bool obey_done) {
+	if (obey_done && S->done) {
+		return;
+	}
+
+	d_blk_spmv<MODE, false>(N, val, v, g, out, (MODE == kMgPre || MODE == kMgPost) ? *omega_p : 1.0);
+}
+
 /* mu = E^-1 g on the dense last level (the explicit inverse; kCoarseRows rows per CTA, four warps per row as in
  * k_coarse_apply) */
+__device__ __forceinline__ void d_dense_apply(int nc, double const* __restrict__ Einv, double const* __restrict__ g, double* __restrict__ mu) {
+	__shared__ double quarter_sum[kWarpsPerBlock];
+
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = threadIdx.x / kWarp;
+	int const span = ((nc + 3) / 4 + kWarp - 1) / kWarp * kWarp;
+	int const j_end = min(nc, (warp % 4 + 1) * span);
+	int const n_row_blocks = (nc + kCoarseRows - 1) / kCoarseRows;
+
+	for (int rb = blockIdx.x; rb < n_row_blocks; rb += gridDim.x) {
+		int const row = rb * kCoarseRows + warp / 4;
+		double t = 0;
+
+		if (row < nc) {
+			double const* const e = Einv + (size_t) row * nc;
+			double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+			int j = (warp % 4) * span + lane;
+
+			for (; j + 3 * kWarp < j_end; j += 4 * kWarp) {
+				t0 = fma(ld_stream(&e[j]), __ldcg(&g[j]), t0);
+				t1 = fma(ld_stream(&e[j + kWarp]), __ldcg(&g[j + kWarp]), t1);
+				t2 = fma(ld_stream(&e[j + 2 * kWarp]), __ldcg(&g[j + 2 * kWarp]), t2);
+				t3 = fma(ld_stream(&e[j + 3 * kWarp]), __ldcg(&g[j + 3 * kWarp]), t3);
+			}
+
+			for (; j < j_end; j += kWarp) {
+				t0 = fma(ld_stream(&e[j]), __ldcg(&g[j]), t0);
+			}
+
+			t = warp_sum((t0 + t1) + (t2 + t3));
+		}
+
+		__syncthreads(); /* the previous row block's sums have been consumed */
+
+		if (lane == 0) {
+			quarter_sum[warp] = t;
+		}
+
+		__syncthreads();
+
+		if (lane == 0 && warp % 4 == 0 && row < nc) {
+			mu[row] = (quarter_sum[warp] + quarter_sum[warp + 1]) + (quarter_sum[warp + 2] + quarter_sum[warp + 3]);
+		}
+	}
+}
+
 __global__ void __launch_bounds__(kBlock) k_dense_apply(int nc, double const* __restrict__ Einv, double const* __restrict__ g, double* __restrict__ mu, Scalars const* S, bool obey_done) {
 	if (obey_done && S->done) {
 		return;
 	}
 
-	__shared__ double quarter_sum[kWarpsPerBlock];
-
-	int const lane = threadIdx.x & (kWarp - 1);
-	int const warp = threadIdx.x / kWarp;
-	int const row = blockIdx.x * kCoarseRows + warp / 4;
-	int const span = ((nc + 3) / 4 + kWarp - 1) / kWarp * kWarp;
-	int const j_end = min(nc, (warp % 4 + 1) * span);
-
-	double t = 0;
-
-	if (row < nc) {
-		double const* const e = Einv + (size_t) row * nc;
-		double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-		int j = (warp % 4) * span + lane;
-
-		for (; j + 3 * kWarp < j_end; j += 4 * kWarp) {
-			t0 = fma(ld_stream(&e[j]), __ldg(&g[j]), t0);
-			t1 = fma(ld_stream(&e[j + kWarp]), __ldg(&g[j + kWarp]), t1);
-			t2 = fma(ld_stream(&e[j + 2 * kWarp]), __ldg(&g[j + 2 * kWarp]), t2);
-			t3 = fma(ld_stream(&e[j + 3 * kWarp]), __ldg(&g[j + 3 * kWarp]), t3);
-		}
-
-		for (; j < j_end; j += kWarp) {
-			t0 = fma(ld_stream(&e[j]), __ldg(&g[j]), t0);
-		}
-
-		t = warp_sum((t0 + t1) + (t2 + t3));
-	}
-
-	if (lane == 0) {
-		quarter_sum[warp] = t;
-	}
-
-	__syncthreads();
-
-	if (lane == 0 && warp % 4 == 0 && row < nc) {
-		mu[row] = (quarter_sum[warp] + quarter_sum[warp + 1]) + (quarter_sum[warp + 2] + quarter_sum[warp + 3]);
-	}
+	d_dense_apply(nc, Einv, g, mu);
 }
 
 /* identity on the padding rows of the dense operator (3 n .. nc) */
@@ -619,6 +698,7 @@ struct MgRun {
 	int32_t* bad = nullptr;
 
 	double omega_factor = 1.6;
+	double lambda0 = 4;     /* Gershgorin bound of the scaled level-0 operator (after setup) */
 
 	static size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
 
@@ -766,8 +846,6 @@ struct MgRun {
 			bool const dense = l + 1 == n_levels - 1;
 			int const node_blocks = (w.L.n + kBlock - 1) / kBlock;
 			int const coarse_blocks = (nx.L.n + kBlock - 1) / kBlock;
-			double* const probe = l == 0 ? (double*) tmp_v : w.va;
-			double* const image = l == 0 ? (double*) tmp_q : w.vb;
 			double* const target = dense ? E : nx.val;
 			size_t const target_bytes = dense ? (size_t) nc * nc * sizeof(double) : (size_t) nx.L.n_slots * 9 * sizeof(double);
 
@@ -779,28 +857,22 @@ struct MgRun {
 				return -1;
 			}
 
-			for (int c = 0; c < w.L.n_colors; c++) {
-				for (int m = 0; m < 3; m++) {
-					rc = l == 0
-						? BFMG_LAUNCH((k_mg_probe_vector<2, float>), node_blocks, kBlock, 0, w.L, (float const*) w.pval, c, m, probe)
-						: BFMG_LAUNCH((k_mg_probe_vector<3, double>), node_blocks, kBlock, 0, w.L, (double const*) w.pval, c, m, probe);
+			int const rap_grid = bfmg_grid(((int64_t) nx.L.n + kWarpsPerBlock - 1) / kWarpsPerBlock, 8);
 
-					rc = rc < 0 ? rc : (l == 0
-						? BFMG_LAUNCH(k_spmv<kPlain>, spmv_grid, kBlock, 0, *pat, stop, sbot, (double2 const*) probe, (double2*) image, (double2 const*) nullptr, (double*) nullptr, S)
-						: BFMG_LAUNCH(k_blk_spmv<kMgPlain>, w.grid_rows, kBlock, 0, w.L, w.val, probe, (double const*) nullptr, image, (double const*) nullptr, S, false));
+			if (dense) {
+				rc = l == 0
+					? BFMG_LAUNCH((k_mg_rap<2, float, true>), rap_grid, kBlock, 0, w.L, nx.L, (double const*) stop, (float const*) w.pval, target, nc)
+					: BFMG_LAUNCH((k_mg_rap<3, double, true>), rap_grid, kBlock, 0, w.L, nx.L, (double const*) w.val, (double const*) w.pval, target, nc);
+			}
 
-					if (rc < 0 || !restrict_to(l, image, next_g(l), next_len(l), S, false)) {
-						return -1;
-					}
+			else {
+				rc = l == 0
+					? BFMG_LAUNCH((k_mg_rap<2, float, false>), rap_grid, kBlock, 0, w.L, nx.L, (double const*) stop, (float const*) w.pval, target, nc)
+					: BFMG_LAUNCH((k_mg_rap<3, double, false>), rap_grid, kBlock, 0, w.L, nx.L, (double const*) w.val, (double const*) w.pval, target, nc);
+			}
 
-					rc = dense
-						? BFMG_LAUNCH(k_mg_scatter<true>, coarse_blocks, kBlock, 0, nx.L, w.L.color, c, m, next_g(l), E, nc)
-						: BFMG_LAUNCH(k_mg_scatter<false>, coarse_blocks, kBlock, 0, nx.L, w.L.color, c, m, next_g(l), nx.val, nc);
-
-					if (rc < 0) {
-						return -1;
-					}
-				}
+			if (rc < 0) {
+				return -1;
 			}
 
 			if (dense) {
@@ -837,14 +909,22 @@ struct MgRun {
 		CW.bad = bad;
 
 		int32_t flags[2] = {0, 0};
+		unsigned long long bound0 = 0;
 
 		if (
 			coarse_invert(CW, S, false, 0, nc / kGjBlock) < 0 ||
 			BFMG_CHECK(cudaMemcpyAsync(&flags[0], bad, sizeof(int32_t), cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
 			BFMG_CHECK(cudaMemcpyAsync(&flags[1], &D->bad, sizeof(int32_t), cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
+			BFMG_CHECK(cudaMemcpyAsync(&bound0, &D->gersh[0], sizeof bound0, cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
 			BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0
 		) {
 			return -1;
+		}
+
+		memcpy(&lambda0, &bound0, sizeof lambda0);
+
+		if (!(lambda0 >= 1) || !(lambda0 < 64)) {
+			lambda0 = 4;
 		}
 
 		*usable = flags[0] == 0 && flags[1] == 0;

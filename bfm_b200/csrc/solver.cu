@@ -57,6 +57,8 @@ struct Scalars {
 	int32_t world;  /* ranks sharing the solve; > 1: reductions finish in k_fold */
 	int32_t coarse; /* 1: two-level preconditioner - beta and rho come from k_coarse_apply, not from r.r */
 	double rr;      /* r.r of the current residual (the convergence measure; equals rho without a coarse level) */
+	double xx;      /* ||x^||^2 of the solution accumulated since the last refinement (one GPU) */
+	double floor2;  /* > 0: refinement armed - done = 4 once r.r <= floor2 * xx (the residual has reached FP64's floor) */
 	double part;                       /* this rank's share of the reduction in flight */
 	double gath[BFMG_DIST_MAX_RANKS];  /* every rank's share, in rank order */
 
@@ -117,6 +119,10 @@ __device__ __forceinline__ void fold(Scalars* S, double total) {
 
 		else if (S->iter >= S->max_iter) {
 			S->done = 3;
+		}
+
+		else if (S->floor2 > 0 && total <= S->floor2 * S->xx) {
+			S->done = 4; /* the recursion has reached what FP64 can resolve against ||x^||: refine (bfmg_pcg) */
 		}
 	}
 
@@ -341,6 +347,83 @@ __device__ __forceinline__ bool grid_sum(double v, double* __restrict__ partials
 	return true;
 }
 
+/* the same for two sums at once (partials holds 2 * gridDim.x doubles) */
+__device__ __forceinline__ bool grid_sum2(double v0, double v1, double* __restrict__ partials, uint32_t* ticket, double* total0, double* total1) {
+	__shared__ double warp_part2[2][kWarpsPerBlock];
+	__shared__ bool last2;
+
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = threadIdx.x / kWarp;
+
+	v0 = warp_sum(v0);
+	v1 = warp_sum(v1);
+
+	if (lane == 0) {
+		warp_part2[0][warp] = v0;
+		warp_part2[1][warp] = v1;
+	}
+
+	__syncthreads();
+
+	if (threadIdx.x == 0) {
+		double s0 = 0, s1 = 0;
+
+#pragma unroll
+		for (int w = 0; w < kWarpsPerBlock; w++) {
+			s0 += warp_part2[0][w];
+			s1 += warp_part2[1][w];
+		}
+
+		partials[2 * blockIdx.x + 0] = s0;
+		partials[2 * blockIdx.x + 1] = s1;
+		__threadfence();
+		last2 = atomicAdd(ticket, 1u) == gridDim.x - 1;
+	}
+
+	__syncthreads();
+
+	if (!last2) {
+		return false;
+	}
+
+	__threadfence();
+
+	double s0 = 0, s1 = 0;
+
+	for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) {
+		s0 += __ldcg(&partials[2 * i + 0]);
+		s1 += __ldcg(&partials[2 * i + 1]);
+	}
+
+	s0 = warp_sum(s0);
+	s1 = warp_sum(s1);
+
+	__syncthreads();
+
+	if (lane == 0) {
+		warp_part2[0][warp] = s0;
+		warp_part2[1][warp] = s1;
+	}
+
+	__syncthreads();
+
+	if (threadIdx.x == 0) {
+		double t0 = 0, t1 = 0;
+
+#pragma unroll
+		for (int w = 0; w < kWarpsPerBlock; w++) {
+			t0 += warp_part2[0][w];
+			t1 += warp_part2[1][w];
+		}
+
+		*total0 = t0;
+		*total1 = t1;
+		*ticket = 0;
+	}
+
+	return true;
+}
+
 /* ---- setup kernels --------------------------------------------------------------------------- */
 
 /* dscale = 1 / sqrt(|a_ii|) (1 where the diagonal is 0), b^ = dscale * b */
@@ -498,7 +581,7 @@ __global__ void __launch_bounds__(kBlock) k_update_xr(int n2, double2 const* __r
 	}
 
 	double const alpha = S->alpha;
-	double acc = 0;
+	double acc = 0, acc2 = 0;
 
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
 		double2 const pv = p[i];
@@ -515,11 +598,13 @@ __global__ void __launch_bounds__(kBlock) k_update_xr(int n2, double2 const* __r
 		r[i] = rv;
 
 		acc = fma(rv.x, rv.x, fma(rv.y, rv.y, acc));
+		acc2 = fma(xv.x, xv.x, fma(xv.y, xv.y, acc2));
 	}
 
-	double total;
+	double total, total2;
 
-	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
+	if (grid_sum2(acc, acc2, partials, &S->ticket, &total, &total2) && threadIdx.x == 0) {
+		S->xx = total2; /* this rank's rows: the floor test is only armed on one GPU */
 		reduced<kFoldRr>(S, total);
 	}
 }
@@ -543,29 +628,121 @@ __global__ void __launch_bounds__(kBlock) k_update_p(int n2, double2 const* __re
 	}
 }
 
-/* restart from the true residual: r = p = resid (already in q), rho = ||resid||^2 (in S->sum) */
-__global__ void k_restart(int n2, double2 const* __restrict__ resid, double2* __restrict__ r, double2* __restrict__ p, Scalars* S) {
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
-		double2 const v = resid[i];
-		r[i] = v;
-		p[i] = v;
-	}
-
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		S->rho = S->sum;
-		S->rr = S->sum;
-		S->done = S->iter >= S->max_iter ? 3 : 0;
-	}
-}
-
-/* x = dscale * x^ */
-__global__ void k_unscale(int n2, double2 const* __restrict__ dscale, double2 const* __restrict__ xhat, double2* __restrict__ x) {
+/* x (+)= dscale * x^ on the owned rows: the solution in the reference's variables.  ZERO: x^ = 0 afterwards (a new
+ * accumulator for the correction of a refinement step) */
+template <bool ADD, bool ZERO>
+__global__ void k_unscale(int n2, double2 const* __restrict__ dscale, double2* __restrict__ xhat, double2* __restrict__ x) {
 	int const i = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (i < n2) {
 		double2 const s = dscale[i];
 		double2 const v = xhat[i];
-		x[i] = make_double2(s.x * v.x, s.y * v.y);
+		double2 out = make_double2(s.x * v.x, s.y * v.y);
+
+		if (ADD) {
+			double2 const old = x[i];
+			out.x += old.x;
+			out.y += old.y;
+		}
+
+		x[i] = out;
+
+		if (ZERO) {
+			xhat[i] = make_double2(0, 0);
+		}
+	}
+}
+
+/* ---- the residual of the ORIGINAL system in double-double arithmetic ------------------------------------------
+ *
+ * r^ = D^-1/2 (b - A x) with the unscaled matrix the assembly produced (bit-identical to the reference's) and the
+ * solution in the reference's variables, every row accumulated as an unevaluated sum of two doubles (TwoProduct by
+ * FMA, TwoSum): the rows of a stiffness matrix cancel to ~1e-9 of their terms on these plates, so a plain FP64
+ * evaluation of A x is white noise of size eps |A| |x| - the "floor" of the recomputed residual - and CG cannot
+ * see below it.  Evaluated this way the residual is good to ~eps^2 |A| |x|, and restarting CG on it for a
+ * correction (bfmg_pcg) brings the displacements within ~1e-13 of an exact solve of the reference's system.
+ * __dmul_rn / __dadd_rn keep nvcc from contracting the error-free transformations into FMAs.
+ *   REFINE: r receives r^, last CTA: rho = rr = ||r^||^2, new accumulator, done = 0
+ *   else:   verification: S->sum = ||r^||^2, S->sum2 = ||D^1/2 x||^2 (the scaled solution norm) */
+__device__ __forceinline__ void dd_sub_prod(double a, double x, double& hi, double& lo) {
+	double const p = __dmul_rn(a, x);
+	double const e = fma(a, x, -p);          /* a x = p + e exactly */
+	double const t = __dadd_rn(hi, -p);
+	double const bb = __dadd_rn(t, -hi);
+	double const err = __dadd_rn(__dadd_rn(hi, -__dadd_rn(t, -bb)), __dadd_rn(-p, -bb)); /* hi - p = t + err exactly */
+
+	hi = t;
+	lo = __dadd_rn(lo, __dadd_rn(err, -e));
+}
+
+template <bool REFINE>
+__global__ void __launch_bounds__(kBlock) k_residual_dd(
+	const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ vtop, double2 const* __restrict__ vbot,
+	double2 const* __restrict__ b, double2 const* __restrict__ x, double2 const* __restrict__ dscale, double2* __restrict__ r, double* __restrict__ partials, Scalars* S, int arm_again
+) {
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+	int const n_warps = gridDim.x * blockDim.x / kWarp;
+
+	double acc = 0, acc2 = 0;
+
+	for (int slice = P.row_lo / kWarp + warp; slice < (P.row_hi + kWarp - 1) / kWarp; slice += n_warps) {
+		int const row = slice * kWarp + lane;
+		int const end = __ldg(&P.slice_off[slice + 1]);
+		bool const mine = row >= P.row_lo && row < P.row_hi;
+
+		double2 const bb = mine ? b[row] : make_double2(0, 0);
+		double h0 = bb.x, l0 = 0, h1 = bb.y, l1 = 0;
+
+		for (int slot = __ldg(&P.slice_off[slice]) + lane; slot < end; slot += kWarp) {
+			int const col = ld_stream(&P.scol[slot]);
+			double2 const t = ld_stream(&vtop[slot]);
+			double2 const u = ld_stream(&vbot[slot]);
+			double2 const xv = __ldg(&x[col]);
+
+			dd_sub_prod(t.x, xv.x, h0, l0);
+			dd_sub_prod(t.y, xv.y, h0, l0);
+			dd_sub_prod(u.x, xv.x, h1, l1);
+			dd_sub_prod(u.y, xv.y, h1, l1);
+		}
+
+		if (mine) {
+			double2 const sc = dscale[row];
+			double const r0 = (h0 + l0) * sc.x;
+			double const r1 = (h1 + l1) * sc.y;
+
+			if (REFINE) {
+				r[row] = make_double2(r0, r1);
+			}
+
+			else {
+				double2 const xr = __ldg(&x[row]);
+				acc2 = fma(xr.x / sc.x, xr.x / sc.x, fma(xr.y / sc.y, xr.y / sc.y, acc2));
+			}
+
+			acc = fma(r0, r0, fma(r1, r1, acc));
+		}
+	}
+
+	double total, total2;
+
+	if (grid_sum2(acc, acc2, partials, &S->ticket, &total, &total2) && threadIdx.x == 0) {
+		if (REFINE) {
+			S->rho = total;
+			S->rr = total;
+			S->xx = 0;
+			S->floor2 = arm_again ? S->floor2 : 0;
+			S->done = !(total == total) ? 2 : (total <= S->tol2 * S->bnorm2 ? 1 : (S->iter >= S->max_iter ? 3 : 0));
+		}
+
+		else if (S->world > 1) {
+			reduced<kFoldResidual>(S, total); /* ||x|| follows from k_norm2 on several GPUs */
+		}
+
+		else {
+			S->sum = total;
+			S->sum2 = total2;
+		}
 	}
 }
 
@@ -676,7 +853,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	size_t const mat_bytes = (size_t) pat->n_slots * 2 * sizeof(double2);
 	size_t const send_bytes = shared ? ((size_t) halo->n_send + 1) * sizeof(double2) : 0;
 	size_t const coarse_bytes = coarse != nullptr ? vec_bytes + (((size_t) nc + 8) * (3 + world) + (size_t) nc * nc + kGjBlock * kGjBlock + 64) * sizeof(double) : 0;
-	size_t const total = mat_bytes + 7 * vec_bytes + send_bytes + (size_t) max_grid * sizeof(double) + sizeof(Scalars) + 512 + coarse_bytes;
+	size_t const total = mat_bytes + 7 * vec_bytes + send_bytes + 2 * (size_t) max_grid * sizeof(double) + sizeof(Scalars) + 512 + coarse_bytes;
 
 	CoarseWork CW = {};
 
@@ -699,7 +876,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		q = (double2*) at, at += vec_bytes;
 		zmg = (double2*) at, at += vec_bytes;
 		sendbuf = (double2*) at, at += send_bytes;
-		partials = (double*) at, at += (size_t) max_grid * sizeof(double);
+		partials = (double*) at, at += 2 * (size_t) max_grid * sizeof(double); /* k_update_xr and k_residual_dd reduce two sums */
 		at = (char*) (((uintptr_t) at + 127) & ~(uintptr_t) 127);
 		S = (Scalars*) at, at += sizeof(Scalars);
 		at = (char*) (((uintptr_t) at + 127) & ~(uintptr_t) 127);
@@ -958,12 +1135,48 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		/* iterations per chunk: a chunk is replayed as one CUDA graph and the host learns about convergence one
 		 * chunk late, so launches after convergence are wasted - 64 cheap iterations, or 8 multigrid ones */
 		int const chunk = opts->chunk > 0 ? opts->chunk : (use_mg ? 8 : 64);
-		int restarts = 0;
+		int refinements = 0;
+		bool have_base = false; /* d_x holds the solution accumulated before the last refinement */
 
 		{
 			char const* const env = getenv("BFM_CG_GRAPH");
 			graphable = (!shared || p2p) && (env == nullptr || atoi(env) != 0);
 		}
+
+		/* Refinement on the original system (one GPU, multilevel preconditioner).  The scaled matrix A^ is rounded,
+		 * and any FP64 evaluation of A^ x^ is white noise of ~eps |A^| |x^| - on these plates 1e-7 .. 1e-6 of
+		 * ||b^||, because ||x^|| / ||b^|| ~ cond(A).  CG's recursion happily goes below that, but the iterate stops
+		 * improving there: measured, the displacements stay 3e-9 (0.5 M DOF) away from an exact solve of the
+		 * reference's system.  So once r.r reaches that floor (done = 4, fold<kFoldRr>) the solution so far is
+		 * moved to the reference's variables, the residual of the ORIGINAL system b - A x is evaluated in
+		 * double-double arithmetic (k_residual_dd) and CG restarts on it with a fresh accumulator for the
+		 * correction; the stopping test stays ||r|| <= tol ||b^||.  Costs ~5 % more iterations (the restart loses
+		 * the Krylov space) and brings the displacements within ~1e-13 of the exact solve (tests: SuperLU with
+		 * extended-precision refinement at 0.1 / 0.5 / 2 M DOF).  BFM_CG_REFINE=0 switches it off. */
+
+		int max_refinements = 0;
+
+		if (use_mg) {
+			char const* const env = getenv("BFM_CG_REFINE");
+
+			max_refinements = env != nullptr ? atoi(env) : 2;
+
+			if (max_refinements > 0) {
+				/* measured on the plates: the recursion drifts from the true residual by ~2.2 eps ||x^|| (2e-6 ||b^|| at
+				 * 50 M DOF, 7e-8 at 2 M); refine when the residual is within 3x of that - later the iterations are
+				 * wasted on noise, earlier the correction is large enough to hit its own floor and need a second restart
+				 * (each restart costs the ~15 iterations it takes to rebuild the Krylov space) */
+				char const* const env_phi = getenv("BFM_CG_REFINE_AT");
+				double const phi = (env_phi != nullptr && atof(env_phi) > 0 ? atof(env_phi) : 6.0) * 2.220446049250313e-16;
+				double const floor2 = phi * phi;
+
+				if (BFMG_CHECK(cudaMemcpyAsync(&S->floor2, &floor2, sizeof floor2, cudaMemcpyHostToDevice, bfmg_stream())) < 0 || BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0) {
+					goto out;
+				}
+			}
+		}
+
+		Scalars last = {};
 
 		for (;;) {
 			/* enqueue chunks; poll the status one chunk behind the launch front.  The decision to enqueue
@@ -975,7 +1188,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 
 			while (!done) {
 				/* one chunk of iterations.  Without NCCL calls in it (one GPU, or peer-memory exchanges) the
-				 * chunk is captured once into a CUDA graph and replayed: ten small kernels per iteration
+				 * chunk is captured once into a CUDA graph and replayed: the small kernels of an iteration
 				 * leave the host's launch path and the gaps between them shrink */
 
 				bool const capture = graphable && chunk_exec == nullptr;
@@ -1057,25 +1270,55 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 				goto out;
 			}
 
-			Scalars const last = h_S[(launched_chunks - 1) & 1];
+			last = h_S[(launched_chunks - 1) & 1];
 
-			res->iterations = last.iter;
-			res->rel_residual = last.bnorm2 > 0 ? sqrt(last.rr / last.bnorm2) : 0;
-			res->converged = last.done == 1 ? 1 : (last.done == 3 ? 0 : -1);
-			res->restarts = restarts;
-
-			if (!opts->verify || last.bnorm2 == 0) {
+			if (last.done != 4) {
 				break;
 			}
 
-			/* true residual b^ - A^ x^ into q, its squared norm into S->sum, ||x^||^2 into S->sum2 */
+			/* the recursion has reached FP64's floor: refine on the original system and go on */
+
+			refinements++;
+
+			bool const ok = (have_base
+				? BFMG_LAUNCH((k_unscale<true, true>), (n_own + kBlock - 1) / kBlock, kBlock, 0, n_own, dscale + lo, xhat + lo, (double2*) d_x + lo)
+				: BFMG_LAUNCH((k_unscale<false, true>), (n_own + kBlock - 1) / kBlock, kBlock, 0, n_own, dscale + lo, xhat + lo, (double2*) d_x + lo)) == 0 &&
+				BFMG_LAUNCH(k_residual_dd<true>, G.spmv, kBlock, 0, *pat, vtop, vbot, (double2 const*) d_b, (double2 const*) d_x, dscale, r, partials, S, refinements < max_refinements ? 1 : 0) == 0 &&
+				MG_PRECONDITION(true);
+
+			if (!ok) {
+				goto out;
+			}
+
+			have_base = true;
+		}
+
+		res->iterations = last.iter;
+		res->rel_residual = last.bnorm2 > 0 ? sqrt(last.rr / last.bnorm2) : 0;
+		res->converged = last.done == 1 ? 1 : (last.done == 3 ? 0 : -1);
+		res->restarts = refinements;
+
+		/* the solution in the reference's variables: x = D^-1/2 x^ (+ what was accumulated before a refinement) */
+
+		if (n_own > 0 && (have_base
+			? BFMG_LAUNCH((k_unscale<true, false>), (n_own + kBlock - 1) / kBlock, kBlock, 0, n_own, dscale + lo, xhat + lo, (double2*) d_x + lo)
+			: BFMG_LAUNCH((k_unscale<false, false>), (n_own + kBlock - 1) / kBlock, kBlock, 0, n_own, dscale + lo, xhat + lo, (double2*) d_x + lo)) < 0) {
+			goto out;
+		}
+
+		if (opts->verify && last.bnorm2 != 0) {
+			/* recomputed residual of the ORIGINAL system for the solution as delivered, D^-1/2 (b - A x), evaluated in
+			 * double-double arithmetic, and ||D^1/2 x||.  An FP64 vector x has such a residual of ~eps |A| |x| however
+			 * it was obtained (rounding x alone does that), so on these ill-conditioned plates it reads 1e-8 .. 1e-6
+			 * of ||b^|| for ANY solver, the reference's LU included; what a converged solve must satisfy is a small
+			 * normwise backward error  eta = ||r^|| / (||A^|| ||x^|| + ||b^||)  (||A^||_2 >= 1 taken as 1), which
+			 * opts->true_tol limits.  Both are reported; the displacement error itself is pinned by the tests. */
 
 			if (
-				!HALO(xhat, false) ||
-				BFMG_LAUNCH(k_spmv<kResidual>, G.spmv, kBlock, 0, *pat, stop, sbot, xhat, q, bhat, partials, S) < 0 ||
+				!HALO(d_x, false) ||
+				BFMG_LAUNCH(k_residual_dd<false>, G.spmv, kBlock, 0, *pat, vtop, vbot, (double2 const*) d_b, (double2 const*) d_x, dscale, q, partials, S, 0) < 0 ||
 				!SHARE(kFoldResidual) ||
-				BFMG_LAUNCH(k_norm2, G.vec, kBlock, 0, n_own, xhat + lo, partials, S) < 0 ||
-				!SHARE(kFoldNorm2)
+				(shared && (BFMG_LAUNCH(k_norm2, G.vec, kBlock, 0, n_own, xhat + lo, partials, S) < 0 || !SHARE(kFoldNorm2)))
 			) {
 				goto out;
 			}
@@ -1090,38 +1333,12 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 			Scalars const now = h_S[0];
 
 			res->true_rel_residual = sqrt(now.sum / now.bnorm2);
-
-			/* In FP64 the recomputed residual cannot follow the recursion below ~eps * ||A^|| ||x^||, and on
-			 * these ill-conditioned plates ||x^|| / ||b^|| is ~cond(A^): 1e-8 at 80 k DOF, 5e-6 at 8 M DOF
-			 * (measured), for ANY backward-stable solver, the reference's LU included.  What a converged
-			 * solve must satisfy is a small normwise backward error
-			 *     eta = ||b^ - A^ x^|| / (||A^|| ||x^|| + ||b^||),   ||A^||_2 >= 1 (unit diagonal),
-			 * so eta is bounded with ||A^|| = 1; that is what opts->true_tol limits.  Both are reported. */
-
 			res->backward_error = sqrt(now.sum) / (sqrt(now.sum2) + sqrt(now.bnorm2));
 
-			bool const drifted = res->backward_error > opts->true_tol;
-
-			if (last.done != 1 || !drifted || restarts >= opts->max_restarts || last.iter >= opts->max_iter) {
-				if (last.done == 1 && drifted) {
-					res->converged = 0; /* the recursion converged but the true residual is far off */
-				}
-
-				break;
+			if (last.done == 1 && res->backward_error > opts->true_tol) {
+				res->converged = 0; /* the recursion converged but the delivered solution does not satisfy the system */
 			}
-
-			/* residual replacement: restart CG from the true residual */
-
-			if (BFMG_LAUNCH(k_restart, G.vec, kBlock, 0, n_own, q + lo, r + lo, p + lo, S) < 0 || (use_coarse && !PRECONDITION(true, false, false)) || (use_mg && !MG_PRECONDITION(true))) {
-				goto out;
-			}
-
-			restarts++;
 		}
-	}
-
-	if (n_own > 0 && BFMG_LAUNCH(k_unscale, (n_own + kBlock - 1) / kBlock, kBlock, 0, n_own, dscale + lo, xhat + lo, (double2*) d_x + lo) < 0) {
-		goto out;
 	}
 
 	{

@@ -48,7 +48,7 @@ class Stats(C.Structure):  # bfmx_stats_t
 
 
 class HierInfo(C.Structure):  # bfmx_hier_info_t
-	_fields_ = [("n_levels", C.c_int32), ("n_nodes", C.c_int32 * 12), ("n_colors", C.c_int32 * 12), ("n_slots", C.c_int64 * 12)]
+	_fields_ = [("n_levels", C.c_int32), ("n_nodes", C.c_int32 * 12), ("n_slots", C.c_int64 * 12)]
 
 
 class PartitionInfo(C.Structure):  # bfmx_partition_info_t
@@ -73,7 +73,7 @@ PROTOTYPES = {
 	"bfmx_dist_peer_memory_status": (C.c_char_p, []),
 	"bfmx_coarse_plan": (_int, [_P(abi.Mesh), _int, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
 	"bfmx_hier_info": (_int, [_P(abi.Mesh), _P(HierInfo)]),
-	"bfmx_hier_level": (_int, [_P(abi.Mesh), _int, c_int32_p, C.POINTER(C.c_float), c_int32_p, c_int32_p, c_int32_p]),
+	"bfmx_hier_level": (_int, [_P(abi.Mesh), _int, c_int32_p, C.POINTER(C.c_float), c_int32_p, c_int32_p]),
 	"bfmx_partition_sizes": (_int, [_P(abi.Mesh), _int, _int, _P(PartitionInfo)]),
 	"bfmx_partition_copy": (_int, [_P(abi.Mesh), _int, _int, abi.c_size_t_p, abi.c_size_t_p, abi.c_size_t_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
 	"bfmx_device_available": (_int, []),

@@ -178,16 +178,15 @@ int bfmx_coarse_plan(bfm_mesh_t* mesh, int target, int32_t* n_aggregates, int32_
 typedef struct {
 	int32_t n_levels;
 	int32_t n_nodes[BFMX_HIER_MAX_LEVELS];
-	int32_t n_colors[BFMX_HIER_MAX_LEVELS];  /* probing colours of the aggregates of this level (0 on the last) */
 	int64_t n_slots[BFMX_HIER_MAX_LEVELS];   /* padded SELL-32 slots of the level's operator */
 } bfmx_hier_info_t;
 
 int bfmx_hier_info(bfm_mesh_t* mesh, bfmx_hier_info_t* info);
 /* per level (any pointer may be NULL): aggregate[n] of every node (-1: left out), geometry[2 n] of every node
- * relative to its aggregate's reference point, color[n of level + 1] of every aggregate (not on the last
- * level); pattern_rowptr[n + 1] / pattern_col: the level's operator pattern as CSR with ascending columns
- * (call with pattern_col = NULL first to learn the length) */
-int bfmx_hier_level(bfm_mesh_t* mesh, int level, int32_t* aggregate, float* geometry, int32_t* color, int32_t* pattern_rowptr, int32_t* pattern_col);
+ * relative to its aggregate's reference point (neither on the last level); pattern_rowptr[n + 1] /
+ * pattern_col: the level's operator pattern as CSR with ascending columns (call with pattern_col = NULL first
+ * to learn the length) */
+int bfmx_hier_level(bfm_mesh_t* mesh, int level, int32_t* aggregate, float* geometry, int32_t* pattern_rowptr, int32_t* pattern_col);
 
 /* ---- matrices ---------------------------------------------------------------------------------------- */
 

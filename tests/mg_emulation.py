@@ -13,7 +13,7 @@ from bfm_b200 import ext
 
 
 def hierarchy(lib, mesh):
-	"""[(n, agg, geom, color, (rowptr, col))] per level; [] when the mesh gets no hierarchy"""
+	"""[dict(n, agg, geom, rowptr, col)] per level; [] when the mesh gets no hierarchy"""
 
 	info = ext.HierInfo()
 	assert not lib.lib.bfmx_hier_info(mesh.c_mesh, C.byref(info))
@@ -25,17 +25,16 @@ def hierarchy(lib, mesh):
 		last = l == info.n_levels - 1
 		agg = np.zeros(n, np.int32)
 		geom = np.zeros((n, 2), np.float32)
-		color = np.zeros(info.n_nodes[l + 1] if not last else 0, np.int32)
 		rowptr = np.zeros(n + 1, np.int32)
 
 		p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
 
-		assert not lib.lib.bfmx_hier_level(mesh.c_mesh, l, None if last else p(agg, C.c_int32), None if last else p(geom, C.c_float), None if last else p(color, C.c_int32), p(rowptr, C.c_int32), None)
+		assert not lib.lib.bfmx_hier_level(mesh.c_mesh, l, None if last else p(agg, C.c_int32), None if last else p(geom, C.c_float), p(rowptr, C.c_int32), None)
 
 		col = np.zeros(int(rowptr[-1]), np.int32)
-		assert not lib.lib.bfmx_hier_level(mesh.c_mesh, l, None, None, None, p(rowptr, C.c_int32), p(col, C.c_int32))
+		assert not lib.lib.bfmx_hier_level(mesh.c_mesh, l, None, None, p(rowptr, C.c_int32), p(col, C.c_int32))
 
-		levels.append(dict(n=n, agg=agg, geom=geom.astype(np.float64), color=color, rowptr=rowptr, col=col, n_colors=info.n_colors[l]))
+		levels.append(dict(n=n, agg=agg, geom=geom.astype(np.float64), rowptr=rowptr, col=col))
 
 	return levels
 

@@ -178,19 +178,21 @@ def test_large_plate_properties(nx, ny, kind, lib):
 	stats = ext.last_stats(lib)
 	u = case.instance.effects
 
-	# CG stops on the recursive residual (<= 1e-12); in FP64 the recomputed residual b - A x cannot follow it
-	# below ~eps * ||A|| ||x|| / ||b|| ~ eps * cond(A) - about 1e-8..1e-7 at these sizes - so the bar for it is
-	# loose, and the tight one is the normwise backward error ||b - A x|| / (||x|| + ||b||) (scaled norm)
+	# CG stops on the recursive residual (<= 1e-12).  The recomputed residual of the delivered FP64 solution cannot
+	# follow it below ~eps * ||A|| ||x|| / ||b|| ~ eps * cond(A) - about 1e-8..1e-7 at these sizes, whatever the solver
+	# (rounding x alone does that) - so the bar for it is loose, and the tight one is the normwise backward error
+	# ||b - A x|| / (||x|| + ||b||) (scaled norm).  The displacement error itself is pinned against SuperLU below.
 	assert stats["cg_converged"] == 1 and stats["cg_rel_residual"] <= 1e-12 and stats["cg_true_rel_residual"] <= 1e-6
 	assert stats["cg_backward_error"] <= 1e-12
 
-	# independent check of A x = b with the oracle's sparse system (assembled on the CPU): same residual
+	# independent check of A x = b with the oracle's sparse system (assembled on the CPU): the same residual up to the
+	# noise of evaluating it in plain FP64 here (the library evaluates it in double-double arithmetic)
 	oracle = cases.oracle_problem(case).system()
 	r = oracle.b - oracle.spmv(u.reshape(-1))
 	d = np.sqrt(np.abs(oracle.scipy().diagonal()))
 	independent = np.linalg.norm(r / d) / np.linalg.norm(oracle.b / d)
 
-	assert independent <= 1e-6 and abs(independent - stats["cg_true_rel_residual"]) <= 0.05 * independent + 1e-12
+	assert independent <= 1e-6 and independent <= 4 * stats["cg_true_rel_residual"] + 1e-12
 
 	# the plate and its load are symmetric about y = 0.5: u_y mirrors, u_x flips sign (P1 split breaks it
 	# slightly for triangles, so only quads are held to it)
@@ -207,22 +209,33 @@ def test_large_plate_properties(nx, ny, kind, lib):
 
 
 def _sparse_direct_reference(oracle):
-	"""displacements of the oracle's sparse system by SuperLU (scipy.sparse.linalg.splu) + one step of
-	iterative refinement: a direct solver that shares no code with this repository (the matrix comes from
-	oracle/bfm_oracle.c, itself pinned bit for bit to the compiled reference)"""
+	"""displacements of the oracle's sparse system by SuperLU (scipy.sparse.linalg.splu) with iterative refinement
+	on residuals accumulated in extended precision (x87 long double): a direct solver that shares no code with this
+	repository (the matrix comes from oracle/bfm_oracle.c, itself pinned bit for bit to the compiled reference).
+	A plain FP64 factorisation alone is only good to ~eps * cond(A) - 3e-10 at 2 M DOF, measured - which is too
+	close to the 1e-9 bar to judge anything; refined this way the checker is good to ~1e-13."""
 
 	import scipy.sparse.linalg as spl
 
-	A = oracle.scipy().tocsc()
-	lu = spl.splu(A, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+	A = oracle.scipy()
+	lu = spl.splu(A.tocsc(), permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
 	x = lu.solve(oracle.b.copy())
 
-	# at 2 M DOF the factorisation's own forward error is ~3e-10 (eps * cond): refine twice, report the last step
-	for _ in range(2):
-		dx = lu.solve(oracle.b - A @ x)
-		x += dx
+	val = A.data.astype(np.longdouble)
+	b = oracle.b.astype(np.longdouble)
+	step = np.inf
 
-	return x, float(np.linalg.norm(dx) / np.linalg.norm(x))
+	for _ in range(4):
+		products = val * x.astype(np.longdouble)[A.indices]
+		residual = b - np.add.reduceat(products, A.indptr[:-1])  # every row holds its diagonal: no empty rows
+		dx = lu.solve(residual.astype(np.float64))
+		x += dx
+		step = float(np.linalg.norm(dx) / np.linalg.norm(x))
+
+		if step <= 1e-14:
+			break
+
+	return x, step
 
 
 @pytest.mark.parametrize("nx,ny,kind,jitter", [(448, 112, 3, True), (1000, 250, 3, False), (600, 150, 4, False), (2000, 500, 3, False)])
@@ -247,8 +260,10 @@ def test_displacements_match_independent_sparse_direct_solve(nx, ny, kind, jitte
 
 	want, last_refinement = _sparse_direct_reference(cases.oracle_problem(case).system())
 
-	assert last_refinement <= 1e-11  # the checker itself has converged
-	assert rel_l2(case.instance.effects.reshape(-1), want) <= REL_L2, (stats, last_refinement)
+	err = rel_l2(case.instance.effects.reshape(-1), want)
+
+	assert last_refinement <= 1e-12, (last_refinement, err)  # the checker itself has converged
+	assert err <= REL_L2, (err, stats, last_refinement)
 
 
 # ---- small systems: the one-CTA solver and batches (BASELINE.json configs[4]) ---------------------------
