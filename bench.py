@@ -265,6 +265,44 @@ def mg_iteration_bytes(levels: list[dict], coarse_dim: int) -> dict:
 	return {"total": sum(per_level), "per_level": per_level, "gammas": gammas, "dense_visits": visits}
 
 
+
+# ---- parity where the driver can see it ---------------------------------------------------------------------
+
+
+PARITY_CASES = ["plate_80x20", "plate_q4_24x6", "lepl8_all_kinds", "gear60"]
+PARITY_TOL = 1e-9  # BASELINE.json north_star: displacements within 1e-9 (relative L2) of the reference's own solve
+
+
+def parity_check(binding, rank: int, world: int) -> dict:
+	"""bfm_sim_run on fixture cases (tests/cases.py) against the committed outputs of the UNMODIFIED reference
+	(tests/golden/ref_outputs.npz) - on N > 1 GPUs through the partitioned path, collectively, every rank holding the
+	complete field afterwards.  A miss aborts the run with a non-zero exit code: a throughput number for wrong
+	displacements is worthless."""
+
+	import numpy as np
+
+	sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+	import cases
+	from bfm_b200 import ext
+
+	golden = cases.golden()
+	errors, details = {}, {}
+
+	for name in PARITY_CASES:
+		case = cases.build(name, binding)
+		case.sim.run()
+		stats = ext.last_stats(binding)
+		want = golden[f"{name}/effects"]
+		errors[name] = float(np.linalg.norm(case.instance.effects - want) / np.linalg.norm(want))
+		details[name] = {"iterations": stats["cg_iterations"], "mg_levels": stats["mg_levels"], "n_ranks": stats["n_ranks"], "converged": stats["cg_converged"]}
+
+		if not (errors[name] <= PARITY_TOL and stats["cg_converged"] == 1 and stats["n_ranks"] == world):
+			raise SystemExit(f"[rank {rank}] parity check failed on {name}: relative L2 error {errors[name]:.3e} (tolerance {PARITY_TOL}), stats {stats}")
+
+	return {"tolerance": PARITY_TOL, "reference": "tests/golden/ref_outputs.npz (unmodified reference libbfm)", "rel_l2": errors, "runs": details}
+
+
 # ---- configs[4]: 1024 batched small systems ---------------------------------------------------------
 
 
@@ -367,6 +405,7 @@ def main():
 	ap.add_argument("--batch", type=int, default=1024, help="systems in the batch workload")
 	ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
 	ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+	ap.add_argument("--no-parity-check", action="store_true", help="skip the fixture parity check that precedes the timing")
 	args = ap.parse_args()
 
 	rank = int(os.environ.get("RANK", "0"))
@@ -442,6 +481,8 @@ def main():
 
 		batch_workload(args, binding)
 		return
+
+	parity = None if args.no_parity_check else parity_check(binding, rank, world)
 
 	nx, ny = parse_cells(args.cells)
 	case = workloads.plate_case(nx, ny, binding=binding)
@@ -628,9 +669,37 @@ def main():
 		}
 
 	cpu = None
+	same_size = None
 
 	if rank == 0 and world == 1 and not args.no_cpu_baseline:
 		cpu = time_reference(args.reference_sample, 1, 0)
+
+		# the GPU arm on the very plate the reference arm runs (the dense reference cannot go beyond 46 340 DOF):
+		# the same-work ratio next to the cross-size headline, and parity at the reference's own size
+		sx, sy = parse_cells(args.reference_sample)
+		small = workloads.plate_case(sx, sy, binding=binding)
+		small.sim.run()
+		t0 = time.perf_counter()
+		reps = 20
+
+		for _ in range(reps):
+			small.sim.run()
+
+		seconds = (time.perf_counter() - t0) / reps
+		same_size = {
+			"cells": args.reference_sample, "n_dofs": small.n_dofs, "value": small.n_dofs / seconds, "unit": UNIT, "ms_per_step": seconds * 1e3,
+			"call": "bfm_sim_run on host buffers (one CTA solves a mesh this small)", "reference_value": cpu["value"], "ratio": small.n_dofs / seconds / cpu["value"],
+		}
+
+		golden_path = os.path.join(ROOT, "tests", "golden", "ref_outputs.npz")
+		key = f"plate_{args.reference_sample}/effects"
+
+		if os.path.exists(golden_path):
+			golden = np.load(golden_path)
+
+			if key in golden:
+				got = workloads.effects_view(small.instance).reshape(-1, 2)
+				same_size["rel_l2_vs_reference"] = float(np.linalg.norm(got - golden[key]) / np.linalg.norm(golden[key]))
 
 	if rank == 0:
 		print(json.dumps({
@@ -662,6 +731,8 @@ def main():
 			"roofline": roofline,
 			"roofline_assembly": roofline_assembly,
 			"cpu_baseline": cpu,
+			"same_size": same_size,
+			"parity_check": parity,
 			"e2e": e2e,
 			"gpu_launches": launches,
 			"clocks": clocks,

@@ -269,21 +269,34 @@ int bfmi_csr_set_perm(bfm_matrix_t* matrix, size_t const* perm, size_t n) {
 		return -1;
 	}
 
-	csr->perm = malloc(n * sizeof *csr->perm);
-	csr->inv_perm = malloc(n * sizeof *csr->inv_perm);
+	/* validated and built aside: a failure leaves the matrix exactly as it was */
 
-	if (csr->perm == NULL || csr->inv_perm == NULL) {
+	size_t* const fwd = malloc((n + 1) * sizeof *fwd);
+	size_t* const inv = malloc((n + 1) * sizeof *inv);
+
+	if (fwd == NULL || inv == NULL) {
+		free(fwd);
+		free(inv);
 		return -1;
 	}
 
 	for (size_t i = 0; i < n; i++) {
-		if (perm[i] >= n) {
+		inv[i] = SIZE_MAX;
+	}
+
+	for (size_t i = 0; i < n; i++) {
+		if (perm[i] >= n || inv[perm[i]] != SIZE_MAX) { /* out of range, or not a permutation */
+			free(fwd);
+			free(inv);
 			return -1;
 		}
 
-		csr->perm[i] = perm[i];
-		csr->inv_perm[perm[i]] = i;
+		fwd[i] = perm[i];
+		inv[perm[i]] = i;
 	}
+
+	csr->perm = fwd;
+	csr->inv_perm = inv;
 
 	return 0;
 }

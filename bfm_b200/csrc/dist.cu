@@ -127,6 +127,7 @@ P2pLayout mailbox_layout(int world) {
 	L.coarse_seq = at, at += 2 * kP2pMaxRanks * sizeof(uint64_t);
 	L.mu_seq = at, at += 2 * kP2pMaxRanks * sizeof(uint64_t);
 	L.halo_seq = at, at += 2 * kP2pMaxRanks * sizeof(uint64_t);
+	L.gather_seq = at, at += 2 * kP2pMaxRanks * sizeof(uint64_t);
 	L.panel_seq = at, at += 2 * kP2pMaxRanks * sizeof(uint64_t);
 	L.gj_done = at, at += kP2pMaxRanks * sizeof(uint64_t);
 	L.error = at, at += 64;
@@ -139,6 +140,8 @@ P2pLayout mailbox_layout(int world) {
 	L.mu_val = at, at += align_up((size_t) 2 * L.coarse_cap * sizeof(double), 256);
 	L.halo_val = at, at += align_up((size_t) 2 * world * L.halo_cap * 2 * sizeof(double), 256);
 	L.panel_val = at, at += align_up((size_t) 2 * (32 * (size_t) L.coarse_cap + 32 * 32 + 8) * sizeof(double), 256);
+	L.gather_cap = 3 * 65536 + 64;         /* the first replicated level of the multigrid hierarchy: BFM_MG_REPLICATED_NODES nodes */
+	L.gather_val = at, at += align_up((size_t) 2 * L.gather_cap * sizeof(double), 256);
 	L.total = at;
 
 	return L;

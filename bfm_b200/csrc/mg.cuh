@@ -126,8 +126,12 @@ __global__ void __launch_bounds__(kBlock) k_spmv_mg(
 	double total;
 
 	if (grid_sum(acc, partials, &S->ticket, &total) && threadIdx.x == 0) {
+		if (S->world > 1) {
+			S->part = total; /* this rank's share of r.z: k_share folds it together with r.r and x.x */
+		}
+
 		/* r.z of a symmetric positive definite preconditioner is positive; anything else is a breakdown */
-		if (!(total > 0) || isinf(total)) {
+		else if (!(total > 0) || isinf(total)) {
 			S->done = S->done ? S->done : 2;
 			S->beta = 0;
 		}
@@ -174,12 +178,55 @@ __global__ void __launch_bounds__(kBlock) k_mg_gersh0(const __grid_constant__ bf
 	}
 }
 
-__global__ void k_mg_omega(int n_levels, double factor, MgDev* D) {
+/* several GPUs: all[r * stride + l] holds rank r's bound of level l (and, at index BFMG_MG_MAX_LEVELS, its "bad" flag):
+ * every rank takes the maximum, so that all ranks smooth with the same damping and take the same decision */
+__global__ void k_mg_omega(int n_levels, double factor, MgDev* D, double const* __restrict__ all, int world, int stride) {
 	int const l = threadIdx.x;
 
 	if (l < n_levels) {
-		double const bound = __longlong_as_double((long long) D->gersh[l]);
+		double bound = __longlong_as_double((long long) D->gersh[l]);
+
+		for (int r = 0; r < world; r++) {
+			bound = fmax(bound, all[r * stride + l]);
+		}
+
+		D->gersh[l] = (unsigned long long) __double_as_longlong(bound);
 		D->omega[l] = bound >= 1.0 ? factor / bound : factor; /* a unit diagonal makes every row sum >= 1 */
+	}
+
+	if (l == 0) {
+		for (int r = 0; r < world; r++) {
+			if (all[r * stride + BFMG_MG_MAX_LEVELS] != 0) {
+				D->bad = 1;
+			}
+		}
+	}
+}
+
+/* this rank's bounds and flag as doubles, for the all-gather */
+__global__ void k_mg_bounds(MgDev const* D, int32_t const* bad, double* __restrict__ out) {
+	int const l = threadIdx.x;
+
+	if (l < BFMG_MG_MAX_LEVELS) {
+		out[l] = __longlong_as_double((long long) D->gersh[l]);
+	}
+
+	if (l == BFMG_MG_MAX_LEVELS) {
+		out[l] = D->bad || *bad ? 1 : 0;
+	}
+}
+
+/* several GPUs, first replicated level: every rank computed the rows of its own aggregates (the others are zero);
+ * the operator is their sum, taken in rank order (exact: one non-zero contributor per entry) */
+__global__ void k_mg_sum_ranks(size_t count, int world, double const* __restrict__ all, double* __restrict__ out) {
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < count; i += (size_t) gridDim.x * blockDim.x) {
+		double t = 0;
+
+		for (int r = 0; r < world; r++) {
+			t += all[(size_t) r * count + i];
+		}
+
+		out[i] = t;
 	}
 }
 
@@ -364,7 +411,7 @@ __global__ void __launch_bounds__(kBlock) k_mg_rap(bfmg_mg_level_t L, bfmg_mg_le
 	size_t const np = (size_t) L.n_p;
 	size_t const ns = (size_t) L.n_slots;
 
-	for (int I = warp; I < N.n; I += n_warps) {
+	for (int I = warp; I < N.row_hi; I += n_warps) { /* the rows this rank holds: all of them on one GPU */
 		int const base = N.slice_off[I / kWarp] + I % kWarp;
 		int const len = N.row_len[I];
 
@@ -469,7 +516,7 @@ __global__ void __launch_bounds__(kBlock) k_mg_rap(bfmg_mg_level_t L, bfmg_mg_le
 __global__ void k_blk_diag(bfmg_mg_level_t N, double const* __restrict__ val, double* __restrict__ dsc, MgDev* D) {
 	int const I = blockIdx.x * blockDim.x + threadIdx.x;
 
-	if (I >= N.n) {
+	if (I >= N.row_hi) {
 		return;
 	}
 
@@ -505,7 +552,7 @@ __global__ void __launch_bounds__(kBlock) k_blk_scale(bfmg_mg_level_t N, double*
 		double sr[3] = {0, 0, 0};
 		double sum[3] = {0, 0, 0};
 
-		if (row < N.n) {
+		if (row < N.row_hi) {
 #pragma unroll
 			for (int k = 0; k < 3; k++) {
 				sr[k] = dsc[3 * (size_t) row + k];
@@ -569,7 +616,7 @@ __device__ __forceinline__ void d_blk_spmv(bfmg_mg_level_t const& N, double cons
 			y2 = fma(ld_stream(&val[6 * ns + slot]), x0, fma(ld_stream(&val[7 * ns + slot]), x1, fma(ld_stream(&val[8 * ns + slot]), x2, y2)));
 		}
 
-		if (row < N.n) {
+		if (row < N.row_hi) {
 			size_t const at = 3 * (size_t) row;
 			double const y[3] = {y0, y1, y2};
 
@@ -700,12 +747,37 @@ struct MgRun {
 	double omega_factor = 1.6;
 	double lambda0 = 4;     /* Gershgorin bound of the scaled level-0 operator (after setup) */
 
+	/* several GPUs (exchanges over NVLink peer memory, p2p.cuh): the levels 0 .. first_rep - 1 are distributed - a halo
+	 * exchange before every product with their operators - the levels from first_rep on are held by every rank */
+	bool dist = false;
+	int world = 1;
+	int first_rep = 0;
+	HaloDev HD[BFMG_MG_MAX_LEVELS] = {};
+	double* gpart = nullptr;   /* restriction onto the first replicated level: this rank's entries, the others zero */
+	double* gath = nullptr;    /* set-up: every rank's partial operator of the first replicated level; bounds of all ranks */
+	size_t gath_count = 0;     /* doubles of that operator (9 n_slots, or nc^2 when it is the dense level) */
+	double* bounds = nullptr;  /* [world + 1][BFMG_MG_MAX_LEVELS + 1] */
+
 	static size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
 
-	int alloc(bfmg_mg_t const* mg) {
+	bool rep_is_dense() const { return first_rep == n_levels - 1; }
+
+	int alloc(bfmg_mg_t const* mg, int world_) {
 		M = mg;
 		n_levels = mg->n_levels;
 		nc = mg->nc;
+		world = world_;
+		dist = world > 1;
+		first_rep = 0;
+
+		while (dist && first_rep < n_levels && mg->level[first_rep].distributed) {
+			first_rep++;
+		}
+
+		if (dist && (first_rep == 0 || first_rep >= n_levels)) {
+			bfmg_set_error("multigrid hierarchy of a partitioned job has no replicated level");
+			return -1;
+		}
 
 		size_t total = align256(sizeof(MgDev));
 
@@ -728,6 +800,13 @@ struct MgRun {
 		}
 
 		total += align256((size_t) nc * nc * sizeof(double)) + align256(kGjBlock * kGjBlock * sizeof(double)) + 2 * align256(((size_t) nc + 8) * sizeof(double)) + 256;
+
+		if (dist) {
+			gath_count = rep_is_dense() ? (size_t) nc * nc : (size_t) mg->level[first_rep].n_slots * 9;
+			total += align256(((size_t) next_len(first_rep - 1) + 8) * sizeof(double));
+			total += align256((size_t) world * gath_count * sizeof(double));
+			total += align256((size_t) (world + 1) * (BFMG_MG_MAX_LEVELS + 1) * sizeof(double));
+		}
 
 		if (bfmg_alloc(&ws, total) < 0) {
 			return -1;
@@ -763,6 +842,19 @@ struct MgRun {
 			if (!last) {
 				w.pval = take((size_t) L.n_p * (l == 0 ? 6 * sizeof(float) : 9 * sizeof(double)));
 			}
+
+			HaloDev& H = HD[l];
+
+			H.n_nbr = L.distributed ? L.n_nbr : 0;
+			H.n_send = L.distributed ? L.n_send : 0;
+
+			for (int k = 0; k < H.n_nbr; k++) {
+				H.nbr[k] = L.nbr[k];
+				H.recv_begin[k] = L.recv_begin[k];
+				H.recv_count[k] = L.recv_count[k];
+				H.send_ptr[k] = L.send_ptr[k];
+				H.send_ptr[k + 1] = L.send_ptr[k + 1];
+			}
 		}
 
 		E = (double*) take((size_t) nc * nc * sizeof(double));
@@ -770,6 +862,12 @@ struct MgRun {
 		dg = (double*) take(((size_t) nc + 8) * sizeof(double));
 		dmu = (double*) take(((size_t) nc + 8) * sizeof(double));
 		bad = (int32_t*) take(256);
+
+		if (dist) {
+			gpart = (double*) take(((size_t) next_len(first_rep - 1) + 8) * sizeof(double));
+			gath = (double*) take((size_t) world * gath_count * sizeof(double));
+			bounds = (double*) take((size_t) (world + 1) * (BFMG_MG_MAX_LEVELS + 1) * sizeof(double));
+		}
 
 		/* cycle shape: BFM_MG_GAMMA visits of the next level on every sparse level above the mesh (W-cycle by
 		 * default: the piecewise-rigid interpolation of plain aggregation needs it to stay level-independent) */
@@ -780,19 +878,19 @@ struct MgRun {
 			int g = 2;
 
 			if (env != nullptr && env[0] != 0) {
-				char const* at = env;
+				char const* at_env = env;
 
 				for (int skip = 1; skip < l; skip++) {
-					char const* const comma = strchr(at, ',');
+					char const* const comma = strchr(at_env, ',');
 
 					if (comma == nullptr) {
 						break;
 					}
 
-					at = comma + 1;
+					at_env = comma + 1;
 				}
 
-				g = atoi(at);
+				g = atoi(at_env);
 			}
 
 			W[l].gamma = g >= 1 && g <= 4 ? g : 2;
@@ -807,9 +905,58 @@ struct MgRun {
 		return 0;
 	}
 
+	/* several GPUs: do the halos of every distributed level and the gathered vector fit the mailboxes? */
+	bool fits(P2p const* px) const {
+		if (!dist) {
+			return true;
+		}
+
+		if (px == nullptr || next_len(first_rep - 1) > px->L.gather_cap) {
+			return false;
+		}
+
+		for (int l = 0; l < first_rep; l++) {
+			int const nb = l == 0 ? 2 : 3;
+
+			if (HD[l].n_nbr > kP2pMaxRanks) {
+				return false;
+			}
+
+			for (int k = 0; k < HD[l].n_nbr; k++) {
+				if ((int64_t) HD[l].recv_count[k] * nb > (int64_t) px->L.halo_cap * 2 || (int64_t) (HD[l].send_ptr[k + 1] - HD[l].send_ptr[k]) * nb > (int64_t) px->L.halo_cap * 2) {
+					return false;
+				}
+			}
+		}
+
+		return true;
+	}
+
 	void release() {
 		bfmg_free(ws);
 		ws = nullptr;
+	}
+
+	/* refresh the ghosts of a vector of the distributed level l from their owners (nothing elsewhere) */
+	bool halo(int l, double* vec, Scalars* S, bool obey) {
+		if (!dist || l >= first_rep) {
+			return true;
+		}
+
+		HaloDev const& H = HD[l];
+		int const grid = H.n_send > 0 ? (H.n_send + kBlock - 1) / kBlock : 1;
+
+		int rc = l == 0
+			? BFMG_LAUNCH(k_halo_post<2>, grid, kBlock, 0, H, (double const*) vec, (int32_t const*) W[l].L.send_idx, S, obey)
+			: BFMG_LAUNCH(k_halo_post<3>, grid, kBlock, 0, H, (double const*) vec, (int32_t const*) W[l].L.send_idx, S, obey);
+
+		if (rc == 0 && H.n_nbr > 0) {
+			rc = l == 0
+				? BFMG_LAUNCH(k_halo_take<2>, H.n_nbr, kBlock, 0, H, vec, S, obey)
+				: BFMG_LAUNCH(k_halo_take<3>, H.n_nbr, kBlock, 0, H, vec, S, obey);
+		}
+
+		return rc == 0;
 	}
 
 	/* out = P_l^T v */
@@ -824,17 +971,38 @@ struct MgRun {
 
 	/* right-hand side / solution buffers of level l + 1 as seen from level l */
 	double* next_g(int l) { return l + 1 == n_levels - 1 ? dg : W[l + 1].g; }
-	int next_len(int l) { return l + 1 == n_levels - 1 ? nc : 3 * W[l + 1].L.n; }
+	int next_len(int l) const { return l + 1 == n_levels - 1 ? nc : 3 * M->level[l + 1].n; }
 
-	/* set-up: prolongators, coarse operators by probing, scalings, damping factors, the dense inverse.
-	 * tmp_v / tmp_q: two level-0 work vectors (CG's p and q, free until k_cg_init); *usable = false when a coarse
-	 * operator is not positive definite (the caller then solves with the diagonal preconditioner alone) */
-	int setup(bfmg_pattern_t const* pat, double2 const* stop, double2 const* sbot, double2 const* dscale, double2* tmp_v, double2* tmp_q, int spmv_grid, Scalars* S, bool* usable) {
+	/* right-hand side of level l + 1 = P_l^T v.  A distributed level produces the entries of its own aggregates: the
+	 * owned part of a distributed next level (its ghosts follow by halo()), or - below the first replicated level - a
+	 * slice that every rank stores into every mailbox, from where the complete vector is taken */
+	bool restrict_down(int l, double const* v, Scalars* S, bool obey) {
+		if (dist && l + 1 == first_rep) {
+			int const real = 3 * M->level[l + 1].n;
+
+			return
+				restrict_to(l, v, gpart, real, S, obey) &&
+				BFMG_LAUNCH(k_mg_gather_post, bfmg_grid(((int64_t) 3 * W[l].L.gather_count + kBlock - 1) / kBlock, 2), kBlock, 0, 3 * W[l].L.gather_first, 3 * W[l].L.gather_count, (double const*) gpart, S, obey) == 0 &&
+				BFMG_LAUNCH(k_mg_gather_take, bfmg_grid(((int64_t) real + kBlock - 1) / kBlock, 2), kBlock, 0, real, next_g(l), S, obey) == 0;
+		}
+
+		if (dist && l + 1 < first_rep) {
+			return restrict_to(l, v, next_g(l), 3 * M->level[l + 1].row_hi, S, obey);
+		}
+
+		return restrict_to(l, v, next_g(l), next_len(l), S, obey);
+	}
+
+	/* set-up: prolongators, coarse operators (Galerkin products), scalings, damping factors, the dense inverse.
+	 * *usable = false when a coarse operator is not positive definite (the caller then solves with the diagonal
+	 * preconditioner alone; on several GPUs every rank takes the same decision) */
+	int setup(bfmg_pattern_t const* pat, double2 const* stop, double2 const* sbot, double2 const* dscale, int spmv_grid, Scalars* S, bool* usable) {
 		*usable = false;
 
 		if (
 			BFMG_CHECK(cudaMemsetAsync(D, 0, sizeof(MgDev), bfmg_stream())) < 0 ||
 			BFMG_CHECK(cudaMemsetAsync(bad, 0, sizeof(int32_t), bfmg_stream())) < 0 ||
+			BFMG_CHECK(cudaMemsetAsync(dg, 0, ((size_t) nc + 8) * sizeof(double), bfmg_stream())) < 0 ||
 			BFMG_LAUNCH(k_mg_gersh0, spmv_grid, kBlock, 0, *pat, stop, sbot, &D->gersh[0]) < 0
 		) {
 			return -1;
@@ -844,8 +1012,9 @@ struct MgRun {
 			MgLevelWork& w = W[l];
 			MgLevelWork& nx = W[l + 1];
 			bool const dense = l + 1 == n_levels - 1;
+			bool const transition = dist && l + 1 == first_rep; /* this level is distributed, the next one replicated */
 			int const node_blocks = (w.L.n + kBlock - 1) / kBlock;
-			int const coarse_blocks = (nx.L.n + kBlock - 1) / kBlock;
+			int const coarse_blocks = (nx.L.row_hi + kBlock - 1) / kBlock;
 			double* const target = dense ? E : nx.val;
 			size_t const target_bytes = dense ? (size_t) nc * nc * sizeof(double) : (size_t) nx.L.n_slots * 9 * sizeof(double);
 
@@ -857,7 +1026,7 @@ struct MgRun {
 				return -1;
 			}
 
-			int const rap_grid = bfmg_grid(((int64_t) nx.L.n + kWarpsPerBlock - 1) / kWarpsPerBlock, 8);
+			int const rap_grid = bfmg_grid(((int64_t) nx.L.row_hi + kWarpsPerBlock - 1) / kWarpsPerBlock, 8);
 
 			if (dense) {
 				rc = l == 0
@@ -875,6 +1044,17 @@ struct MgRun {
 				return -1;
 			}
 
+			if (transition) {
+				/* every rank holds the rows of its own aggregates: add the ranks' parts up (one collective, set-up only) */
+
+				if (
+					bfmg_dist_allgather_f64(target, gath, (int) gath_count) < 0 ||
+					BFMG_LAUNCH(k_mg_sum_ranks, bfmg_grid(((int64_t) gath_count + kBlock - 1) / kBlock, 8), kBlock, 0, gath_count, world, (double const*) gath, target) < 0
+				) {
+					return -1;
+				}
+			}
+
 			if (dense) {
 				if (3 * nx.L.n < nc && BFMG_LAUNCH(k_mg_dense_pad, 1, kBlock, 0, 3 * nx.L.n, nc, E) < 0) {
 					return -1;
@@ -883,6 +1063,11 @@ struct MgRun {
 
 			else {
 				rc = BFMG_LAUNCH(k_blk_diag, coarse_blocks, kBlock, 0, nx.L, nx.val, nx.dsc, D);
+
+				if (rc == 0 && !halo(l + 1, nx.dsc, S, false)) { /* the scaling of the ghost columns */
+					rc = -1;
+				}
+
 				rc = rc < 0 ? rc : BFMG_LAUNCH(k_blk_scale, nx.grid_rows, kBlock, 0, nx.L, nx.val, nx.dsc, &D->gersh[l + 1]);
 				rc = rc < 0 ? rc : (l == 0
 					? BFMG_LAUNCH((k_mg_pscale<2, float>), (w.L.n_p + kBlock - 1) / kBlock, kBlock, 0, w.L, nx.dsc, (float*) w.pval)
@@ -894,11 +1079,7 @@ struct MgRun {
 			}
 		}
 
-		if (BFMG_LAUNCH(k_mg_omega, 1, kWarp, 0, n_levels, omega_factor, D) < 0) {
-			return -1;
-		}
-
-		/* dense inverse of the last level (in place, coarse.cuh) */
+		/* dense inverse of the last level (in place, coarse.cuh; replicated: every rank inverts it) */
 
 		CoarseWork CW = {};
 
@@ -908,11 +1089,30 @@ struct MgRun {
 		CW.P = Pblk;
 		CW.bad = bad;
 
+		if (coarse_invert(CW, S, false, 0, nc / kGjBlock) < 0) {
+			return -1;
+		}
+
+		/* damping factors from the row-sum bounds - on several GPUs from the largest bound over the ranks, which also
+		 * agree on whether a coarse operator came out unusable */
+
+		int const stride = BFMG_MG_MAX_LEVELS + 1;
+
+		if (dist && (
+			BFMG_LAUNCH(k_mg_bounds, 1, kWarp, 0, (MgDev const*) D, (int32_t const*) bad, bounds + (size_t) world * stride) < 0 ||
+			bfmg_dist_allgather_f64(bounds + (size_t) world * stride, bounds, stride) < 0
+		)) {
+			return -1;
+		}
+
+		if (BFMG_LAUNCH(k_mg_omega, 1, kWarp, 0, n_levels, omega_factor, D, (double const*) bounds, dist ? world : 0, stride) < 0) {
+			return -1;
+		}
+
 		int32_t flags[2] = {0, 0};
 		unsigned long long bound0 = 0;
 
 		if (
-			coarse_invert(CW, S, false, 0, nc / kGjBlock) < 0 ||
 			BFMG_CHECK(cudaMemcpyAsync(&flags[0], bad, sizeof(int32_t), cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
 			BFMG_CHECK(cudaMemcpyAsync(&flags[1], &D->bad, sizeof(int32_t), cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
 			BFMG_CHECK(cudaMemcpyAsync(&bound0, &D->gersh[0], sizeof bound0, cudaMemcpyDeviceToHost, bfmg_stream())) < 0 ||
@@ -927,6 +1127,7 @@ struct MgRun {
 			lambda0 = 4;
 		}
 
+		/* D->bad carries every rank's verdict after k_mg_omega; the dense inverse is replicated, its verdict the same everywhere */
 		*usable = flags[0] == 0 && flags[1] == 0;
 		return 0;
 	}
@@ -937,16 +1138,16 @@ struct MgRun {
 		bool const dense_next = l + 1 == n_levels - 1;
 		double const* const om = &D->omega[l];
 
-		if (BFMG_LAUNCH(k_blk_spmv<kMgPre>, w.grid_rows, kBlock, 0, w.L, w.val, w.g, w.g, w.vt, om, S, obey) < 0) {
+		if (!halo(l, w.g, S, obey) || BFMG_LAUNCH(k_blk_spmv<kMgPre>, w.grid_rows, kBlock, 0, w.L, w.val, w.g, w.g, w.vt, om, S, obey) < 0) {
 			return nullptr;
 		}
 
 		for (int visit = 0; visit < w.gamma; visit++) {
-			if (visit > 0 && BFMG_LAUNCH(k_blk_spmv<kMgResid>, w.grid_rows, kBlock, 0, w.L, w.val, w.va, w.g, w.vt, om, S, obey) < 0) {
+			if (visit > 0 && (!halo(l, w.va, S, obey) || BFMG_LAUNCH(k_blk_spmv<kMgResid>, w.grid_rows, kBlock, 0, w.L, w.val, w.va, w.g, w.vt, om, S, obey) < 0)) {
 				return nullptr;
 			}
 
-			if (!restrict_to(l, w.vt, next_g(l), next_len(l), S, obey)) {
+			if (!restrict_down(l, w.vt, S, obey)) {
 				return nullptr;
 			}
 
@@ -969,15 +1170,15 @@ struct MgRun {
 			}
 
 			int const rc = visit == 0
-				? BFMG_LAUNCH((k_mg_prolong<3, double, false>), w.grid_nodes, kBlock, 0, w.L, 0, w.L.n, (double const*) w.pval, mu, w.g, w.va, om, S, obey)
-				: BFMG_LAUNCH((k_mg_prolong<3, double, true>), w.grid_nodes, kBlock, 0, w.L, 0, w.L.n, (double const*) w.pval, mu, w.g, w.va, om, S, obey);
+				? BFMG_LAUNCH((k_mg_prolong<3, double, false>), w.grid_nodes, kBlock, 0, w.L, 0, w.L.row_hi, (double const*) w.pval, mu, w.g, w.va, om, S, obey)
+				: BFMG_LAUNCH((k_mg_prolong<3, double, true>), w.grid_nodes, kBlock, 0, w.L, 0, w.L.row_hi, (double const*) w.pval, mu, w.g, w.va, om, S, obey);
 
 			if (rc < 0) {
 				return nullptr;
 			}
 		}
 
-		if (BFMG_LAUNCH(k_blk_spmv<kMgPost>, w.grid_rows, kBlock, 0, w.L, w.val, w.va, w.g, w.vb, om, S, obey) < 0) {
+		if (!halo(l, w.va, S, obey) || BFMG_LAUNCH(k_blk_spmv<kMgPost>, w.grid_rows, kBlock, 0, w.L, w.val, w.va, w.g, w.vb, om, S, obey) < 0) {
 			return nullptr;
 		}
 
@@ -987,7 +1188,7 @@ struct MgRun {
 	/* z = M^-1 r on level 0: t (work) and z are level-0 vectors; the result lands in `out` (may alias t) together
 	 * with r.z -> beta, rho in S.  FIRST: initial residual (beta = 0, runs regardless of S->done). */
 	template <bool FIRST>
-	bool apply(bfmg_pattern_t const* pat, double2 const* stop, double2 const* sbot, double2 const* r, double2* t, double2* z, double2* out, double* partials, int spmv_grid, int vec_grid, Scalars* S) {
+	bool apply(bfmg_pattern_t const* pat, double2 const* stop, double2 const* sbot, double2* r, double2* t, double2* z, double2* out, double* partials, int spmv_grid, int vec_grid, Scalars* S) {
 		bool const obey = !FIRST;
 		bool const dense_next = n_levels == 2;
 		double const* const om = &D->omega[0];
@@ -995,8 +1196,9 @@ struct MgRun {
 		int const n_own = pat->row_hi - pat->row_lo;
 
 		if (
-			BFMG_LAUNCH((k_spmv_mg<kMgPre, FIRST>), spmv_grid, kBlock, 0, *pat, stop, sbot, r, r, t, om, partials, S) < 0 ||
-			!restrict_to(0, (double const*) t, next_g(0), next_len(0), S, obey)
+			!halo(0, (double*) r, S, obey) ||
+			BFMG_LAUNCH((k_spmv_mg<kMgPre, FIRST>), spmv_grid, kBlock, 0, *pat, stop, sbot, (double2 const*) r, (double2 const*) r, t, om, partials, S) < 0 ||
+			!restrict_down(0, (double const*) t, S, obey)
 		) {
 			return false;
 		}
@@ -1019,9 +1221,16 @@ struct MgRun {
 			}
 		}
 
-		return
-			BFMG_LAUNCH((k_mg_prolong<2, float, false>), vec_grid, kBlock, 0, W[0].L, lo, n_own, (float const*) W[0].pval, mu, (double const*) r, (double*) z, om, S, obey) == 0 &&
-			BFMG_LAUNCH((k_spmv_mg<kMgPost, FIRST>), spmv_grid, kBlock, 0, *pat, stop, sbot, (double2 const*) z, r, out, om, partials, S) == 0;
+		if (
+			BFMG_LAUNCH((k_mg_prolong<2, float, false>), vec_grid, kBlock, 0, W[0].L, lo, n_own, (float const*) W[0].pval, mu, (double const*) r, (double*) z, om, S, obey) < 0 ||
+			!halo(0, (double*) z, S, obey) ||
+			BFMG_LAUNCH((k_spmv_mg<kMgPost, FIRST>), spmv_grid, kBlock, 0, *pat, stop, sbot, (double2 const*) z, (double2 const*) r, out, om, partials, S) < 0
+		) {
+			return false;
+		}
+
+		/* several GPUs: r.z, r.r and x.x of all ranks, folded in rank order by one thread per rank */
+		return !dist || (FIRST ? BFMG_LAUNCH(k_share<kShareMgFirst>, 1, 1, 0, S, 0) : BFMG_LAUNCH(k_share<kShareMg>, 1, 1, 0, S, 0)) == 0;
 	}
 };
 

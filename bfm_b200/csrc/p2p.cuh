@@ -9,8 +9,11 @@
  *             there and folds them in rank order
  *   coarse    k_restrict stores W^T r (and the r.r share) into every peer; k_coarse_fold waits and folds
  *   mu        each rank applies ITS rows of E^-1 and stores its part of mu into every peer
- *   halo      k_halo_post packs the interface entries of p straight into the neighbour's staging area;
- *             k_halo_take waits for the neighbours' rounds and copies them into the ghost range of p
+ *   halo      k_halo_post packs the interface entries of a vector straight into the neighbour's staging area;
+ *             k_halo_take waits for the neighbours' rounds and copies them into the ghost range (every distributed
+ *             level of the multigrid hierarchy uses the same channel: the exchanges follow each other in stream order)
+ *   gather    multigrid: every rank stores its slice of the first replicated level's right-hand side into every
+ *             mailbox; k_mg_gather_take waits for all slices and copies the complete vector out
  *   panel     set-up only: the Gauss-Jordan inversion of the coarse operator is distributed by row blocks;
  *             the owner of a pivot block stores its row panel into every peer, and every rank acknowledges
  *             each finished step so that the two panel buffers can be reused safely
@@ -38,6 +41,7 @@ struct P2pLayout {
 	size_t coarse_seq;  /* uint64 [2][kP2pMaxRanks] */
 	size_t mu_seq;      /* uint64 [2][kP2pMaxRanks] */
 	size_t halo_seq;    /* uint64 [2][kP2pMaxRanks] */
+	size_t gather_seq;  /* uint64 [2][kP2pMaxRanks]  multigrid: right-hand side of the first replicated level */
 	size_t panel_seq;   /* uint64 [2][kP2pMaxRanks]  distributed Gauss-Jordan: pivot panels, by owner */
 	size_t gj_done;     /* uint64 [kP2pMaxRanks]     ... steps every rank has finished (flow control) */
 	size_t error;       /* int32 */
@@ -45,9 +49,11 @@ struct P2pLayout {
 	size_t mu_val;      /* double [2][coarse_cap] */
 	size_t halo_val;    /* double2 [2][world][halo_cap] */
 	size_t panel_val;   /* double [2][32 * coarse_cap + 32 * 32 + 8]: row panel, inverse of the pivot block, bad flag */
+	size_t gather_val;  /* double [2][gather_cap]: every rank writes its slice of the vector into every mailbox */
 	size_t total;
 	int32_t coarse_cap; /* doubles per rank in the coarse channel (n_c + 8 must fit) */
-	int32_t halo_cap;   /* node entries per neighbour in the halo channel */
+	int32_t halo_cap;   /* node entries (two doubles each) per neighbour in the halo channel */
+	int32_t gather_cap; /* doubles in the gather channel */
 };
 
 struct P2p {

@@ -68,7 +68,8 @@ struct Scalars {
 	int32_t rr_rides;    /* the r.r share travels with the coarse restriction instead of the scalar channel */
 	uint32_t ticket2;    /* last-CTA ticket of k_restrict / k_halo_post (grid_sum has its own) */
 	int32_t pad2;
-	uint64_t ep_scalar, ep_coarse, ep_mu, ep_halo;
+	uint64_t ep_scalar, ep_coarse, ep_mu, ep_halo, ep_gather;
+	double part2, part3; /* further shares of this rank for reductions that travel together (multigrid: r.z with r.r and x.x) */
 	P2p X;
 };
 
@@ -207,7 +208,10 @@ struct HaloDev {
 	int32_t send_ptr[kP2pMaxRanks + 1];
 };
 
-__global__ void __launch_bounds__(kBlock) k_halo_post(const __grid_constant__ HaloDev H, double2 const* __restrict__ v, int32_t const* __restrict__ send_idx, Scalars* S, bool obey_done) {
+/* NB doubles per node: 2 on the mesh level, 3 on the levels of the multigrid hierarchy.  Always launched, even by a
+ * rank with nothing to send on this level: the round counter must advance alike on every rank. */
+template <int NB>
+__global__ void __launch_bounds__(kBlock) k_halo_post(const __grid_constant__ HaloDev H, double const* __restrict__ v, int32_t const* __restrict__ send_idx, Scalars* S, bool obey_done) {
 	if (obey_done && S->done) {
 		return;
 	}
@@ -223,11 +227,14 @@ __global__ void __launch_bounds__(kBlock) k_halo_post(const __grid_constant__ Ha
 			k++;
 		}
 
-		double2 const val = v[send_idx[i]];
-		double* const dst = (double*) (X.box[H.nbr[k]] + X.L.halo_val) + (((round & 1) * X.world + X.me) * (size_t) X.L.halo_cap + (i - H.send_ptr[k])) * 2;
+		double const* const src = v + (size_t) NB * send_idx[i];
+		double* const dst = (double*) (X.box[H.nbr[k]] + X.L.halo_val) + ((round & 1) * X.world + X.me) * (size_t) X.L.halo_cap * 2 + (size_t) (i - H.send_ptr[k]) * NB;
 
-		p2p_store_f64(dst, val.x);
-		p2p_store_f64(dst + 1, val.y);
+#pragma unroll
+		for (int c = 0; c < NB; c++) {
+			p2p_store_f64(dst + c, src[c]);
+		}
+
 		__threadfence_system();
 	}
 
@@ -255,7 +262,8 @@ __global__ void __launch_bounds__(kBlock) k_halo_post(const __grid_constant__ Ha
 }
 
 /* one CTA per neighbour: wait for its round, copy its entries into the ghost range of v */
-__global__ void __launch_bounds__(kBlock) k_halo_take(const __grid_constant__ HaloDev H, double2* __restrict__ v, Scalars* S, bool obey_done) {
+template <int NB>
+__global__ void __launch_bounds__(kBlock) k_halo_take(const __grid_constant__ HaloDev H, double* __restrict__ v, Scalars* S, bool obey_done) {
 	if (obey_done && S->done) {
 		return;
 	}
@@ -271,10 +279,154 @@ __global__ void __launch_bounds__(kBlock) k_halo_take(const __grid_constant__ Ha
 
 	__syncthreads();
 
-	double2 const* const staged = (double2 const*) (X.box[X.me] + X.L.halo_val) + ((round & 1) * X.world + src) * (size_t) X.L.halo_cap;
+	double const* const staged = (double const*) (X.box[X.me] + X.L.halo_val) + ((round & 1) * X.world + src) * (size_t) X.L.halo_cap * 2;
+	double* const dst = v + (size_t) NB * H.recv_begin[k];
 
-	for (int i = threadIdx.x; i < H.recv_count[k]; i += kBlock) {
-		v[H.recv_begin[k] + i] = __ldcg(&staged[i]);
+	for (int i = threadIdx.x; i < NB * H.recv_count[k]; i += kBlock) {
+		dst[i] = __ldcg(&staged[i]);
+	}
+}
+
+/* ---- multigrid on several GPUs: the right-hand side of the first replicated level ------------------------------
+ * every rank computed the entries [first, first + count) of src (the aggregates of its own nodes) and stores them
+ * into every mailbox, its own included; k_mg_gather_take waits for all ranks and copies the complete vector out */
+__global__ void __launch_bounds__(kBlock) k_mg_gather_post(int first, int count, double const* __restrict__ src, Scalars* S, bool obey_done) {
+	if (obey_done && S->done) {
+		return;
+	}
+
+	P2p const& X = S->X;
+	uint64_t const round = S->ep_gather + 1;
+
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+		double const val = src[first + i];
+
+		for (int r = 0; r < X.world; r++) {
+			p2p_store_f64((double*) (X.box[r] + X.L.gather_val) + (round & 1) * (size_t) X.L.gather_cap + first + i, val);
+		}
+	}
+
+	__threadfence_system();
+
+	__shared__ bool last;
+
+	__syncthreads();
+
+	if (threadIdx.x == 0) {
+		__threadfence_system();
+		last = atomicAdd(&S->ticket2, 1u) == gridDim.x - 1;
+	}
+
+	__syncthreads();
+
+	if (last && threadIdx.x == 0) {
+		__threadfence_system();
+
+		for (int r = 0; r < X.world; r++) {
+			p2p_publish(X, r, X.L.gather_seq, round);
+		}
+
+		S->ep_gather = round;
+		S->ticket2 = 0;
+	}
+}
+
+__global__ void __launch_bounds__(kBlock) k_mg_gather_take(int n, double* __restrict__ dst, Scalars* S, bool obey_done) {
+	if (obey_done && S->done) {
+		return;
+	}
+
+	P2p const& X = S->X;
+	uint64_t const round = S->ep_gather;
+
+	if (threadIdx.x < X.world) {
+		p2p_wait(X, p2p_seq(X, X.me, X.L.gather_seq, round, threadIdx.x), round);
+	}
+
+	__syncthreads();
+
+	double const* const staged = (double const*) (X.box[X.me] + X.L.gather_val) + (round & 1) * (size_t) X.L.gather_cap;
+
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		dst[i] = __ldcg(&staged[i]);
+	}
+}
+
+/* ---- several GPUs: up to three sums that travel together, posted and folded by one thread ----------------------
+ * S->part (, part2, part3) hold this rank's shares; every rank's thread stores them into every mailbox, waits for
+ * all ranks and adds them in rank order - the same bits everywhere.
+ *   kShareMg / kShareMgFirst   multigrid iteration: r.z -> beta, rho;  r.r -> convergence (not FIRST);  x.x -> S->xx
+ *   kShareRefine               restart on the recomputed residual: rho = rr = sum, new accumulator
+ *   kShareVerify               S->sum = ||r^||^2, S->sum2 = ||x^||^2 */
+enum ShareMode { kShareMg, kShareMgFirst, kShareRefine, kShareVerify };
+
+template <ShareMode MODE>
+__global__ void k_share(Scalars* S, int arm_again) {
+	if (MODE == kShareMg && S->done) {
+		return;
+	}
+
+	P2p const& X = S->X;
+	uint64_t const round = S->ep_scalar + 1;
+	double const mine[3] = {S->part, S->part2, S->part3};
+
+	for (int r = 0; r < X.world; r++) {
+		double* const slot = (double*) (X.box[r] + X.L.scalar_val) + ((round & 1) * kP2pMaxRanks + X.me) * kP2pScalarSlots;
+
+		p2p_store_f64(slot + 0, mine[0]);
+		p2p_store_f64(slot + 1, mine[1]);
+		p2p_store_f64(slot + 2, mine[2]);
+	}
+
+	__threadfence_system();
+
+	for (int r = 0; r < X.world; r++) {
+		p2p_publish(X, r, X.L.scalar_seq, round);
+	}
+
+	S->ep_scalar = round;
+
+	double total[3] = {0, 0, 0};
+
+	for (int r = 0; r < X.world; r++) {
+		p2p_wait(X, p2p_seq(X, X.me, X.L.scalar_seq, round, r), round);
+
+		double const* const slot = (double const*) (X.box[X.me] + X.L.scalar_val) + ((round & 1) * kP2pMaxRanks + r) * kP2pScalarSlots;
+
+		total[0] += __ldcg(slot + 0);
+		total[1] += __ldcg(slot + 1);
+		total[2] += __ldcg(slot + 2);
+	}
+
+	if (MODE == kShareMg || MODE == kShareMgFirst) {
+		S->xx = total[2];
+
+		if (MODE == kShareMg) {
+			fold<kFoldRr>(S, total[1]);
+		}
+
+		if (!(total[0] > 0) || isinf(total[0])) {
+			S->done = S->done ? S->done : 2;
+			S->beta = 0;
+		}
+
+		else {
+			S->beta = MODE == kShareMgFirst ? 0 : total[0] / S->rho;
+			S->rho = total[0];
+		}
+	}
+
+	else if (MODE == kShareRefine) {
+		S->rho = total[0];
+		S->rr = total[0];
+		S->xx = 0;
+		S->floor2 = arm_again ? S->floor2 : 0;
+		S->done = !(total[0] == total[0]) ? 2 : (total[0] <= S->tol2 * S->bnorm2 ? 1 : (S->iter >= S->max_iter ? 3 : 0));
+	}
+
+	else {
+		S->sum = total[0];
+		S->sum2 = total[1];
 	}
 }
 
@@ -604,8 +756,16 @@ __global__ void __launch_bounds__(kBlock) k_update_xr(int n2, double2 const* __r
 	double total, total2;
 
 	if (grid_sum2(acc, acc2, partials, &S->ticket, &total, &total2) && threadIdx.x == 0) {
-		S->xx = total2; /* this rank's rows: the floor test is only armed on one GPU */
-		reduced<kFoldRr>(S, total);
+		S->xx = total2;
+
+		if (S->world > 1 && S->coarse == 2) { /* multigrid on several GPUs: both travel with r.z (k_share) */
+			S->part2 = total;
+			S->part3 = total2;
+		}
+
+		else {
+			reduced<kFoldRr>(S, total);
+		}
 	}
 }
 
@@ -727,7 +887,13 @@ __global__ void __launch_bounds__(kBlock) k_residual_dd(
 	double total, total2;
 
 	if (grid_sum2(acc, acc2, partials, &S->ticket, &total, &total2) && threadIdx.x == 0) {
-		if (REFINE) {
+		if (S->world > 1 && S->coarse == 2) { /* multigrid on several GPUs: k_share<kShareRefine / kShareVerify> folds */
+			S->part = total;
+			S->part2 = total2;
+			S->part3 = 0;
+		}
+
+		else if (REFINE) {
 			S->rho = total;
 			S->rr = total;
 			S->xx = 0;
@@ -829,11 +995,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	}
 
 	/* the multilevel preconditioner (mg.cuh) replaces the single coarse level where a hierarchy is given */
-	bool use_mg = mg != nullptr && !shared;
-
-	if (use_mg) {
-		coarse = nullptr;
-	}
+	bool use_mg = mg != nullptr; /* on several GPUs: only with the exchanges over peer memory (decided below) */
 
 	MgRun MG;
 
@@ -913,8 +1075,8 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	/* p2p: the producing kernel has already stored this rank's share into every peer's mailbox (reduced<>) */
 #define SHARE(WHAT) (!shared || ((p2p || bfmg_dist_allgather_f64(&S->part, S->gath, 1) == 0) && BFMG_LAUNCH(k_fold<WHAT>, 1, 1, 0, S) == 0))
 #define HALO(vec, obey) (!shared || (p2p \
-		? ((HD.n_send == 0 || BFMG_LAUNCH(k_halo_post, (HD.n_send + kBlock - 1) / kBlock, kBlock, 0, HD, (double2 const*) (vec), halo->d_send_idx, S, (obey)) == 0) && \
-		   (HD.n_nbr == 0 || BFMG_LAUNCH(k_halo_take, HD.n_nbr, kBlock, 0, HD, (double2*) (vec), S, (obey)) == 0)) \
+		? (BFMG_LAUNCH(k_halo_post<2>, HD.n_send > 0 ? (HD.n_send + kBlock - 1) / kBlock : 1, kBlock, 0, HD, (double const*) (vec), halo->d_send_idx, S, (obey)) == 0 && \
+		   (HD.n_nbr == 0 || BFMG_LAUNCH(k_halo_take<2>, HD.n_nbr, kBlock, 0, HD, (double*) (vec), S, (obey)) == 0)) \
 		: bfmg_dist_halo(halo, (double*) (vec), (double*) sendbuf) == 0))
 
 	/* g = W^T vec: per-aggregate sums over the owned rows, completed across ranks in rank order */
@@ -953,8 +1115,12 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	bool p2p = false;
 	HaloDev HD = {};
 
+	if (use_mg && MG.alloc(mg, world) < 0) {
+		goto out;
+	}
+
 	if (shared) {
-		int fits = px != nullptr && halo->n_nbr <= kP2pMaxRanks && (nc == 0 || nc + 8 <= px->L.coarse_cap);
+		int fits = px != nullptr && halo->n_nbr <= kP2pMaxRanks && (use_mg ? MG.fits(px) : (nc == 0 || nc + 8 <= px->L.coarse_cap));
 
 		HD.n_nbr = halo->n_nbr <= kP2pMaxRanks ? halo->n_nbr : 0;
 		HD.n_send = halo->n_send;
@@ -978,6 +1144,15 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		}
 
 		p2p = all_fit != 0;
+
+		if (use_mg && !p2p) {
+			bfmg_set_error("the multilevel preconditioner of a partitioned job needs the exchanges over NVLink peer memory (%s)", bfmg_dist_p2p_status());
+			goto out;
+		}
+	}
+
+	if (use_mg) {
+		use_coarse = false;
 	}
 
 	{
@@ -1013,7 +1188,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 	if (use_mg) {
 		bool usable = false;
 
-		if (MG.alloc(mg) < 0 || MG.setup(pat, stop, sbot, dscale, p, q, G.spmv, S, &usable) < 0) {
+		if (MG.setup(pat, stop, sbot, dscale, G.spmv, S, &usable) < 0) {
 			goto out;
 		}
 
@@ -1022,10 +1197,10 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		}
 
 		else {
-			int32_t const one = 1;
+			int32_t const two = 2; /* beta and rho come from the preconditioner; on several GPUs r.r and x.x travel with r.z */
 
 			if (
-				BFMG_CHECK(cudaMemcpyAsync(&S->coarse, &one, sizeof one, cudaMemcpyHostToDevice, bfmg_stream())) < 0 ||
+				BFMG_CHECK(cudaMemcpyAsync(&S->coarse, &two, sizeof two, cudaMemcpyHostToDevice, bfmg_stream())) < 0 ||
 				BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0
 			) {
 				goto out;
@@ -1283,7 +1458,9 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 			bool const ok = (have_base
 				? BFMG_LAUNCH((k_unscale<true, true>), (n_own + kBlock - 1) / kBlock, kBlock, 0, n_own, dscale + lo, xhat + lo, (double2*) d_x + lo)
 				: BFMG_LAUNCH((k_unscale<false, true>), (n_own + kBlock - 1) / kBlock, kBlock, 0, n_own, dscale + lo, xhat + lo, (double2*) d_x + lo)) == 0 &&
+				HALO(d_x, false) &&
 				BFMG_LAUNCH(k_residual_dd<true>, G.spmv, kBlock, 0, *pat, vtop, vbot, (double2 const*) d_b, (double2 const*) d_x, dscale, r, partials, S, refinements < max_refinements ? 1 : 0) == 0 &&
+				(!shared || BFMG_LAUNCH(k_share<kShareRefine>, 1, 1, 0, S, refinements < max_refinements ? 1 : 0) == 0) &&
 				MG_PRECONDITION(true);
 
 			if (!ok) {
@@ -1317,8 +1494,9 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 			if (
 				!HALO(d_x, false) ||
 				BFMG_LAUNCH(k_residual_dd<false>, G.spmv, kBlock, 0, *pat, vtop, vbot, (double2 const*) d_b, (double2 const*) d_x, dscale, q, partials, S, 0) < 0 ||
-				!SHARE(kFoldResidual) ||
-				(shared && (BFMG_LAUNCH(k_norm2, G.vec, kBlock, 0, n_own, xhat + lo, partials, S) < 0 || !SHARE(kFoldNorm2)))
+				(shared && use_mg
+					? BFMG_LAUNCH(k_share<kShareVerify>, 1, 1, 0, S, 0) < 0
+					: (!SHARE(kFoldResidual) || (shared && (BFMG_LAUNCH(k_norm2, G.vec, kBlock, 0, n_own, xhat + lo, partials, S) < 0 || !SHARE(kFoldNorm2)))))
 			) {
 				goto out;
 			}

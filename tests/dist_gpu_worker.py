@@ -52,7 +52,7 @@ def main():
 		stats = ext.last_stats(lib)
 
 		if rank == 0:
-			sys.stderr.write(f"case {name}: {stats['cg_iterations']} iterations, coarse {stats['coarse_dim']}, peer memory {stats['uses_peer_memory']}\n")
+			sys.stderr.write(f"case {name}: {stats['cg_iterations']} iterations, {stats['mg_levels']} multigrid levels, coarse {stats['coarse_dim']}, refinements {stats['cg_restarts']}, peer memory {stats['uses_peer_memory']}\n")
 		u = case.instance.effects.copy()
 
 		want = golden[f"{name}/effects"]

@@ -1,6 +1,7 @@
 """SURVEY.md 8(f).1 - the reference's own scripts, UNMODIFIED, on this library (tools/examples_harness).
 
-Needs the reference checkout (absent on the GPU box -> skipped there) and cffi.  The harness runs the
+Needs the reference checkout and cffi: /root/reference in the build container; on the GPU box the copy of its scripts,
+pybfm sources, headers and meshes that __graft_entry__.build() stages under the git-ignored baseline/_ref/.  The harness runs the
 reference's binding generator against our headers and library, then the script with a pyglet stand-in:
   - on the compiled reference library (oracle/_ref) the scripts run to completion on the CPU and
     lepl1110.py rewrites the reference's golden U.txt / V.txt byte for byte - the harness adds nothing;
@@ -17,7 +18,11 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HARNESS = os.path.join(ROOT, "tools", "examples_harness", "run_reference_example.py")
-REFERENCE = os.environ.get("BFM_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.dirname(HARNESS))
+
+import run_reference_example  # noqa: E402
+
+REFERENCE = run_reference_example.default_reference()
 
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "pybfm")), reason="reference checkout not present")
 
@@ -57,24 +62,46 @@ def test_harness_is_transparent_on_the_reference_library(tmp_path, ref):
 	("examples/benchmark.py", ()),
 	("examples/deformation.py", ()),
 ])
-def test_reference_scripts_run_unmodified_on_our_library(script, args, tmp_path, lib):
-	proc = _run(tmp_path, script, *args)
-
+def test_reference_scripts_stop_loudly_without_a_device(script, args, tmp_path, lib):
 	if _have_gpu(lib):
-		assert proc.returncode == 0, proc.stderr[-3000:]
+		pytest.skip("a device is present: see test_reference_scripts_run_unmodified_on_the_gpu")
 
-		if script == "lepl1110.py":
-			import numpy as np
-
-			for name in ("U.txt", "V.txt"):
-				got = (tmp_path / "data" / name).read_text().split("\n", 1)[1].split()
-				want = open(os.path.join(REFERENCE, "data", name)).read().split("\n", 1)[1].split()
-				assert np.allclose([float(v) for v in got], [float(v) for v in want], rtol=2e-7, atol=1e-16)
-
-		return
+	proc = _run(tmp_path, script, *args)
 
 	# no device here: everything up to the hot path worked through the reference's own cffi binding
 	# (mesh readers, problem parser, object model, GL-free instance set-up), and the hot path said why it stopped
 	assert proc.returncode != 0
 	assert "lib.bfm_sim_run" in proc.stderr and "AssertionError" in proc.stderr
 	assert "no usable CUDA device" in proc.stderr and "no CPU fallback" in proc.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("script,args", [
+	("lepl1110.py", ("meshes/8.lepl1110", "problems/problem.txt")),
+	("examples/benchmark.py", ()),
+	("examples/deformation.py", ()),
+])
+def test_reference_scripts_run_unmodified_on_the_gpu(script, args, tmp_path, lib):
+	"""BASELINE.json north_star: "lepl1110.py, examples/deformation.py and examples/benchmark.py run unchanged" - through
+	the reference's own cffi binding (pybfm/bfm/gen_libbfm.py), on the B200; lepl1110.py must write the reference's golden
+	U.txt / V.txt to the printed 8 digits (pybfm/bfm/sim.py:33-34 -> bfm_sim_run -> ez.c:211-229)"""
+
+	assert _have_gpu(lib), lib.lib.bfmx_device_error()
+
+	proc = _run(tmp_path, script, *args)
+
+	assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-3000:]
+
+	if script == "lepl1110.py":
+		import numpy as np
+
+		for name in ("U.txt", "V.txt"):
+			got = (tmp_path / "data" / name).read_text().split("\n", 1)[1].split()
+			want = open(os.path.join(REFERENCE, "data", name)).read().split("\n", 1)[1].split()
+			assert np.allclose([float(v) for v in got], [float(v) for v in want], rtol=2e-7, atol=1e-16)
+
+	if script == "examples/benchmark.py":
+		assert "Average time taken to simulate" in proc.stdout  # examples/benchmark.py:18
+
+	if script == "examples/deformation.py":
+		assert (tmp_path / "index.html").exists()  # Bfm.export wrote the WebGL page with the displacements inlined

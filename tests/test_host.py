@@ -549,7 +549,9 @@ def test_bench_reference_arm_prints_the_contract_line():
 	assert line["impl"] == "reference" and line["unit"] == "DOF/s" and line["value"] > 0
 	assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 1
 	assert line["e2e"] == {"value": line["value"], "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-	assert line["config"]["n_dofs"] == 50025002 and line["higher_is_better"] is True
+	# the line describes the plate the reference really ran (the dense reference cannot hold the GPU arm's 50 M DOF)
+	assert line["config"]["n_dofs"] == 2 * 41 * 11 and line["config"]["cells"] == "40x10" and line["same_config"] is False
+	assert "50025002 DOF" in line["config"]["gpu_arm_workload"] and line["higher_is_better"] is True
 
 
 def test_edge_derivation_parallel_path_matches_live_reference(lib, ref, tmp_path):

@@ -34,6 +34,41 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 
 
+STAGED = os.path.join(ROOT, "baseline", "_ref", "reference")
+
+
+def default_reference() -> str:
+	"""the reference checkout: $BFM_REFERENCE, /root/reference (the build container), else the copy __graft_entry__.build()
+	staged under the git-ignored baseline/_ref/ so that it travels to the GPU box"""
+
+	for cand in (os.environ.get("BFM_REFERENCE"), "/root/reference", STAGED):
+		if cand and os.path.isdir(os.path.join(cand, "pybfm")):
+			return cand
+
+	return "/root/reference"
+
+
+def stage_reference(reference: str = "/root/reference", target: str = STAGED) -> str | None:
+	"""copy what the reference's scripts need at run time (scripts, pybfm sources, headers, meshes, problems, golden
+	U/V, shaders, web: 2 MB, no library sources) into baseline/_ref/reference.  The directory is git-ignored - nothing
+	of the reference enters this repository's history - but not gpurun-ignored, so the examples can run on the GPU box,
+	where /root/reference does not exist."""
+
+	if not os.path.isdir(os.path.join(reference, "pybfm")):
+		return None
+
+	for name in ("examples", "problems", "shaders", "web", "data", "meshes", os.path.join("pybfm", "bfm"), os.path.join("libbfm", "src", "bfm")):
+		shutil.copytree(os.path.join(reference, name), os.path.join(target, name), dirs_exist_ok=True, ignore=shutil.ignore_patterns("__pycache__", "*.so", "*.c", "*.o"))
+
+	shutil.copyfile(os.path.join(reference, "lepl1110.py"), os.path.join(target, "lepl1110.py"))
+
+	for root, dirs, files in os.walk(target):
+		for name in dirs + files:
+			os.chmod(os.path.join(root, name), 0o755 if name in dirs else 0o644)
+
+	return target
+
+
 def _link(src: str, dst: str):
 	os.makedirs(os.path.dirname(dst), exist_ok=True)
 
@@ -142,7 +177,7 @@ def run_script(workdir: str, script: str, args: list[str]) -> int:
 
 def main():
 	ap = argparse.ArgumentParser()
-	ap.add_argument("--reference", default=os.environ.get("BFM_REFERENCE", "/root/reference"))
+	ap.add_argument("--reference", default=default_reference())
 	ap.add_argument("--workdir", default=None, help="run directory (default: a fresh temporary directory)")
 	ap.add_argument("--library", default=None, help="libbfm to run on (default: ours; oracle/_ref/libbfm_ref.so checks the harness itself on the CPU)")
 	ap.add_argument("--keep", action="store_true")
