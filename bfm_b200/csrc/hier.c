@@ -40,7 +40,18 @@
 #include <omp.h>
 #endif
 
+#include <stdio.h>
+#include <time.h>
+
 #define SLICE 32
+
+/* BFM_MG_VERBOSE=1: where the time of the hierarchy build goes, on stderr */
+static double hier_clock(void) {
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double) ts.tv_sec * 1e3 + (double) ts.tv_nsec * 1e-6;
+}
+
 #define MIN_NODES_LEVEL0 3 /* nodes an aggregate of mesh nodes needs for three independent modes */
 
 static inline int64_t slot_of(int32_t const* slice_off, int32_t a, int32_t t) {
@@ -193,29 +204,66 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 
 	/* connected pieces of every bin: nodes of one bin joined through couplings of the operator.  The smaller
 	 * root wins, so the result does not depend on traversal order; on a solid mesh a bin is one piece, on
-	 * truss-like geometry a bin can cut through members that do not touch and each becomes its own aggregate */
+	 * truss-like geometry a bin can cut through members that do not touch and each becomes its own aggregate.
+	 * Unions never leave a bin, so the bins are independent: nodes are bucketed by bin (counting sort, ascending
+	 * inside a bin) and the buckets shared out over the host threads. */
 
-	for (int32_t a = lo; a < hi; a++) {
-		for (int32_t t = 0; t < L->row_len[a]; t++) {
-			int32_t const b = L->scol[slot_of(L->slice_off, a, t)];
+	{
+		int64_t const n_bins = nbx * nby;
+		int64_t* const start = calloc((size_t) n_bins + 2, sizeof *start);
+		int32_t* const order = malloc(((size_t) (hi - lo) + 1) * sizeof *order);
 
-			if (b < a && b >= lo && bin[b] == bin[a]) {
-				int32_t ra, rb;
+		if (start == NULL || order == NULL) {
+			free(start);
+			free(order);
+			free(bin);
+			free(parent);
+			free(size);
+			return 0;
+		}
 
-				FIND(a, ra);
-				FIND(b, rb);
+		for (int32_t a = lo; a < hi; a++) {
+			start[bin[a] + 2]++;
+		}
 
-				if (ra != rb) {
-					if (ra < rb) {
-						parent[rb] = ra;
-					}
+		for (int64_t b = 0; b < n_bins; b++) {
+			start[b + 2] += start[b + 1];
+		}
 
-					else {
-						parent[ra] = rb;
+		for (int32_t a = lo; a < hi; a++) {
+			order[start[bin[a] + 1]++] = a;
+		}
+
+#pragma omp parallel for schedule(dynamic, 64) if (hi - lo > 100000)
+		for (int64_t b = 0; b < n_bins; b++) {
+			for (int64_t i = start[b]; i < start[b + 1]; i++) {
+				int32_t const a = order[i];
+
+				for (int32_t t = 0; t < L->row_len[a]; t++) {
+					int32_t const c = L->scol[slot_of(L->slice_off, a, t)];
+
+					if (c < a && c >= lo && bin[c] == bin[a]) {
+						int32_t ra, rc;
+
+						FIND(a, ra);
+						FIND(c, rc);
+
+						if (ra != rc) {
+							if (ra < rc) {
+								parent[rc] = ra;
+							}
+
+							else {
+								parent[ra] = rc;
+							}
+						}
 					}
 				}
 			}
 		}
+
+		free(start);
+		free(order);
 	}
 
 	/* pieces below min_nodes join a piece they are coupled to (a few passes: a chain of tiny pieces needs more
@@ -809,8 +857,14 @@ bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, bfmi
 			goto fail;
 		}
 
+		double const t_agg = hier_clock();
 		int32_t const n_agg = aggregate_level(L, target, l == 0 ? MIN_NODES_LEVEL0 : 1, L->agg);
 
+		if (getenv("BFM_MG_VERBOSE") != NULL) {
+			fprintf(stderr, "[hier] level %d: %d nodes (%d own) -> %d aggregates in %.1f ms\n", l, L->n, n_own, n_agg, hier_clock() - t_agg);
+		}
+
+		double const t_rest = hier_clock();
 		bfmi_hier_level_t* const N = &h->level[l + 1];
 
 		N->dofs = 3;
@@ -1204,6 +1258,10 @@ bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, bfmi
 		}
 
 		n_glob = n_glob_next;
+
+		if (getenv("BFM_MG_VERBOSE") != NULL) {
+			fprintf(stderr, "[hier] level %d: transfer + pattern of level %d (%s, %lld nodes over all ranks) in %.1f ms\n", l, l + 1, N->distributed ? "distributed" : "replicated", (long long) n_glob, hier_clock() - t_rest);
+		}
 
 		if (n_glob <= dense_limit) {
 			if (N->distributed) {

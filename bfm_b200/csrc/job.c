@@ -1181,14 +1181,36 @@ int bfmx_job_create_batch(bfmx_job_t** out, bfm_sim_t** sims, size_t n_sims) {
 
 	double const t0 = now_ms();
 
-	job->plan = bfmi_plan_for_mesh(state, cm);
+	/* examples/benchmark.py-style loops run the same batch again and again: the symbolic plan of the combined mesh
+	 * (and its device mirror) is kept as long as the combined connectivity is the same - 36 ms -> a few ms per call
+	 * at 1024 x 335 nodes.  The combined mesh object itself dies with the job, so the key is its content. */
 
-	if (job->plan == NULL || bfmi_plan_upload(state, job->plan) < 0) {
-		goto fail;
+	static bfmi_plan_t* batch_plan;
+	static uint64_t batch_hash;
+
+	uint64_t const hash = bfmi_mesh_hash(cm);
+
+	if (batch_plan != NULL && batch_hash == hash && (size_t) batch_plan->nb == nb_total && batch_plan->n_elems == ne_total && batch_plan->kind == (int) kind) {
+		job->plan = batch_plan;
+		bfmi_plan_retain(job->plan);
 	}
 
-	job->stats.ms_plan = (float) (now_ms() - t0);
-	job->stats.h2d_bytes += ((size_t) job->plan->n_slices + 1 + 2 * (size_t) job->plan->nb + 2 * (size_t) job->plan->n_slots + 1 + (size_t) job->plan->n_ctr + job->plan->n_elems * (size_t) job->plan->kind) * 4;
+	else {
+		job->plan = bfmi_plan_for_mesh(state, cm);
+
+		if (job->plan == NULL || bfmi_plan_upload(state, job->plan) < 0) {
+			goto fail;
+		}
+
+		job->stats.ms_plan = (float) (now_ms() - t0);
+		job->stats.h2d_bytes += ((size_t) job->plan->n_slices + 1 + 2 * (size_t) job->plan->nb + 2 * (size_t) job->plan->n_slots + 1 + (size_t) job->plan->n_ctr + job->plan->n_elems * (size_t) job->plan->kind) * 4;
+
+		bfmi_plan_release(batch_plan);
+		batch_plan = job->plan;
+		batch_hash = hash;
+		bfmi_plan_retain(batch_plan);
+	}
+
 	job->pat = job->plan->dev;
 
 	job->h_slice_tab = calloc((size_t) job->plan->n_slices + 1, sizeof *job->h_slice_tab);
