@@ -640,12 +640,16 @@ def main():
 		t0 = time.perf_counter()
 		assert not lib.bfmx_timer_start(1)
 		h2d = d2h = 0
+		stages = {"ms_plan": 0.0, "ms_upload": 0.0, "ms_assemble": 0.0, "ms_bc": 0.0, "ms_solve": 0.0, "ms_download": 0.0}
 
 		for _ in range(args.steps):
 			case.sim.run()
 			st = ext.last_stats(binding)
 			h2d += st["h2d_bytes"]
 			d2h += st["d2h_bytes"]
+
+			for key in stages:
+				stages[key] += st[key] / args.steps
 
 		# the displacements are on the host now; read them like pybfm does
 		checksum = float(np.abs(workloads.effects_view(case.instance)).max())
@@ -666,6 +670,7 @@ def main():
 			"first_call_ms": first_call_ms,
 			"symbolic_setup_ms_once_per_mesh": symbolic_ms,
 			"max_abs_displacement": checksum,
+			"stages_ms": stages | {"host_side_rest": ms_e2e - sum(stages.values())},  # rank 0's stages; the rest is host work of job creation (cache look-ups, BC work lists)
 		}
 
 	cpu = None

@@ -394,6 +394,7 @@ int bfm_instance_destroy(bfm_instance_t* instance) {
 	bfm_state_t* const state = instance->state;
 
 	if (instance->effects != NULL) {
+		bfmg_host_unpin(instance->effects); /* bfm_sim_run page-locks large result buffers in place */
 		state->free(instance->effects);
 	}
 

@@ -71,6 +71,12 @@ __device__ __forceinline__ double2 ld_stream(double2 const* p) {
 	return v;
 }
 
+__device__ __forceinline__ float2 ld_stream(float2 const* p) {
+	float2 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+	return v;
+}
+
 __device__ __forceinline__ double ld_stream(double const* p) {
 	double v;
 	asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));

@@ -1402,20 +1402,33 @@ static uint64_t hash_coords(double const* coords, size_t count) {
 	size_t const chunk = 1 << 16;
 	size_t const n_chunks = (count + chunk - 1) / chunk;
 	uint64_t total = 0x51ed270b7a2c3f11ull ^ count;
+	uint64_t const* const bits = (uint64_t const*) coords; /* the bit patterns: -0.0 and 0.0 are different meshes here, harmlessly */
 
 #pragma omp parallel for schedule(static) reduction(^ : total) if (n_chunks > 16)
 	for (size_t c = 0; c < n_chunks; c++) {
 		size_t const end = (c + 1) * chunk < count ? (c + 1) * chunk : count;
-		uint64_t hsh = 0xcbf29ce484222325ull + c;
+		uint64_t h0 = 0xcbf29ce484222325ull + c, h1 = 0x84222325cbf29ce4ull ^ c, h2 = 0x9e3779b97f4a7c15ull + 3 * c, h3 = 0xc2b2ae3d27d4eb4full ^ (c << 7);
+		size_t i = c * chunk;
 
-		for (size_t i = c * chunk; i < end; i++) {
-			uint64_t bits;
-			memcpy(&bits, &coords[i], sizeof bits);
-			hsh = (hsh ^ bits) * 0x100000001b3ull;
-			hsh ^= hsh >> 31;
+		for (; i + 4 <= end; i += 4) { /* four independent chains: memory speed, not multiplier latency */
+			h0 = (h0 ^ bits[i + 0]) * 0x100000001b3ull;
+			h1 = (h1 ^ bits[i + 1]) * 0x9e3779b97f4a7c15ull;
+			h2 = (h2 ^ bits[i + 2]) * 0xc2b2ae3d27d4eb4full;
+			h3 = (h3 ^ bits[i + 3]) * 0x165667b19e3779f9ull;
+			h0 ^= h0 >> 31, h1 ^= h1 >> 29, h2 ^= h2 >> 27, h3 ^= h3 >> 33;
 		}
 
-		total ^= hsh * (2 * c + 1);
+		for (; i < end; i++) {
+			h0 = (h0 ^ bits[i]) * 0x100000001b3ull;
+			h0 ^= h0 >> 31;
+		}
+
+		uint64_t hsh = (h0 * 31 + h1) * 0x100000001b3ull;
+
+		hsh = ((hsh ^ (hsh >> 32)) * 31 + h2) * 0x9e3779b97f4a7c15ull;
+		hsh = ((hsh ^ (hsh >> 29)) * 31 + h3) * 0xc2b2ae3d27d4eb4full;
+
+		total ^= (hsh ^ (hsh >> 31)) * (2 * c + 1);
 	}
 
 	return total;

@@ -16,6 +16,7 @@
 #include "internal.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -364,26 +365,61 @@ static int affected_rows(bfmi_plan_t const* plan, bc_op_t* op) {
 static int op_dirichlet_xy(bfm_mesh_t const* gmesh, bfm_condition_t const* cond, bc_op_t* op) {
 	size_t const nn = gmesh->n_nodes;
 	int32_t const shift = cond->kind == BFM_CONDITION_KIND_DIRICHLET_X ? 0 : 1;
-	size_t count = 0;
+	size_t count = 0, cap = 1024;
 
-	for (size_t j = 0; j < nn; j++) {
-		count += cond->nodes[j];
-	}
+	/* the mask is one byte per node and almost empty on a large mesh (25 MB for a few thousand clamped nodes at
+	 * 50 M DOF): eight bytes at a time, one pass */
 
 	op->kind = OP_DIRICHLET;
-	op->dofs = malloc((count + 1) * sizeof *op->dofs);
-	op->vals = malloc((count + 1) * sizeof *op->vals);
+	op->dofs = malloc(cap * sizeof *op->dofs);
 
-	if (op->dofs == NULL || op->vals == NULL) {
+	if (op->dofs == NULL) {
 		return -1;
 	}
 
-	for (size_t j = 0; j < nn; j++) {
-		if (cond->nodes[j]) {
-			op->dofs[op->n_dofs] = (int32_t) (2 * j) + shift;
-			op->vals[op->n_dofs++] = cond->value;
+	for (size_t j = 0; j < nn;) {
+		if (j + 8 <= nn) {
+			uint64_t word;
+
+			memcpy(&word, &cond->nodes[j], sizeof word);
+
+			if (word == 0) {
+				j += 8;
+				continue;
+			}
+		}
+
+		size_t const end = j + 8 <= nn ? j + 8 : nn;
+
+		for (; j < end; j++) {
+			if (cond->nodes[j]) {
+				if (count == cap) {
+					int32_t* const grown = realloc(op->dofs, cap * 2 * sizeof *op->dofs);
+
+					if (grown == NULL) {
+						return -1;
+					}
+
+					op->dofs = grown;
+					cap *= 2;
+				}
+
+				op->dofs[count++] = (int32_t) (2 * j) + shift;
+			}
 		}
 	}
+
+	op->vals = malloc((count + 1) * sizeof *op->vals);
+
+	if (op->vals == NULL) {
+		return -1;
+	}
+
+	for (size_t i = 0; i < count; i++) {
+		op->vals[i] = cond->value;
+	}
+
+	op->n_dofs = (int32_t) count;
 
 	return 0;
 }
@@ -793,6 +829,10 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 	job->mesh = mesh;
 
 	double const t0 = now_ms();
+	bool const verbose = getenv("BFM_JOB_VERBOSE") != NULL;
+	double t_mark = t0;
+
+#define MARK(what) do { if (verbose) { double const now_ = now_ms(); fprintf(stderr, "[job] %-28s %8.2f ms\n", (what), now_ - t_mark); t_mark = now_; } } while (0)
 
 	/* several GPUs: this rank assembles and solves the local mesh of its row block (partition.c) */
 
@@ -806,11 +846,15 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 		job->mesh = &job->part->local;
 	}
 
+	MARK("partition (cache look-up)");
+
 	job->plan = bfmi_plan_for_mesh(state, job->mesh);
 
 	if (job->plan == NULL) {
 		goto fail;
 	}
+
+	MARK("plan (cache look-up)");
 
 	bool const fresh = !job->plan->on_device;
 
@@ -824,9 +868,19 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 		job->stats.h2d_bytes += ((size_t) job->plan->n_slices + 1 + 2 * (size_t) job->plan->nb + 2 * (size_t) job->plan->n_slots + 1 + (size_t) job->plan->n_ctr + job->plan->n_elems * (size_t) job->plan->kind) * 4;
 	}
 
-	if (fill_tables(state, kind, instance, job->mesh, n_forces, forces, &job->tab, &job->h_nforce, n_forces, job->mesh->n_nodes, 0) < 0 || build_ops(job) < 0) {
+	MARK("plan upload");
+
+	if (fill_tables(state, kind, instance, job->mesh, n_forces, forces, &job->tab, &job->h_nforce, n_forces, job->mesh->n_nodes, 0) < 0) {
 		goto fail;
 	}
+
+	MARK("shape / force tables");
+
+	if (build_ops(job) < 0) {
+		goto fail;
+	}
+
+	MARK("boundary-condition work lists");
 
 	job->pat = job->plan->dev;
 
@@ -864,6 +918,8 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 	if (job_alloc_device(job, n_forces) < 0) {
 		goto fail;
 	}
+
+	MARK("device buffers");
 
 	/* coarse level of the solver for meshes the one-CTA path does not take.  How many aggregates: iterations fall
 	 * like 1 / sqrt(n_agg) while inverting E grows like n_agg^3 and applying E^-1 like n_agg^2 per iteration;
@@ -923,6 +979,9 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 			}
 		}
 	}
+
+	MARK("hierarchy (cache look-up)");
+#undef MARK
 
 	job->stats.n_dofs = 2 * mesh->n_nodes;
 	job->stats.n_dofs_owned = 2 * (size_t) (job->pat.row_hi - job->pat.row_lo);
@@ -1441,6 +1500,10 @@ int bfmx_job_upload(bfmx_job_t* job) {
 	int const t0 = bfmg_tick();
 	int rv = 0;
 
+	if (nb * 2 * sizeof(double) >= ((size_t) 32 << 20) && job->n_sys == 0) {
+		bfmg_host_pin(job->mesh->coords, nb * 2 * sizeof(double)); /* lives as long as the mesh: pinned once, unpinned by its destroy */
+	}
+
 	rv |= UP(job->d_coords, job->mesh->coords, nb * 2, double);
 
 	if (job->h_nforce != NULL) {
@@ -1658,6 +1721,10 @@ int bfmx_job_download(bfmx_job_t* job) {
 	}
 
 	/* effects[node * dim + k] = x[node * dim + k] (sim.c:127-131): same interleaving, one copy */
+
+	if (bytes >= ((size_t) 32 << 20)) {
+		bfmg_host_pin(job->instance->effects, bytes); /* lives as long as the instance: pinned once, unpinned by its destroy */
+	}
 
 	if (bfmg_download(job->instance->effects, d_src, bytes) < 0) {
 		return BFMI_FAIL(job->state, "download failed: %s", bfmg_last_error());

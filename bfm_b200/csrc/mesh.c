@@ -31,6 +31,8 @@ int bfm_mesh_destroy(bfm_mesh_t* mesh) {
 	bfmi_part_forget(mesh); /* ... and its row partition */
 	bfmi_coarse_forget(mesh); /* ... and the solver's aggregates */
 
+	bfmg_host_unpin(mesh->coords); /* bfm_sim_run page-locks large coordinate arrays in place */
+
 	state->free(mesh->coords);
 	state->free(mesh->elems);
 	state->free(mesh->edges);

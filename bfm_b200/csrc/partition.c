@@ -91,6 +91,8 @@ static void part_free(bfmi_part_t* part) {
 	bfmi_plan_forget(&part->local);
 	bfmg_free(part->d_send_idx);
 
+	bfmg_host_unpin(part->local.coords);
+
 	free(part->l2g);
 	free(part->elem_l2g);
 	free(part->local.coords);

@@ -86,7 +86,8 @@ def terrain_stand_in(path: str):
 	for k in range(nz):
 		for i in range(nx):
 			x = -3.0 + 6.0 * i / (nx - 1)
-			y = -1.2 + 0.9 * (x / 3.0) ** 2  # a valley: the bridge's feet sit below it at both ends
+			y = -0.45 + 0.12 * x ** 2  # a valley whose flanks rise above the feet of bridge-dam.obj at both ends (27 clamped nodes):
+			                           # with no node below the terrain the script would set up a singular, unconstrained system
 			z = -0.03 + 0.03 * k
 			lines.append(f"v {x:.6f} {y:.6f} {z:.6f}")
 
