@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(kBlock) k_assemble(
 	double2* __restrict__ vtop, double2* __restrict__ vbot, double2* __restrict__ bvec,
 	bfmg_asm_tables_t const* __restrict__ tabs, int32_t const* __restrict__ slice_tab
 ) {
+	pdl_sync();
+
 	int const lane = threadIdx.x & (kWarp - 1);
 	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
 	int const n_warps = gridDim.x * blockDim.x / kWarp;
@@ -222,6 +224,8 @@ __global__ void __launch_bounds__(kBlock) k_assemble(
  * ---------------------------------------------------------------------------------------------- */
 
 __global__ void k_bc_mark(int32_t* __restrict__ stamp, double* __restrict__ cval, int32_t epoch, int32_t const* __restrict__ dofs, double const* __restrict__ vals, int n) {
+	pdl_sync();
+
 	int const i = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (i < n) {
@@ -234,6 +238,8 @@ __global__ void __launch_bounds__(kBlock) k_bc_dirichlet(
 	const __grid_constant__ bfmg_pattern_t P, double2* __restrict__ vtop, double2* __restrict__ vbot, double2* __restrict__ bvec,
 	int32_t const* __restrict__ stamp, double const* __restrict__ cval, int32_t epoch, int32_t const* __restrict__ rows, int n_rows
 ) {
+	pdl_sync();
+
 	int const i = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (i >= n_rows) {
@@ -305,6 +311,8 @@ __global__ void __launch_bounds__(kBlock) k_bc_dirichlet(
 }
 
 __global__ void k_bc_add(double* __restrict__ bvec, int32_t const* __restrict__ group_dof, int32_t const* __restrict__ group_ptr, double const* __restrict__ add, int n_groups) {
+	pdl_sync();
+
 	int const i = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (i >= n_groups) {

@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(THREADS) k_pcg_cta(
 	double2 const* __restrict__ bhat, double2 const* __restrict__ dscale, double2* __restrict__ x_out,
 	bfmg_batch_range_t const* __restrict__ ranges, bfmg_batch_status_t* __restrict__ status, double tol, int max_iter
 ) {
+	pdl_sync();
+
 	extern __shared__ double2 smem[];
 	__shared__ double part[2][THREADS / kWarp];
 

@@ -36,6 +36,8 @@ struct CoarseWork {
 };
 
 __global__ void k_wrow(int nb, double2 const* __restrict__ dscale, double2 const* __restrict__ wgeom, float4* __restrict__ wrow) {
+	pdl_sync();
+
 	int const i = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (i < nb) {
@@ -47,6 +49,8 @@ __global__ void k_wrow(int nb, double2 const* __restrict__ dscale, double2 const
 
 /* gpart[3 g + k] = sum over the owned nodes a of aggregate g of (R_a^T S_a v_a)_k; one CTA per aggregate */
 __global__ void __launch_bounds__(kBlock) k_restrict(bfmg_coarse_t C, float4 const* __restrict__ wrow, double2 const* __restrict__ v, double* __restrict__ gpart, Scalars* S, bool obey_done) {
+	pdl_sync();
+
 	if (obey_done && S->done) {
 		return;
 	}
@@ -155,6 +159,8 @@ __global__ void __launch_bounds__(kBlock) k_restrict(bfmg_coarse_t C, float4 con
  * slot nc holding the ranks' shares of r.r, folded here too when FOLD_RR (k_fold<kFoldRr>'s job otherwise) */
 template <bool FOLD_RR>
 __global__ void k_coarse_fold(int nc, int n_real, int world, double const* __restrict__ ggath, double* __restrict__ g, Scalars* S, bool obey_done) {
+	pdl_sync();
+
 	if (obey_done && S->done) {
 		return;
 	}
@@ -210,6 +216,8 @@ constexpr int kCoarseRows = kWarpsPerBlock / 4;
  * stores its part of mu into every peer's mailbox; k_coarse_finish then does the scalar part */
 template <bool FIRST, bool DIST>
 __global__ void __launch_bounds__(kBlock) k_coarse_apply(int nc, int row0, double const* __restrict__ Einv, double const* __restrict__ g, double* __restrict__ mu, double* __restrict__ partials, Scalars* S) {
+	pdl_sync();
+
 	if (!FIRST && S->done) {
 		return;
 	}
@@ -300,6 +308,8 @@ __global__ void __launch_bounds__(kBlock) k_coarse_apply(int nc, int row0, doubl
  * the scalars: rz = r.r + g.mu, beta, rho.  One CTA. */
 template <bool FIRST>
 __global__ void __launch_bounds__(kBlock) k_coarse_finish(int nc, double const* __restrict__ g, double* __restrict__ mu, Scalars* S) {
+	pdl_sync();
+
 	if (!FIRST && S->done) {
 		return;
 	}
@@ -350,6 +360,8 @@ __global__ void __launch_bounds__(kBlock) k_coarse_finish(int nc, double const* 
 
 /* p = r + W mu + beta p */
 __global__ void __launch_bounds__(kBlock) k_update_p_coarse(int n2, int row0, bfmg_coarse_t C, float4 const* __restrict__ wrow, double const* __restrict__ mu, double2 const* __restrict__ r, double2* __restrict__ p, Scalars const* S, bool obey_done) {
+	pdl_sync();
+
 	if (obey_done && S->done) {
 		return;
 	}
@@ -381,6 +393,8 @@ __global__ void __launch_bounds__(kBlock) k_update_p_coarse(int n2, int row0, bf
 
 /* v = mode m of every aggregate of colour c, 0 elsewhere (all local rows, ghosts included: no exchange needed) */
 __global__ void k_probe_vector(int nb, bfmg_coarse_t C, float4 const* __restrict__ wrow, int color, int mode, double2* __restrict__ v) {
+	pdl_sync();
+
 	int const a = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (a >= nb) {
@@ -401,6 +415,8 @@ __global__ void k_probe_vector(int nb, bfmg_coarse_t C, float4 const* __restrict
 
 /* g = W^T A^ (modes m of colour c): rows 3h..3h+2 are column 3 src + m of E, src = the colour-c aggregate near h */
 __global__ void k_probe_scatter(bfmg_coarse_t C, int color, int mode, double const* __restrict__ g, double* __restrict__ E) {
+	pdl_sync();
+
 	int const h = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (h >= C.n_agg) {
@@ -420,6 +436,8 @@ __global__ void k_probe_scatter(bfmg_coarse_t C, int color, int mode, double con
 
 /* identity on the padding rows (3 n_agg .. nc) */
 __global__ void k_coarse_pad(bfmg_coarse_t C, double* __restrict__ E) {
+	pdl_sync();
+
 	int const i = 3 * C.n_agg + blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (i < C.nc) {
@@ -433,6 +451,8 @@ __global__ void k_coarse_pad(bfmg_coarse_t C, double* __restrict__ E) {
  * E_*K = -E_*K P;  E_KK = P.  After the last block E holds its inverse. */
 
 __global__ void __launch_bounds__(1024) k_gj_diag(int n, int k, double const* __restrict__ E, double* __restrict__ P, int32_t* bad) {
+	pdl_sync();
+
 	__shared__ double a[kGjBlock][kGjBlock + 1];
 
 	int const i = threadIdx.x / kGjBlock;
@@ -474,6 +494,8 @@ __global__ void __launch_bounds__(1024) k_gj_diag(int n, int k, double const* __
 
 /* row panel: E[K, J] = P * E[K, J] for every column block J != k; one CTA per J */
 __global__ void __launch_bounds__(1024) k_gj_row(int n, int k, int lim, double* __restrict__ E, double const* __restrict__ P) {
+	pdl_sync();
+
 	int const J = blockIdx.x;
 
 	if (J == k || J * kGjBlock >= lim) {
@@ -520,6 +542,8 @@ __device__ __forceinline__ double const* gj_panel(Scalars const* S, GjPanel cons
  * (A 128 x 128 / 8 x 8-per-thread variant was measured SLOWER - 168 registers, one CTA per SM: 620 us against 380 us
  * per launch at n = 6304 - so the small tile stays.) */
 __global__ void __launch_bounds__(256, 4) k_gj_update(int n, int k, int lim, double* __restrict__ E, int row_lo, int row_hi, GjPanel G, Scalars* S) {
+	pdl_sync();
+
 	__shared__ double col[64][kGjBlock + 1]; /* E[I, K] */
 	__shared__ double row[kGjBlock][64 + 1]; /* R[K, J] */
 
@@ -604,6 +628,8 @@ __global__ void __launch_bounds__(256, 4) k_gj_update(int n, int k, int lim, dou
  * One CTA per row block from row_lo on.  Distributed: P comes from the mailbox, the owner's "not positive
  * definite" verdict is taken over, and the last CTA acknowledges the step to every peer. */
 __global__ void __launch_bounds__(1024) k_gj_col(int n, int k, int lim, double* __restrict__ E, double const* __restrict__ Plocal, int row_lo, GjPanel G, int32_t* bad, Scalars* S) {
+	pdl_sync();
+
 	int const I = row_lo / kGjBlock + blockIdx.x;
 
 	__shared__ double p[kGjBlock][kGjBlock + 1];
@@ -683,6 +709,8 @@ __global__ void __launch_bounds__(1024) k_gj_col(int n, int k, int lim, double* 
 /* distributed: the owner of pivot block k stores R = E[K, :] (already multiplied by P), P and its verdict into
  * every rank's panel buffer of this round, then publishes the round */
 __global__ void __launch_bounds__(kBlock) k_gj_bcast(int n, int k, double const* __restrict__ E, double const* __restrict__ P, int32_t const* __restrict__ bad, GjPanel G, Scalars* S) {
+	pdl_sync();
+
 	P2p const& X = S->X;
 
 	/* the buffer of this parity was last read in step k - 2: every rank must have acknowledged it */
@@ -730,6 +758,8 @@ __global__ void __launch_bounds__(kBlock) k_gj_bcast(int n, int k, double const*
 }
 
 __global__ void k_gj_ack_all(uint64_t rounds, Scalars* S) {
+	pdl_sync();
+
 	P2p const& X = S->X;
 
 	if (threadIdx.x < X.world) {

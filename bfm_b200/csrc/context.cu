@@ -162,6 +162,17 @@ cudaStream_t bfmg_stream() {
 	return G.stream;
 }
 
+bool bfmg_pdl() {
+	static int enabled = -1;
+
+	if (enabled < 0) {
+		char const* const env = getenv("BFM_PDL");
+		enabled = env != nullptr && atoi(env) != 0 ? 1 : 0; /* off unless asked for: measured, it buys nothing inside a replayed graph */
+	}
+
+	return enabled == 1;
+}
+
 void* bfmg_pinned() {
 	return G.pinned;
 }

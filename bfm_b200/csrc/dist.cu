@@ -295,6 +295,8 @@ void teardown_p2p() {
 
 /* sendbuf[i] = v[send_idx[i]] : the owned entries the neighbours ghost, grouped by neighbour */
 __global__ void k_halo_pack(double2 const* __restrict__ v, int32_t const* __restrict__ send_idx, double2* __restrict__ sendbuf, int n) {
+	pdl_sync();
+
 	int const i = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (i < n) {

@@ -32,10 +32,44 @@ BFMG_HIDDEN int bfmg_dist_p2p_failed();
 
 #define BFMG_CHECK(call) bfmg_check((call), #call, __FILE__, __LINE__)
 
+/* Programmatic dependent launch (BFM_PDL=1; off by default).  A multigrid-preconditioned iteration is a string of
+ * ~200 kernels, most of them a few microseconds long, so what they cost is the gap between the end of one and the
+ * start of the next.  Every kernel of this library begins with pdl_sync() - it lets the NEXT kernel of the stream be
+ * scheduled at once (griddepcontrol.launch_dependents, PREEXIT in SASS) and then waits until the PREVIOUS one has
+ * finished and its writes are visible (griddepcontrol.wait, ACQBULK) - and with BFM_PDL=1 it is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, so that its launch latency overlaps the predecessor's execution;
+ * stream capture keeps the edges.  Nothing may be read before pdl_sync(): it is the first statement of every kernel,
+ * and a no-op in a classic launch.  Measured on the B200 (profiles/r2_summary.md): 915 vs 914 ms per 50 M-DOF step,
+ * 57.4 vs 57.1 ms at 2 M DOF - inside a replayed CUDA graph the launches are already back to back, so the default
+ * stays the classic launch. */
+__device__ __forceinline__ void pdl_sync() {
+	asm volatile("griddepcontrol.launch_dependents;");
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+BFMG_HIDDEN bool bfmg_pdl(); /* context.cu: programmatic launches on (default) */
+
+template <typename... Params, typename... Args>
+static inline cudaError_t bfmg_launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+	cudaLaunchConfig_t config = {};
+	cudaLaunchAttribute attribute[1];
+
+	attribute[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attribute[0].val.programmaticStreamSerializationAllowed = 1;
+
+	config.gridDim = grid;
+	config.blockDim = block;
+	config.dynamicSmemBytes = smem;
+	config.stream = bfmg_stream();
+	config.attrs = attribute;
+	config.numAttrs = bfmg_pdl() ? 1 : 0;
+
+	return cudaLaunchKernelEx(&config, kernel, static_cast<Params>(args)...);
+}
+
 /* launch on the library stream, count it, report configuration errors */
 #define BFMG_LAUNCH(kernel, grid, block, smem, ...)                       \
-	(bfmg_count_launch(1), (kernel)<<<(grid), (block), (smem), bfmg_stream()>>>(__VA_ARGS__), \
-	 bfmg_check(cudaGetLastError(), #kernel, __FILE__, __LINE__))
+	(bfmg_count_launch(1), bfmg_check(bfmg_launch((kernel), dim3(grid), dim3(block), (smem), __VA_ARGS__), #kernel, __FILE__, __LINE__))
 
 constexpr int kWarp = 32;
 constexpr int kBlock = 256;                  /* 8 warps per CTA for every kernel in this library */

@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(kBlock) k_spmv_mg(
 	const __grid_constant__ bfmg_pattern_t P, float2 const* __restrict__ vtop, float2 const* __restrict__ vbot,
 	double2 const* __restrict__ v, double2 const* __restrict__ g, double2* __restrict__ out, double const* __restrict__ omega_p, double* __restrict__ partials, Scalars* S
 ) {
+	pdl_sync();
+
 	if (!FIRST && S->done) {
 		return;
 	}
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_mg(
 
 		double y0 = 0, y1 = 0;
 
-#pragma unroll 4
+#pragma unroll 8
 		for (int slot = beg + lane; slot < end; slot += kWarp) {
 			int const col = ld_stream(&P.scol[slot]);
 			float2 const t = ld_stream(&vtop[slot]);
@@ -148,6 +150,8 @@ __global__ void __launch_bounds__(kBlock) k_spmv_mg(
  * PCG does not notice, while the two products stream 20 instead of 36 bytes per block (CG's own product, the Galerkin
  * operators and the refinement residual use the FP64 values) */
 __global__ void __launch_bounds__(kBlock) k_mg_gersh0(const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ vtop, double2 const* __restrict__ vbot, float2* __restrict__ ftop, float2* __restrict__ fbot, unsigned long long* __restrict__ gersh) {
+	pdl_sync();
+
 	int const lane = threadIdx.x & (kWarp - 1);
 	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
 	int const n_warps = gridDim.x * blockDim.x / kWarp;
@@ -187,6 +191,8 @@ __global__ void __launch_bounds__(kBlock) k_mg_gersh0(const __grid_constant__ bf
 /* several GPUs: all[r * stride + l] holds rank r's bound of level l (and, at index BFMG_MG_MAX_LEVELS, its "bad" flag):
  * every rank takes the maximum, so that all ranks smooth with the same damping and take the same decision */
 __global__ void k_mg_omega(int n_levels, double factor, MgDev* D, double const* __restrict__ all, int world, int stride) {
+	pdl_sync();
+
 	int const l = threadIdx.x;
 
 	if (l < n_levels) {
@@ -211,6 +217,8 @@ __global__ void k_mg_omega(int n_levels, double factor, MgDev* D, double const* 
 
 /* this rank's bounds and flag as doubles, for the all-gather */
 __global__ void k_mg_bounds(MgDev const* D, int32_t const* bad, double* __restrict__ out) {
+	pdl_sync();
+
 	int const l = threadIdx.x;
 
 	if (l < BFMG_MG_MAX_LEVELS) {
@@ -225,6 +233,8 @@ __global__ void k_mg_bounds(MgDev const* D, int32_t const* bad, double* __restri
 /* several GPUs, first replicated level: every rank computed the rows of its own aggregates (the others are zero);
  * the operator is their sum, taken in rank order (exact: one non-zero contributor per entry) */
 __global__ void k_mg_sum_ranks(size_t count, int world, double const* __restrict__ all, double* __restrict__ out) {
+	pdl_sync();
+
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < count; i += (size_t) gridDim.x * blockDim.x) {
 		double t = 0;
 
@@ -244,6 +254,8 @@ __global__ void k_mg_sum_ranks(size_t count, int world, double const* __restrict
  * positive definite), double above.  dsc = D^-1/2 of the FINE level (level 0: solver.cu's dscale). */
 template <int NB, typename PT>
 __global__ void k_mg_tentative(bfmg_mg_level_t L, double const* __restrict__ dsc, PT* __restrict__ pval) {
+	pdl_sync();
+
 	int const a = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (a >= L.n) {
@@ -282,6 +294,8 @@ __global__ void k_mg_tentative(bfmg_mg_level_t L, double const* __restrict__ dsc
 /* P <- P D_c^-1/2 once the coarse level's scaling is known */
 template <int NB, typename PT>
 __global__ void k_mg_pscale(bfmg_mg_level_t L, double const* __restrict__ dsc_coarse, PT* __restrict__ pval) {
+	pdl_sync();
+
 	int const e = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (e >= L.n_p) {
@@ -356,6 +370,8 @@ __device__ __forceinline__ void d_mg_restrict(bfmg_mg_level_t const& L, PT const
 
 template <int NB, typename PT>
 __global__ void __launch_bounds__(kBlock) k_mg_restrict(bfmg_mg_level_t L, PT const* __restrict__ pval, double const* __restrict__ v, double* __restrict__ out, int n_out, Scalars const* S, bool obey_done) {
+	pdl_sync();
+
 	if (obey_done && S->done) {
 		return;
 	}
@@ -396,6 +412,8 @@ __device__ __forceinline__ void d_mg_prolong(bfmg_mg_level_t const& L, int row0,
 
 template <int NB, typename PT, bool ADD>
 __global__ void __launch_bounds__(kBlock) k_mg_prolong(bfmg_mg_level_t L, int row0, int n_rows, PT const* __restrict__ pval, double const* __restrict__ mu, double const* __restrict__ g, double* __restrict__ z, double const* __restrict__ omega_p, Scalars const* S, bool obey_done) {
+	pdl_sync();
+
 	if (obey_done && S->done) {
 		return;
 	}
@@ -411,6 +429,8 @@ __global__ void __launch_bounds__(kBlock) k_mg_prolong(bfmg_mg_level_t L, int ro
  * (a00,a01) / (a10,a11); above: nine planes).  DENSE: the result goes into the row-major n_dense x n_dense matrix. */
 template <int NB, typename PT, bool DENSE>
 __global__ void __launch_bounds__(kBlock) k_mg_rap(bfmg_mg_level_t L, bfmg_mg_level_t N, double const* __restrict__ fine, PT const* __restrict__ pval, double* __restrict__ val, int n_dense) {
+	pdl_sync();
+
 	int const lane = threadIdx.x & (kWarp - 1);
 	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
 	int const n_warps = gridDim.x * blockDim.x / kWarp;
@@ -520,6 +540,8 @@ __global__ void __launch_bounds__(kBlock) k_mg_rap(bfmg_mg_level_t L, bfmg_mg_le
 
 /* dsc = 1 / sqrt(diagonal); a diagonal that is not positive marks the hierarchy unusable */
 __global__ void k_blk_diag(bfmg_mg_level_t N, double const* __restrict__ val, double* __restrict__ dsc, MgDev* D) {
+	pdl_sync();
+
 	int const I = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (I >= N.row_hi) {
@@ -545,6 +567,8 @@ __global__ void k_blk_diag(bfmg_mg_level_t N, double const* __restrict__ val, do
 
 /* A <- D^-1/2 A D^-1/2 in place, and the largest absolute row sum of the result */
 __global__ void __launch_bounds__(kBlock) k_blk_scale(bfmg_mg_level_t N, double* __restrict__ val, double const* __restrict__ dsc, unsigned long long* __restrict__ gersh) {
+	pdl_sync();
+
 	int const lane = threadIdx.x & (kWarp - 1);
 	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
 	int const n_warps = gridDim.x * blockDim.x / kWarp;
@@ -610,7 +634,7 @@ __device__ __forceinline__ void d_blk_spmv(bfmg_mg_level_t const& N, double cons
 
 		double y0 = 0, y1 = 0, y2 = 0;
 
-#pragma unroll 2
+#pragma unroll 4
 		for (int slot = __ldg(&N.slice_off[slice]) + lane; slot < end; slot += kWarp) {
 			int const col = ld_stream(&N.scol[slot]);
 			double const x0 = ldv<CG>(&v[3 * (size_t) col + 0]);
@@ -650,6 +674,8 @@ __device__ __forceinline__ void d_blk_spmv(bfmg_mg_level_t const& N, double cons
 
 template <MgMode MODE>
 __global__ void __launch_bounds__(kBlock) k_blk_spmv(bfmg_mg_level_t N, double const* __restrict__ val, double const* __restrict__ v, double const* __restrict__ g, double* __restrict__ out, double const* __restrict__ omega_p, Scalars const* S, bool obey_done) {
+	pdl_sync();
+
 	if (obey_done && S->done) {
 		return;
 	}
@@ -706,6 +732,8 @@ __device__ __forceinline__ void d_dense_apply(int nc, double const* __restrict__
 }
 
 __global__ void __launch_bounds__(kBlock) k_dense_apply(int nc, double const* __restrict__ Einv, double const* __restrict__ g, double* __restrict__ mu, Scalars const* S, bool obey_done) {
+	pdl_sync();
+
 	if (obey_done && S->done) {
 		return;
 	}
@@ -715,6 +743,8 @@ __global__ void __launch_bounds__(kBlock) k_dense_apply(int nc, double const* __
 
 /* identity on the padding rows of the dense operator (3 n .. nc) */
 __global__ void k_mg_dense_pad(int n_real, int nc, double* __restrict__ E) {
+	pdl_sync();
+
 	int const i = n_real + blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (i < nc) {

@@ -172,6 +172,8 @@ __device__ __forceinline__ void reduced(Scalars* S, double total) {
 /* several GPUs: S->gath holds every rank's share; fold them in rank order - same bits on every rank */
 template <Fold WHAT>
 __global__ void k_fold(Scalars* S) {
+	pdl_sync();
+
 	if ((WHAT == kFoldPq || WHAT == kFoldRr) && S->done) {
 		return;
 	}
@@ -212,6 +214,8 @@ struct HaloDev {
  * rank with nothing to send on this level: the round counter must advance alike on every rank. */
 template <int NB>
 __global__ void __launch_bounds__(kBlock) k_halo_post(const __grid_constant__ HaloDev H, double const* __restrict__ v, int32_t const* __restrict__ send_idx, Scalars* S, bool obey_done) {
+	pdl_sync();
+
 	if (obey_done && S->done) {
 		return;
 	}
@@ -264,6 +268,8 @@ __global__ void __launch_bounds__(kBlock) k_halo_post(const __grid_constant__ Ha
 /* one CTA per neighbour: wait for its round, copy its entries into the ghost range of v */
 template <int NB>
 __global__ void __launch_bounds__(kBlock) k_halo_take(const __grid_constant__ HaloDev H, double* __restrict__ v, Scalars* S, bool obey_done) {
+	pdl_sync();
+
 	if (obey_done && S->done) {
 		return;
 	}
@@ -291,6 +297,8 @@ __global__ void __launch_bounds__(kBlock) k_halo_take(const __grid_constant__ Ha
  * every rank computed the entries [first, first + count) of src (the aggregates of its own nodes) and stores them
  * into every mailbox, its own included; k_mg_gather_take waits for all ranks and copies the complete vector out */
 __global__ void __launch_bounds__(kBlock) k_mg_gather_post(int first, int count, double const* __restrict__ src, Scalars* S, bool obey_done) {
+	pdl_sync();
+
 	if (obey_done && S->done) {
 		return;
 	}
@@ -332,6 +340,8 @@ __global__ void __launch_bounds__(kBlock) k_mg_gather_post(int first, int count,
 }
 
 __global__ void __launch_bounds__(kBlock) k_mg_gather_take(int n, double* __restrict__ dst, Scalars* S, bool obey_done) {
+	pdl_sync();
+
 	if (obey_done && S->done) {
 		return;
 	}
@@ -362,6 +372,8 @@ enum ShareMode { kShareMg, kShareMgFirst, kShareRefine, kShareVerify };
 
 template <ShareMode MODE>
 __global__ void k_share(Scalars* S, int arm_again) {
+	pdl_sync();
+
 	if (MODE == kShareMg && S->done) {
 		return;
 	}
@@ -580,6 +592,8 @@ __device__ __forceinline__ bool grid_sum2(double v0, double v1, double* __restri
 
 /* dscale = 1 / sqrt(|a_ii|) (1 where the diagonal is 0), b^ = dscale * b */
 __global__ void k_jacobi(const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ vtop, double2 const* __restrict__ vbot, double2 const* __restrict__ b, double2* __restrict__ dscale, double2* __restrict__ bhat) {
+	pdl_sync();
+
 	int const row = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (row >= P.nb) {
@@ -602,6 +616,8 @@ __global__ void k_jacobi(const __grid_constant__ bfmg_pattern_t P, double2 const
 
 /* A^ = D^-1/2 A D^-1/2, slot by slot (fully coalesced) */
 __global__ void k_scale_matrix(const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ vtop, double2 const* __restrict__ vbot, double2 const* __restrict__ dscale, double2* __restrict__ stop, double2* __restrict__ sbot) {
+	pdl_sync();
+
 	int const lane = threadIdx.x & (kWarp - 1);
 	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
 	int const n_warps = gridDim.x * blockDim.x / kWarp;
@@ -624,6 +640,8 @@ __global__ void k_scale_matrix(const __grid_constant__ bfmg_pattern_t P, double2
 
 /* r = p = b^, x = 0, rho = ||b^||^2 */
 __global__ void __launch_bounds__(kBlock) k_cg_init(int n2, double2 const* __restrict__ bhat, double2* __restrict__ x, double2* __restrict__ r, double2* __restrict__ p, double* __restrict__ partials, Scalars* S, double tol, int max_iter) {
+	pdl_sync();
+
 	double acc = 0;
 
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
@@ -658,6 +676,8 @@ __global__ void __launch_bounds__(kBlock) k_spmv(
 	const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ vtop, double2 const* __restrict__ vbot,
 	double2 const* __restrict__ p, double2* __restrict__ q, double2 const* __restrict__ bhat, double* __restrict__ partials, Scalars* S
 ) {
+	pdl_sync();
+
 	if (MODE == kDot && S->done) {
 		return;
 	}
@@ -728,6 +748,8 @@ __global__ void __launch_bounds__(kBlock) k_spmv(
 
 /* x += alpha p;  r -= alpha q;  partial r.r;  last CTA: beta = rho' / rho, rho = rho', convergence */
 __global__ void __launch_bounds__(kBlock) k_update_xr(int n2, double2 const* __restrict__ p, double2 const* __restrict__ q, double2* __restrict__ x, double2* __restrict__ r, double* __restrict__ partials, Scalars* S) {
+	pdl_sync();
+
 	if (S->done) {
 		return;
 	}
@@ -771,6 +793,8 @@ __global__ void __launch_bounds__(kBlock) k_update_xr(int n2, double2 const* __r
 
 /* p = r + beta p */
 __global__ void __launch_bounds__(kBlock) k_update_p(int n2, double2 const* __restrict__ r, double2* __restrict__ p, Scalars const* S) {
+	pdl_sync();
+
 	if (S->done) {
 		return;
 	}
@@ -792,6 +816,8 @@ __global__ void __launch_bounds__(kBlock) k_update_p(int n2, double2 const* __re
  * accumulator for the correction of a refinement step) */
 template <bool ADD, bool ZERO>
 __global__ void k_unscale(int n2, double2 const* __restrict__ dscale, double2* __restrict__ xhat, double2* __restrict__ x) {
+	pdl_sync();
+
 	int const i = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (i < n2) {
@@ -840,6 +866,8 @@ __global__ void __launch_bounds__(kBlock) k_residual_dd(
 	const __grid_constant__ bfmg_pattern_t P, double2 const* __restrict__ vtop, double2 const* __restrict__ vbot,
 	double2 const* __restrict__ b, double2 const* __restrict__ x, double2 const* __restrict__ dscale, double2* __restrict__ r, double* __restrict__ partials, Scalars* S, int arm_again
 ) {
+	pdl_sync();
+
 	int const lane = threadIdx.x & (kWarp - 1);
 	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
 	int const n_warps = gridDim.x * blockDim.x / kWarp;
@@ -914,6 +942,8 @@ __global__ void __launch_bounds__(kBlock) k_residual_dd(
 
 /* S->sum2 = ||v||^2 (verification pass only) */
 __global__ void __launch_bounds__(kBlock) k_norm2(int n2, double2 const* __restrict__ v, double* __restrict__ partials, Scalars* S) {
+	pdl_sync();
+
 	double acc = 0;
 
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
