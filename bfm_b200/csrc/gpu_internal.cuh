@@ -117,6 +117,12 @@ __device__ __forceinline__ double ld_stream(double const* p) {
 	return v;
 }
 
+__device__ __forceinline__ float ld_stream(float const* p) {
+	float v;
+	asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+	return v;
+}
+
 __device__ __forceinline__ int ld_stream(int const* p) {
 	int v;
 	asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));

@@ -759,7 +759,7 @@ static int ghost_owner(bfmi_hier_level_t const* L, int32_t b) {
 bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, bfmi_part_t const* part) {
 	/* aggregate sizes: nodes per aggregate on the mesh level and on the levels above; the last level is solved by
 	 * a dense inverse and may hold this many nodes (three unknowns each) */
-	int64_t const ratio0 = env_i64("BFM_MG_RATIO0", 12);
+	int64_t const ratio0 = env_i64("BFM_MG_RATIO0", 16);
 	int64_t const ratio = env_i64("BFM_MG_RATIO", 6);
 	int64_t const dense_nodes = env_i64("BFM_MG_DENSE_NODES", 1024);
 	int64_t const dense_limit = 2 * dense_nodes; /* pieces of bins can exceed the target */
@@ -1435,7 +1435,7 @@ static uint64_t hash_coords(double const* coords, size_t count) {
 }
 
 static uint64_t settings_hash(void) {
-	return (uint64_t) env_i64("BFM_MG_RATIO0", 12) * 1000003u + (uint64_t) env_i64("BFM_MG_RATIO", 6) * 10007u + (uint64_t) env_i64("BFM_MG_DENSE_NODES", 1024) + (uint64_t) env_i64("BFM_MG_REPLICATED_NODES", 65536) * 7919u;
+	return (uint64_t) env_i64("BFM_MG_RATIO0", 16) * 1000003u + (uint64_t) env_i64("BFM_MG_RATIO", 6) * 10007u + (uint64_t) env_i64("BFM_MG_DENSE_NODES", 1024) + (uint64_t) env_i64("BFM_MG_REPLICATED_NODES", 65536) * 7919u;
 }
 
 static bool same_key(bfmi_hier_t const* h, bfmi_plan_t const* plan, uint64_t coords_hash, int rank, int world) {

@@ -107,6 +107,7 @@ BFMI_HIDDEN bfmi_part_t* bfmi_part_for_mesh(bfm_state_t* state, bfm_mesh_t const
 BFMI_HIDDEN void bfmi_part_release(bfmi_part_t* part);
 BFMI_HIDDEN void bfmi_part_forget(bfm_mesh_t const* mesh);
 BFMI_HIDDEN uint64_t bfmi_mesh_hash(bfm_mesh_t const* mesh);
+BFMI_HIDDEN uint64_t bfmi_mesh_hash_part(bfm_mesh_t const* mesh, int rank, int world); /* XOR over the ranks = bfmi_mesh_hash */
 
 /* ---------------------------------------------------------------------------------------------
  * coarse level of the solver (coarse.c): node aggregates, their colouring, device mirrors

@@ -837,7 +837,37 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 	/* several GPUs: this rank assembles and solves the local mesh of its row block (partition.c) */
 
 	if (partitioned && bfmg_dist_world() > 1) {
-		job->part = bfmi_part_for_mesh(state, mesh, bfmi_mesh_hash(mesh), bfmg_dist_rank(), bfmg_dist_world());
+		/* the partition is cached by the hash of the GLOBAL connectivity (1.2 GB at 50 M DOF), which every rank holds:
+		 * each rank hashes its world-th of it and the parts are combined over the communicator */
+		uint64_t hash = 0;
+
+		{
+			int const world = bfmg_dist_world();
+			uint64_t const mine = bfmi_mesh_hash_part(mesh, bfmg_dist_rank(), world);
+			double parts[2] = {(double) (uint32_t) mine, (double) (uint32_t) (mine >> 32)}; /* exact in a double */
+			double all[2 * BFMG_DIST_MAX_RANKS];
+			double *d_send = NULL, *d_recv = NULL;
+
+			if (
+				bfmg_alloc((void**) &d_send, sizeof parts) < 0 || bfmg_alloc((void**) &d_recv, sizeof all) < 0 ||
+				bfmg_upload(d_send, parts, sizeof parts) < 0 || bfmg_dist_allgather_f64(d_send, d_recv, 2) < 0 ||
+				bfmg_download(all, d_recv, (size_t) world * sizeof parts) < 0
+			) {
+				bfmg_free(d_send);
+				bfmg_free(d_recv);
+				BFMI_FAIL(state, "exchanging the mesh hash failed: %s", bfmg_last_error());
+				goto fail;
+			}
+
+			bfmg_free(d_send);
+			bfmg_free(d_recv);
+
+			for (int r = 0; r < world; r++) {
+				hash ^= (uint64_t) all[2 * r] | (uint64_t) all[2 * r + 1] << 32;
+			}
+		}
+
+		job->part = bfmi_part_for_mesh(state, mesh, hash, bfmg_dist_rank(), bfmg_dist_world());
 
 		if (job->part == NULL) {
 			goto fail;

@@ -21,7 +21,7 @@
  *   z += P cycle_{l+1}(P^T t)     restriction, recursion (gamma visits: V- or W-cycle), prolongation
  *   z += w (g - A z)              one fused SpMV (kPost); on level 0 it also leaves r.z for CG
  *
- * with w = 1.6 / (largest absolute row sum): a Gershgorin bound of the largest eigenvalue, so w lambda_max < 2
+ * with w = 1.8 / (largest absolute row sum): a Gershgorin bound of the largest eigenvalue, so w lambda_max < 2
  * always holds and the smoother - hence the whole cycle - is symmetric positive definite.  The preconditioner
  * changes how fast CG converges, not what it converges to: the stopping test stays on the true CG residual.
  *
@@ -565,8 +565,9 @@ __global__ void k_blk_diag(bfmg_mg_level_t N, double const* __restrict__ val, do
 	}
 }
 
-/* A <- D^-1/2 A D^-1/2 in place, and the largest absolute row sum of the result */
-__global__ void __launch_bounds__(kBlock) k_blk_scale(bfmg_mg_level_t N, double* __restrict__ val, double const* __restrict__ dsc, unsigned long long* __restrict__ gersh) {
+/* A <- D^-1/2 A D^-1/2 in place, its FP32 copy for the cycle's products (as on level 0: the cycle only shapes the
+ * preconditioner; the Galerkin product of the next level reads the FP64 values), and the largest absolute row sum */
+__global__ void __launch_bounds__(kBlock) k_blk_scale(bfmg_mg_level_t N, double* __restrict__ val, float* __restrict__ fval, double const* __restrict__ dsc, unsigned long long* __restrict__ gersh) {
 	pdl_sync();
 
 	int const lane = threadIdx.x & (kWarp - 1);
@@ -602,6 +603,7 @@ __global__ void __launch_bounds__(kBlock) k_blk_scale(bfmg_mg_level_t N, double*
 					double const x = val[at] * sr[k] * sc;
 
 					val[at] = x;
+					fval[at] = (float) x;
 					sum[k] += fabs(x);
 				}
 			}
@@ -621,8 +623,8 @@ __global__ void __launch_bounds__(kBlock) k_blk_scale(bfmg_mg_level_t N, double*
 }
 
 /* warp = slice, lane = node row; modes as k_spmv_mg (no dot product: the coarse levels feed no CG scalar) */
-template <MgMode MODE, bool CG>
-__device__ __forceinline__ void d_blk_spmv(bfmg_mg_level_t const& N, double const* __restrict__ val, double const* __restrict__ v, double const* __restrict__ g, double* __restrict__ out, double w) {
+template <MgMode MODE, bool CG, typename VT>
+__device__ __forceinline__ void d_blk_spmv(bfmg_mg_level_t const& N, VT const* __restrict__ val, double const* __restrict__ v, double const* __restrict__ g, double* __restrict__ out, double w) {
 	int const lane = threadIdx.x & (kWarp - 1);
 	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
 	int const n_warps = gridDim.x * blockDim.x / kWarp;
@@ -641,9 +643,9 @@ __device__ __forceinline__ void d_blk_spmv(bfmg_mg_level_t const& N, double cons
 			double const x1 = ldv<CG>(&v[3 * (size_t) col + 1]);
 			double const x2 = ldv<CG>(&v[3 * (size_t) col + 2]);
 
-			y0 = fma(ld_stream(&val[0 * ns + slot]), x0, fma(ld_stream(&val[1 * ns + slot]), x1, fma(ld_stream(&val[2 * ns + slot]), x2, y0)));
-			y1 = fma(ld_stream(&val[3 * ns + slot]), x0, fma(ld_stream(&val[4 * ns + slot]), x1, fma(ld_stream(&val[5 * ns + slot]), x2, y1)));
-			y2 = fma(ld_stream(&val[6 * ns + slot]), x0, fma(ld_stream(&val[7 * ns + slot]), x1, fma(ld_stream(&val[8 * ns + slot]), x2, y2)));
+			y0 = fma((double) ld_stream(&val[0 * ns + slot]), x0, fma((double) ld_stream(&val[1 * ns + slot]), x1, fma((double) ld_stream(&val[2 * ns + slot]), x2, y0)));
+			y1 = fma((double) ld_stream(&val[3 * ns + slot]), x0, fma((double) ld_stream(&val[4 * ns + slot]), x1, fma((double) ld_stream(&val[5 * ns + slot]), x2, y1)));
+			y2 = fma((double) ld_stream(&val[6 * ns + slot]), x0, fma((double) ld_stream(&val[7 * ns + slot]), x1, fma((double) ld_stream(&val[8 * ns + slot]), x2, y2)));
 		}
 
 		if (row < N.row_hi) {
@@ -672,15 +674,15 @@ __device__ __forceinline__ void d_blk_spmv(bfmg_mg_level_t const& N, double cons
 	}
 }
 
-template <MgMode MODE>
-__global__ void __launch_bounds__(kBlock) k_blk_spmv(bfmg_mg_level_t N, double const* __restrict__ val, double const* __restrict__ v, double const* __restrict__ g, double* __restrict__ out, double const* __restrict__ omega_p, Scalars const* S, bool obey_done) {
+template <MgMode MODE, typename VT>
+__global__ void __launch_bounds__(kBlock) k_blk_spmv(bfmg_mg_level_t N, VT const* __restrict__ val, double const* __restrict__ v, double const* __restrict__ g, double* __restrict__ out, double const* __restrict__ omega_p, Scalars const* S, bool obey_done) {
 	pdl_sync();
 
 	if (obey_done && S->done) {
 		return;
 	}
 
-	d_blk_spmv<MODE, false>(N, val, v, g, out, (MODE == kMgPre || MODE == kMgPost) ? *omega_p : 1.0);
+	d_blk_spmv<MODE, false, VT>(N, val, v, g, out, (MODE == kMgPre || MODE == kMgPost) ? *omega_p : 1.0);
 }
 
 /* mu = E^-1 g on the dense last level (the explicit inverse; kCoarseRows rows per CTA, four warps per row as in
@@ -757,6 +759,7 @@ __global__ void k_mg_dense_pad(int n_real, int nc, double* __restrict__ E) {
 struct MgLevelWork {
 	bfmg_mg_level_t L;
 	double* val;      /* levels >= 1 (sparse): nine planes of n_slots doubles */
+	float* fval;      /* ... and their FP32 copy, which the cycle's products stream */
 	double* dsc;      /* levels >= 1: D^-1/2, three per node */
 	void* pval;       /* prolongator to the next level: float [6][n_p] on level 0, double [9][n_p] above */
 	double *g, *va, *vb, *vt; /* levels >= 1: right-hand side and three work vectors, three per node */
@@ -780,7 +783,7 @@ struct MgRun {
 	double* dmu = nullptr;  /* its solution [nc] */
 	int32_t* bad = nullptr;
 
-	double omega_factor = 1.6;
+	double omega_factor = 1.8;
 	double lambda0 = 4;     /* Gershgorin bound of the scaled level-0 operator (after setup) */
 	float2* ftop = nullptr; /* FP32 copy of the scaled level-0 operator for the smoothing products: plane of (a00,a01) */
 	float2* fbot = nullptr; /* ... and of (a10,a11) */
@@ -824,7 +827,7 @@ struct MgRun {
 			bool const last = l == n_levels - 1;
 
 			if (l >= 1 && !last) {
-				total += align256((size_t) L.n_slots * 9 * sizeof(double));
+				total += align256((size_t) L.n_slots * 9 * sizeof(double)) + align256((size_t) L.n_slots * 9 * sizeof(float));
 			}
 
 			if (l >= 1) {
@@ -869,6 +872,7 @@ struct MgRun {
 
 			if (l >= 1 && !last) {
 				w.val = (double*) take((size_t) L.n_slots * 9 * sizeof(double));
+				w.fval = (float*) take((size_t) L.n_slots * 9 * sizeof(float));
 			}
 
 			if (l >= 1) {
@@ -1108,7 +1112,7 @@ struct MgRun {
 					rc = -1;
 				}
 
-				rc = rc < 0 ? rc : BFMG_LAUNCH(k_blk_scale, nx.grid_rows, kBlock, 0, nx.L, nx.val, nx.dsc, &D->gersh[l + 1]);
+				rc = rc < 0 ? rc : BFMG_LAUNCH(k_blk_scale, nx.grid_rows, kBlock, 0, nx.L, nx.val, nx.fval, nx.dsc, &D->gersh[l + 1]);
 				rc = rc < 0 ? rc : (l == 0
 					? BFMG_LAUNCH((k_mg_pscale<2, float>), (w.L.n_p + kBlock - 1) / kBlock, kBlock, 0, w.L, nx.dsc, (float*) w.pval)
 					: BFMG_LAUNCH((k_mg_pscale<3, double>), (w.L.n_p + kBlock - 1) / kBlock, kBlock, 0, w.L, nx.dsc, (double*) w.pval));
@@ -1178,12 +1182,12 @@ struct MgRun {
 		bool const dense_next = l + 1 == n_levels - 1;
 		double const* const om = &D->omega[l];
 
-		if (!halo(l, w.g, S, obey) || BFMG_LAUNCH(k_blk_spmv<kMgPre>, w.grid_rows, kBlock, 0, w.L, w.val, w.g, w.g, w.vt, om, S, obey) < 0) {
+		if (!halo(l, w.g, S, obey) || BFMG_LAUNCH((k_blk_spmv<kMgPre, float>), w.grid_rows, kBlock, 0, w.L, (float const*) w.fval, w.g, w.g, w.vt, om, S, obey) < 0) {
 			return nullptr;
 		}
 
 		for (int visit = 0; visit < w.gamma; visit++) {
-			if (visit > 0 && (!halo(l, w.va, S, obey) || BFMG_LAUNCH(k_blk_spmv<kMgResid>, w.grid_rows, kBlock, 0, w.L, w.val, w.va, w.g, w.vt, om, S, obey) < 0)) {
+			if (visit > 0 && (!halo(l, w.va, S, obey) || BFMG_LAUNCH((k_blk_spmv<kMgResid, float>), w.grid_rows, kBlock, 0, w.L, (float const*) w.fval, w.va, w.g, w.vt, om, S, obey) < 0)) {
 				return nullptr;
 			}
 
@@ -1218,7 +1222,7 @@ struct MgRun {
 			}
 		}
 
-		if (!halo(l, w.va, S, obey) || BFMG_LAUNCH(k_blk_spmv<kMgPost>, w.grid_rows, kBlock, 0, w.L, w.val, w.va, w.g, w.vb, om, S, obey) < 0) {
+		if (!halo(l, w.va, S, obey) || BFMG_LAUNCH((k_blk_spmv<kMgPost, float>), w.grid_rows, kBlock, 0, w.L, (float const*) w.fval, w.va, w.g, w.vb, om, S, obey) < 0) {
 			return nullptr;
 		}
 

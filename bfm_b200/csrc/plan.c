@@ -47,13 +47,13 @@ static void sort_u64(uint64_t* v, size_t n) {
 /* order-sensitive 64-bit hash of the connectivity, chunked so that OpenMP can help on big meshes.  It runs on every
  * bfm_sim_run (the cached plan is only valid while the connectivity is what it was), over 1.2 GB at 50 M DOF, so the
  * inner loop keeps four independent multiply chains going: memory speed instead of multiplier latency. */
-static uint64_t hash_elems(size_t const* elems, size_t count) {
+static uint64_t hash_elems_part(size_t const* elems, size_t count, size_t first_chunk, size_t chunk_stride) {
 	size_t const chunk = 1 << 16;
 	size_t const n_chunks = (count + chunk - 1) / chunk;
-	uint64_t total = 0x9e3779b97f4a7c15ull ^ count;
+	uint64_t total = first_chunk == 0 ? 0x9e3779b97f4a7c15ull ^ count : 0; /* the parts of all ranks XOR to the whole */
 
-#pragma omp parallel for schedule(static) reduction(^ : total) if (n_chunks > 16)
-	for (size_t c = 0; c < n_chunks; c++) {
+#pragma omp parallel for schedule(static) reduction(^ : total) if (n_chunks > 16 * chunk_stride)
+	for (size_t c = first_chunk; c < n_chunks; c += chunk_stride) {
 		size_t const end = (c + 1) * chunk < count ? (c + 1) * chunk : count;
 		uint64_t h0 = 0xcbf29ce484222325ull + c, h1 = 0x84222325cbf29ce4ull ^ c, h2 = 0x9e3779b97f4a7c15ull + 3 * c, h3 = 0xc2b2ae3d27d4eb4full ^ (c << 7);
 		size_t i = c * chunk;
@@ -82,8 +82,18 @@ static uint64_t hash_elems(size_t const* elems, size_t count) {
 	return total;
 }
 
+static uint64_t hash_elems(size_t const* elems, size_t count) {
+	return hash_elems_part(elems, count, 0, 1);
+}
+
 uint64_t bfmi_mesh_hash(bfm_mesh_t const* mesh) {
 	return hash_elems(mesh->elems, mesh->n_elems * mesh->kind);
+}
+
+/* several ranks holding the same mesh (one process per GPU, SPMD): rank r hashes every world-th chunk; the XOR of all
+ * parts is bfmi_mesh_hash - each process reads 1 / world of the connectivity instead of all of it */
+uint64_t bfmi_mesh_hash_part(bfm_mesh_t const* mesh, int rank, int world) {
+	return hash_elems_part(mesh->elems, mesh->n_elems * mesh->kind, (size_t) rank, (size_t) world);
 }
 
 static void plan_free(bfmi_plan_t* plan) {

@@ -63,7 +63,7 @@ def tentative(level, dofs, sq):
 
 
 class Emulation:
-	def __init__(self, A, levels, gamma=2, omega=1.6, single_precision_p=True):
+	def __init__(self, A, levels, gamma=2, omega=1.8, single_precision_p=True):
 		"""A: the assembled matrix (scipy, DOFs interleaved per node); levels: hierarchy()"""
 
 		d = np.abs(A.diagonal())
