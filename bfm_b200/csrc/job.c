@@ -1806,20 +1806,35 @@ int bfm_sim_run(bfm_sim_t* sim) {
 		return -1;
 	}
 
+	bool const verbose = getenv("BFM_JOB_VERBOSE") != NULL;
+
 	for (size_t i = 0; i < sim->n_instances; i++) {
 		bfmx_job_t* job;
+		double t[7];
+
+		t[0] = now_ms();
 
 		if (bfmx_job_create(&job, sim, i) < 0) {
 			return -1;
 		}
 
-		int rv = bfmx_job_upload(job) < 0 || bfmx_job_assemble(job) < 0 ? -1 : 0;
+		t[1] = now_ms();
+
+		int rv = bfmx_job_upload(job) < 0 ? -1 : 0;
+
+		t[2] = now_ms();
+
+		rv = rv < 0 || bfmx_job_assemble(job) < 0 ? -1 : 0;
+
+		t[3] = t[4] = now_ms();
 
 		if (rv == 0) {
 			/* the reference ignores bfm_matrix_solve's status and always fills instance->effects (sim.c:122-131).  A PCG that
 			 * misses its tolerance is reported as -1 here (state->err says why) - but the best iterate is still delivered,
 			 * on every rank alike, so callers that ignore the status get what the reference would have given them */
 			int const solved = bfmx_job_solve(job);
+
+			t[4] = now_ms();
 
 			if (job->solved && bfmx_job_download(job) < 0) {
 				rv = -1;
@@ -1828,8 +1843,16 @@ int bfm_sim_run(bfm_sim_t* sim) {
 			rv = solved < 0 ? -1 : rv;
 		}
 
+		t[5] = now_ms();
+
 		bfmx_publish_stats(&job->stats);
 		bfmx_job_destroy(job);
+
+		t[6] = now_ms();
+
+		if (verbose) {
+			fprintf(stderr, "[sim_run] create %.1f  upload %.1f  assemble %.1f  solve %.1f  download %.1f  destroy %.1f ms (host wall clock)\n", t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5]);
+		}
 
 		if (rv < 0) {
 			return -1;
