@@ -24,7 +24,7 @@ C_SOURCES = ["core.c", "mesh.c", "ez.c", "matrix.c", "perm.c", "plan.c", "partit
 
 # assembly.cu must not contract a*b+c into an FMA: bit-for-bit parity with the reference's gcc/x86-64
 # arithmetic (see the header of assembly.cu).  The solver is free to use FMAs.
-CU_SOURCES = {"context.cu": ["-Xcompiler", "-fopenmp"], "assembly.cu": ["-fmad=false"], "solver.cu": [], "dist.cu": [], "batch.cu": []}
+CU_SOURCES = {"context.cu": ["-Xcompiler", "-fopenmp"], "assembly.cu": ["-fmad=false"], "solver.cu": [], "dist.cu": [], "batch.cu": [], "symbolic.cu": []}
 
 INCLUDES = ["-I" + os.path.join(ROOT, "include"), "-I" + SRC]
 

@@ -59,6 +59,19 @@ typedef struct {
 	int32_t row_lo, row_hi;
 } bfmg_pattern_t;
 
+/* ---- symbolic phase on the device (symbolic.cu): once per mesh ------------------------------------------- */
+
+/* the SELL-32 node-block pattern and the element-to-nonzero map of a mesh from its connectivity (d_elems:
+ * n_elems * kind node numbers, all < n_nodes; stays the caller's).  Fills nb, n_slices, n_slots, kind, row_lo / row_hi
+ * and every array of *pat except elems (allocated here: bfmg_free); *n_ctr = entries of pat->ctr.  The arrays are
+ * those plan.c's host builder produces, entry for entry. */
+int bfmg_plan_build(int32_t n_nodes, int64_t n_elems, int32_t kind, int32_t const* d_elems, bfmg_pattern_t* pat, int64_t* n_ctr);
+
+/* the edge list of reference mesh.c:32-102 (half-edges ordered by smaller node descending, larger ascending, ties in
+ * element order; opposite neighbours fused): *d_edges = n_edges records of four int64 - nodes[0], nodes[1],
+ * elems[0], elems[1] (-1 on the boundary), the layout of bfm_edge_t - allocated here (bfmg_free); NULL when empty */
+int bfmg_edges_build(int32_t n_nodes, int64_t n_elems, int32_t kind, int32_t const* d_elems, int64_t** d_edges, int64_t* n_edges);
+
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink (dist.cu) ------------------------------------ */
 
 #define BFMG_DIST_ID_BYTES 128

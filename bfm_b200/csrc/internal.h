@@ -53,8 +53,11 @@ typedef struct bfmi_plan {
 	uint32_t* ctr;      /* [n_ctr] element << 4 | local row node << 2 | local column node */
 	int32_t* elems32;   /* [n_elems * kind] connectivity narrowed to 32 bits */
 
-	bfmg_pattern_t dev; /* device mirror, filled by bfmi_plan_upload */
+	bfmg_pattern_t dev; /* device arrays: built there by symbolic.cu, or mirrored by bfmi_plan_upload */
 	bool on_device;
+	bool built_on_device;         /* symbolic.cu built it: ctr_ptr, ctr, elems32 exist on the device only */
+	size_t h2d_bytes, d2h_bytes;  /* what building / mirroring it moved over PCIe */
+	bool accounted;               /* ... and whether a job has put that (and the build time) into its stats yet */
 } bfmi_plan_t;
 
 BFMI_HIDDEN bfmi_plan_t* bfmi_plan_for_mesh(bfm_state_t* state, bfm_mesh_t const* mesh); /* cached, retained */

@@ -886,7 +886,9 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 
 	MARK("plan (cache look-up)");
 
-	bool const fresh = !job->plan->on_device;
+	bool const fresh = !job->plan->accounted; /* built (and mirrored) by this very call: its time and bytes go into the stats once */
+
+	job->plan->accounted = true;
 
 	if (bfmi_plan_upload(state, job->plan) < 0) {
 		goto fail;
@@ -895,7 +897,8 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 	if (fresh) {
 		job->stats.ms_plan = (float) (now_ms() - t0);
 
-		job->stats.h2d_bytes += ((size_t) job->plan->n_slices + 1 + 2 * (size_t) job->plan->nb + 2 * (size_t) job->plan->n_slots + 1 + (size_t) job->plan->n_ctr + job->plan->n_elems * (size_t) job->plan->kind) * 4;
+		job->stats.h2d_bytes += job->plan->h2d_bytes;
+		job->stats.d2h_bytes += job->plan->d2h_bytes;
 	}
 
 	MARK("plan upload");
@@ -1292,7 +1295,8 @@ int bfmx_job_create_batch(bfmx_job_t** out, bfm_sim_t** sims, size_t n_sims) {
 		}
 
 		job->stats.ms_plan = (float) (now_ms() - t0);
-		job->stats.h2d_bytes += ((size_t) job->plan->n_slices + 1 + 2 * (size_t) job->plan->nb + 2 * (size_t) job->plan->n_slots + 1 + (size_t) job->plan->n_ctr + job->plan->n_elems * (size_t) job->plan->kind) * 4;
+		job->stats.h2d_bytes += job->plan->h2d_bytes;
+		job->stats.d2h_bytes += job->plan->d2h_bytes;
 
 		bfmi_plan_release(batch_plan);
 		batch_plan = job->plan;

@@ -10,6 +10,7 @@
 
 #include <ctype.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 /* reference mesh.c:6-14 */
@@ -119,6 +120,69 @@ static void half_edge_sort(bfm_edge_t* v, bfm_edge_t* tmp, size_t n) {
 	memcpy(v, tmp, n * sizeof *v);
 }
 
+/* the same list from the kernels of symbolic.cu (per-node segments instead of a global sort; identical order).
+ * 1: done, 0: not applicable here (the caller takes the host path), -1: failed */
+static int edges_on_device(bfm_mesh_t* mesh) {
+	bfm_state_t* const state = mesh->state;
+	size_t const sides = mesh->kind;
+	size_t const n_half = mesh->n_elems * sides;
+	size_t const nn = mesh->n_nodes;
+
+	if ((sides != 3 && sides != 4) || nn == 0 || nn >= (1u << 30) || n_half >= INT32_MAX || n_half < 2) {
+		return 0;
+	}
+
+	int32_t* const elems32 = malloc(n_half * sizeof *elems32);
+	bool bad = elems32 == NULL;
+
+	if (!bad) {
+#pragma omp parallel for schedule(static) reduction(|| : bad) if (n_half > ((size_t) 1 << 18))
+		for (size_t i = 0; i < n_half; i++) {
+			bad = bad || mesh->elems[i] >= nn;
+			elems32[i] = (int32_t) mesh->elems[i];
+		}
+	}
+
+	if (bad) { /* connectivity outside the node table: the host sort does not mind, the per-node segments would */
+		free(elems32);
+		return 0;
+	}
+
+	int32_t* d_elems = NULL;
+	int64_t* d_edges = NULL;
+	int64_t n_out = 0;
+	int rv = -1;
+
+	if (
+		bfmg_alloc((void**) &d_elems, n_half * sizeof *d_elems) == 0 && bfmg_upload(d_elems, elems32, n_half * sizeof *d_elems) == 0 &&
+		bfmg_edges_build((int32_t) nn, (int64_t) mesh->n_elems, (int32_t) sides, d_elems, &d_edges, &n_out) == 0
+	) {
+		_Static_assert(sizeof(bfm_edge_t) == 4 * sizeof(int64_t), "an edge record is nodes[2], elems[2], 8 bytes each");
+
+		mesh->edges = n_out > 0 ? state->alloc((size_t) n_out * sizeof *mesh->edges) : NULL;
+
+		if (mesh->edges != NULL && bfmg_download(mesh->edges, d_edges, (size_t) n_out * sizeof *mesh->edges) == 0) {
+			mesh->n_edges = (size_t) n_out;
+			rv = 1;
+		}
+
+		else if (mesh->edges != NULL) {
+			state->free(mesh->edges);
+			mesh->edges = NULL;
+		}
+	}
+
+	else {
+		BFMI_FAIL(state, "edge derivation on the device failed: %s", bfmg_last_error());
+	}
+
+	bfmg_free(d_elems);
+	bfmg_free(d_edges);
+	free(elems32);
+
+	return rv;
+}
+
 int bfmx_mesh_compute_edges(bfm_mesh_t* mesh) {
 	bfm_state_t* const state = mesh->state;
 	size_t const sides = mesh->kind;
@@ -128,6 +192,20 @@ int bfmx_mesh_compute_edges(bfm_mesh_t* mesh) {
 		state->free(mesh->edges);
 		mesh->edges = NULL;
 		mesh->n_edges = 0;
+	}
+
+	/* big meshes go through the device when there is one (BFM_EDGES=device / host forces either way; small meshes
+	 * are not worth a CUDA context: the readers must stay usable on a machine without a GPU) */
+
+	char const* const how = getenv("BFM_EDGES");
+	bool const want_device = how != NULL ? strcmp(how, "device") == 0 : n_half >= ((size_t) 1 << 20);
+
+	if (want_device && bfmg_available()) {
+		int const rv = edges_on_device(mesh);
+
+		if (rv != 0) {
+			return rv < 0 ? -1 : 0;
+		}
 	}
 
 	bfm_edge_t* const edges = state->alloc(n_half * sizeof *edges);

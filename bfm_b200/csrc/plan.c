@@ -8,8 +8,12 @@
  * the contributor list holds (element, local row node j, local column node k), sorted by element,
  * then j, then k: the order in which the reference's element loop (system.c:460) adds to that entry.
  *
- * Built once per mesh on the host (OpenMP over nodes) and cached by mesh identity + a hash of the
- * connectivity, so repeated bfm_sim_run calls on the same mesh (examples/benchmark.py) reuse it.
+ * Built once per mesh and cached by mesh identity + a hash of the connectivity, so repeated bfm_sim_run calls on the
+ * same mesh (examples/benchmark.py) reuse it.  With a CUDA device the builder is symbolic.cu (count / scan / per-node
+ * sort kernels; the host only narrows the connectivity to 32 bits and receives the arrays host code reads: columns,
+ * row lengths, slice offsets, diagonal slots); build_from_mesh below is the same construction on the host (OpenMP
+ * over nodes) - what introspection gets on a machine without a device, what BFM_PLAN=host forces, and what the GPU
+ * test compares the kernels with, array for array.
  */
 #include "internal.h"
 
@@ -209,6 +213,94 @@ int64_t bfmi_plan_find(bfmi_plan_t const* plan, int32_t a, int32_t b) {
 }
 
 /* ---- plan from a mesh ------------------------------------------------------------------------- */
+
+/* the same plan built by symbolic.cu.  The contributor map (ctr_ptr, ctr) stays on the device - only the assembly
+ * kernel reads it; bfmx_mesh_pattern_copy fetches it on demand */
+static bfmi_plan_t* build_on_device(bfm_mesh_t const* mesh, uint64_t hash) {
+	size_t const kind = mesh->kind;
+	size_t const nn = mesh->n_nodes;
+	size_t const ne = mesh->n_elems;
+
+	if (nn == 0 || nn >= (1u << 30) || ne >= (1u << 28) || ne * kind * kind >= INT32_MAX) {
+		return NULL;
+	}
+
+	bfmi_plan_t* const plan = calloc(1, sizeof *plan);
+
+	if (plan == NULL) {
+		return NULL;
+	}
+
+	plan->refs = 1;
+	plan->mesh = mesh;
+	plan->n_nodes = nn;
+	plan->n_elems = ne;
+	plan->kind = (int) kind;
+	plan->elems_hash = hash;
+	plan->nb = (int32_t) nn;
+
+	int32_t* const elems32 = malloc((ne * kind + 1) * sizeof *elems32);
+	int32_t* d_elems = NULL;
+	bool bad = elems32 == NULL;
+
+	if (!bad) {
+#pragma omp parallel for schedule(static) reduction(|| : bad) if (ne * kind > ((size_t) 1 << 18))
+		for (size_t i = 0; i < ne * kind; i++) {
+			bad = bad || mesh->elems[i] >= nn; /* connectivity points outside the node table */
+			elems32[i] = (int32_t) mesh->elems[i];
+		}
+	}
+
+	if (bad || bfmg_alloc((void**) &d_elems, (ne * kind + 1) * sizeof *d_elems) < 0 || bfmg_upload(d_elems, elems32, ne * kind * sizeof *d_elems) < 0) {
+		free(elems32);
+		bfmg_free(d_elems);
+		free(plan);
+		return NULL;
+	}
+
+	free(elems32);
+
+	if (bfmg_plan_build(plan->nb, (int64_t) ne, (int32_t) kind, d_elems, &plan->dev, &plan->n_ctr) < 0) {
+		bfmg_free(d_elems);
+		free(plan);
+		return NULL;
+	}
+
+	plan->dev.elems = d_elems;
+	plan->on_device = true; /* from here on plan_free releases the device arrays */
+	plan->built_on_device = true;
+	plan->n_slices = plan->dev.n_slices;
+	plan->n_slots = plan->dev.n_slots;
+
+	plan->slice_off = malloc(((size_t) plan->n_slices + 1) * sizeof *plan->slice_off);
+	plan->row_len = malloc((nn + 1) * sizeof *plan->row_len);
+	plan->scol = malloc(((size_t) plan->n_slots + 1) * sizeof *plan->scol);
+	plan->diag_pos = malloc((nn + 1) * sizeof *plan->diag_pos);
+
+	if (
+		plan->slice_off == NULL || plan->row_len == NULL || plan->scol == NULL || plan->diag_pos == NULL ||
+		bfmg_download(plan->slice_off, plan->dev.slice_off, ((size_t) plan->n_slices + 1) * sizeof *plan->slice_off) < 0 ||
+		bfmg_download(plan->row_len, plan->dev.row_len, nn * sizeof *plan->row_len) < 0 ||
+		bfmg_download(plan->scol, plan->dev.scol, (size_t) plan->n_slots * sizeof *plan->scol) < 0 ||
+		bfmg_download(plan->diag_pos, plan->dev.diag_pos, nn * sizeof *plan->diag_pos) < 0
+	) {
+		plan_free(plan);
+		return NULL;
+	}
+
+	int64_t blocks = 0;
+
+#pragma omp parallel for schedule(static) reduction(+ : blocks) if (nn > 50000)
+	for (size_t a = 0; a < nn; a++) {
+		blocks += plan->row_len[a];
+	}
+
+	plan->n_blocks = blocks;
+	plan->h2d_bytes = ne * kind * sizeof(int32_t);
+	plan->d2h_bytes = ((size_t) plan->n_slices + 1 + 2 * nn + (size_t) plan->n_slots) * sizeof(int32_t);
+
+	return plan;
+}
 
 static bfmi_plan_t* build_from_mesh(bfm_mesh_t const* mesh, uint64_t hash) {
 	size_t const kind = mesh->kind;
@@ -413,10 +505,13 @@ bfmi_plan_t* bfmi_plan_for_mesh(bfm_state_t* state, bfm_mesh_t const* mesh) {
 		}
 	}
 
-	bfmi_plan_t* const plan = build_from_mesh(mesh, hash);
+	/* with a device the kernels of symbolic.cu build it (BFM_PLAN=host: the OpenMP twin above, for comparison) */
+	char const* const how = getenv("BFM_PLAN");
+	bool const on_device = bfmg_available() && (how == NULL || strcmp(how, "host") != 0);
+	bfmi_plan_t* const plan = on_device ? build_on_device(mesh, hash) : build_from_mesh(mesh, hash);
 
 	if (plan == NULL) {
-		BFMI_FAIL(state, "cannot build the sparsity plan (mesh too large for 32-bit indices, bad connectivity or out of memory)");
+		BFMI_FAIL(state, "cannot build the sparsity plan (mesh too large for 32-bit indices, bad connectivity or out of memory%s%s)", on_device ? "; " : "", on_device ? bfmg_last_error() : "");
 		return NULL;
 	}
 
@@ -566,6 +661,7 @@ int bfmi_plan_upload(bfm_state_t* state, bfmi_plan_t* plan) {
 	d->row_hi = plan->nb;
 
 	plan->on_device = true; /* from here on plan_free releases whatever was allocated */
+	plan->h2d_bytes = ((size_t) plan->n_slices + 1 + 2 * (size_t) plan->nb + 2 * (size_t) plan->n_slots + 1 + (size_t) plan->n_ctr + plan->n_elems * (size_t) plan->kind) * sizeof(int32_t);
 
 	if (
 		mirror((void**) &d->slice_off, plan->slice_off, ((size_t) plan->n_slices + 1) * sizeof(int32_t)) < 0 ||
@@ -608,13 +704,22 @@ int bfmx_mesh_pattern_copy(bfm_mesh_t* mesh, int32_t* slice_off, int32_t* row_le
 		return -1;
 	}
 
+	int rv = 0;
+
 	memcpy(slice_off, plan->slice_off, ((size_t) plan->n_slices + 1) * sizeof *slice_off);
 	memcpy(row_len, plan->row_len, (size_t) plan->nb * sizeof *row_len);
 	memcpy(scol, plan->scol, (size_t) plan->n_slots * sizeof *scol);
 	memcpy(diag_pos, plan->diag_pos, (size_t) plan->nb * sizeof *diag_pos);
-	memcpy(ctr_ptr, plan->ctr_ptr, ((size_t) plan->n_slots + 1) * sizeof *ctr_ptr);
-	memcpy(ctr, plan->ctr, (size_t) plan->n_ctr * sizeof *ctr);
+
+	if (plan->ctr_ptr != NULL) {
+		memcpy(ctr_ptr, plan->ctr_ptr, ((size_t) plan->n_slots + 1) * sizeof *ctr_ptr);
+		memcpy(ctr, plan->ctr, (size_t) plan->n_ctr * sizeof *ctr);
+	}
+
+	else { /* built by symbolic.cu: the contributor map lives on the device only */
+		rv = bfmg_download(ctr_ptr, plan->dev.ctr_ptr, ((size_t) plan->n_slots + 1) * sizeof *ctr_ptr) < 0 || bfmg_download(ctr, plan->dev.ctr, (size_t) plan->n_ctr * sizeof *ctr) < 0 ? -1 : 0;
+	}
 
 	bfmi_plan_release(plan);
-	return 0;
+	return rv;
 }
