@@ -20,7 +20,7 @@ OBJ = os.path.join(SRC, "_obj")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libbfm.so")
 
-C_SOURCES = ["core.c", "mesh.c", "ez.c", "matrix.c", "perm.c", "plan.c", "partition.c", "coarse.c", "hier.c", "csr.c", "job.c"]
+C_SOURCES = ["core.c", "mesh.c", "ez.c", "matrix.c", "perm.c", "plan.c", "renumber.c", "partition.c", "coarse.c", "hier.c", "csr.c", "job.c"]
 
 # assembly.cu must not contract a*b+c into an FMA: bit-for-bit parity with the reference's gcc/x86-64
 # arithmetic (see the header of assembly.cu).  The solver is free to use FMAs.

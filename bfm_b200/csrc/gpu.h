@@ -72,6 +72,10 @@ int bfmg_plan_build(int32_t n_nodes, int64_t n_elems, int32_t kind, int32_t cons
  * elems[0], elems[1] (-1 on the boundary), the layout of bfm_edge_t - allocated here (bfmg_free); NULL when empty */
 int bfmg_edges_build(int32_t n_nodes, int64_t n_elems, int32_t kind, int32_t const* d_elems, int64_t** d_edges, int64_t* n_edges);
 
+/* d_dst[i] = d_src[d_index[i]] for n node blocks (two doubles each): displacements from the internal numbering of
+ * renumber.c back into the caller's */
+int bfmg_gather_blocks(double* d_dst, double const* d_src, int32_t const* d_index, size_t n);
+
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink (dist.cu) ------------------------------------ */
 
 #define BFMG_DIST_ID_BYTES 128

@@ -61,6 +61,7 @@ typedef struct bfmi_plan {
 } bfmi_plan_t;
 
 BFMI_HIDDEN bfmi_plan_t* bfmi_plan_for_mesh(bfm_state_t* state, bfm_mesh_t const* mesh); /* cached, retained */
+BFMI_HIDDEN bfmi_plan_t* bfmi_plan_for_mesh_hashed(bfm_state_t* state, bfm_mesh_t const* mesh, uint64_t hash); /* hash = bfmi_mesh_hash(mesh) */
 BFMI_HIDDEN bfmi_plan_t* bfmi_plan_from_csr(bfm_state_t* state, size_t n, size_t const* rowptr, size_t const* col);
 BFMI_HIDDEN void bfmi_plan_retain(bfmi_plan_t* plan);
 BFMI_HIDDEN void bfmi_plan_release(bfmi_plan_t* plan);
@@ -69,6 +70,34 @@ BFMI_HIDDEN int bfmi_plan_upload(bfm_state_t* state, bfmi_plan_t* plan);
 
 /* slot of block (a, b), or -1 */
 BFMI_HIDDEN int64_t bfmi_plan_find(bfmi_plan_t const* plan, int32_t a, int32_t b);
+
+/* ---------------------------------------------------------------------------------------------
+ * internal node numbering for meshes numbered without locality (renumber.c)
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct bfmi_renum {
+	int refs;
+
+	/* cache key */
+	bfm_mesh_t const* orig;
+	size_t n_nodes, n_elems;
+	int kind;
+	uint64_t hash;      /* of the caller's connectivity */
+
+	int32_t* to_new;    /* [n_nodes] the caller's node -> internal node */
+	int32_t* to_old;    /* ... and back */
+	int32_t* d_to_new;  /* device copy (bfmi_renum_upload) */
+
+	bfm_mesh_t mesh;    /* the internal mesh: same elements in the same order, nodes renumbered; no edges, no domains */
+	uint64_t mesh_hash; /* of its connectivity */
+} bfmi_renum_t;
+
+/* NULL: the caller's numbering is kept.  Otherwise retained, with the coordinates of the internal mesh refreshed
+ * from the caller's.  hash = bfmi_mesh_hash(mesh) */
+BFMI_HIDDEN bfmi_renum_t* bfmi_renum_for_mesh(bfm_mesh_t const* mesh, uint64_t hash);
+BFMI_HIDDEN void bfmi_renum_release(bfmi_renum_t* r);
+BFMI_HIDDEN void bfmi_renum_forget(bfm_mesh_t const* mesh);
+BFMI_HIDDEN int bfmi_renum_upload(bfmi_renum_t* r);
 
 /* ---------------------------------------------------------------------------------------------
  * row partition of a mesh over the ranks of a multi-GPU job (partition.c)

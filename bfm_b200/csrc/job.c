@@ -62,6 +62,9 @@ struct bfmx_job {
 	bfm_mesh_t const* gmesh; /* the instance's mesh (global numbering) */
 	bfm_mesh_t const* mesh;  /* what this rank assembles: gmesh, or the local mesh of its partition */
 
+	bfmi_renum_t* renum;     /* bfm_sim_run on a mesh numbered without locality: the internally renumbered copy the job works on (renumber.c); else NULL */
+	double* d_xp;            /* ... and the solution back in the caller's numbering */
+
 	bfmi_part_t* part;       /* NULL on one GPU */
 	bfmi_plan_t* plan;       /* of `mesh` */
 	bfmg_pattern_t pat;      /* plan->dev with the owned row range */
@@ -647,6 +650,56 @@ static void localize_op(bfmi_part_t const* part, bc_op_t* op) {
 	op->n_groups = kept_groups;
 }
 
+/* the lists above are in the caller's DOF numbers; the job works on the internal numbering of renumber.c.  Dirichlet
+ * lists are put back in ascending order of the new numbers (k_bc_dirichlet and affected_rows expect ascending DOFs;
+ * which DOFs are constrained and to what value does not change); the additions of a group keep their order */
+typedef struct {
+	int32_t dof;
+	int32_t at;
+} dof_at_t;
+
+static int cmp_dof_at(void const* a, void const* b) {
+	dof_at_t const* const x = a;
+	dof_at_t const* const y = b;
+	return x->dof < y->dof ? -1 : x->dof > y->dof;
+}
+
+static int renumber_op(bfmi_renum_t const* renum, bc_op_t* op) {
+	if (op->kind != OP_DIRICHLET) {
+		for (int32_t g = 0; g < op->n_groups; g++) {
+			op->group_dof[g] = 2 * renum->to_new[op->group_dof[g] / 2] + op->group_dof[g] % 2;
+		}
+
+		return 0;
+	}
+
+	dof_at_t* const order = malloc(((size_t) op->n_dofs + 1) * sizeof *order);
+	double* const vals = malloc(((size_t) op->n_dofs + 1) * sizeof *vals);
+
+	if (order == NULL || vals == NULL) {
+		free(order), free(vals);
+		return -1;
+	}
+
+	for (int32_t i = 0; i < op->n_dofs; i++) {
+		order[i].dof = 2 * renum->to_new[op->dofs[i] / 2] + op->dofs[i] % 2;
+		order[i].at = i;
+	}
+
+	qsort(order, (size_t) op->n_dofs, sizeof *order, cmp_dof_at);
+
+	for (int32_t i = 0; i < op->n_dofs; i++) {
+		op->dofs[i] = order[i].dof;
+		vals[i] = op->vals[order[i].at];
+	}
+
+	free(order);
+	free(op->vals);
+	op->vals = vals;
+
+	return 0;
+}
+
 /* one instance's conditions, in instance order, as work lists in the DOF numbering of `gmesh` */
 static int build_ops_for(bfm_mesh_t const* gmesh, bfm_sim_kind_t sim_kind, bfm_instance_t const* instance, bc_op_t** out_ops, size_t* out_n) {
 	bool const axisym = sim_kind == BFM_SIM_KIND_AXISYMMETRIC_STRAIN;
@@ -725,6 +778,10 @@ static int build_ops(bfmx_job_t* job) {
 
 	for (size_t i = 0; i < job->n_ops; i++) {
 		bc_op_t* const op = &job->ops[i];
+
+		if (job->renum != NULL && renumber_op(job->renum, op) < 0) {
+			return -1;
+		}
 
 		if (job->part != NULL) {
 			localize_op(job->part, op);
@@ -834,14 +891,19 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 
 #define MARK(what) do { if (verbose) { double const now_ = now_ms(); fprintf(stderr, "[job] %-28s %8.2f ms\n", (what), now_ - t_mark); t_mark = now_; } } while (0)
 
-	/* several GPUs: this rank assembles and solves the local mesh of its row block (partition.c) */
+	/* bfm_sim_run only (the public matrix API keeps the caller's numbering): the hash of the connectivity keys every
+	 * per-mesh cache below.  Several GPUs: every rank holds the GLOBAL connectivity (1.2 GB at 50 M DOF), so each
+	 * hashes its world-th of it and the parts are combined over the communicator */
 
-	if (partitioned && bfmg_dist_world() > 1) {
-		/* the partition is cached by the hash of the GLOBAL connectivity (1.2 GB at 50 M DOF), which every rank holds:
-		 * each rank hashes its world-th of it and the parts are combined over the communicator */
-		uint64_t hash = 0;
+	uint64_t hash = 0;
+	bfm_mesh_t const* wmesh = mesh; /* the mesh the job works on, before any partition */
 
-		{
+	if (partitioned) {
+		if (bfmg_dist_world() == 1) {
+			hash = bfmi_mesh_hash(mesh);
+		}
+
+		else {
 			int const world = bfmg_dist_world();
 			uint64_t const mine = bfmi_mesh_hash_part(mesh, bfmg_dist_rank(), world);
 			double parts[2] = {(double) (uint32_t) mine, (double) (uint32_t) (mine >> 32)}; /* exact in a double */
@@ -867,7 +929,31 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 			}
 		}
 
-		job->part = bfmi_part_for_mesh(state, mesh, hash, bfmg_dist_rank(), bfmg_dist_world());
+		MARK("connectivity hash");
+
+		/* a numbering without locality (renumber.c): from here on the job works on an internally renumbered copy of
+		 * the mesh - same elements, same order - and hands the displacements back in the caller's numbering */
+
+		job->renum = bfmi_renum_for_mesh(mesh, hash);
+
+		if (job->renum != NULL) {
+			wmesh = &job->renum->mesh;
+			hash = job->renum->mesh_hash;
+			job->mesh = wmesh;
+
+			if (bfmi_renum_upload(job->renum) < 0 || bfmg_alloc((void**) &job->d_xp, mesh->n_nodes * 2 * sizeof(double)) < 0) {
+				BFMI_FAIL(state, "device allocation failed: %s", bfmg_last_error());
+				goto fail;
+			}
+		}
+
+		MARK("numbering (cache look-up)");
+	}
+
+	/* several GPUs: this rank assembles and solves the local mesh of its row block (partition.c) */
+
+	if (partitioned && bfmg_dist_world() > 1) {
+		job->part = bfmi_part_for_mesh(state, wmesh, hash, bfmg_dist_rank(), bfmg_dist_world());
 
 		if (job->part == NULL) {
 			goto fail;
@@ -878,7 +964,7 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 
 	MARK("partition (cache look-up)");
 
-	job->plan = bfmi_plan_for_mesh(state, job->mesh);
+	job->plan = partitioned && job->part == NULL ? bfmi_plan_for_mesh_hashed(state, job->mesh, hash) : bfmi_plan_for_mesh(state, job->mesh);
 
 	if (job->plan == NULL) {
 		goto fail;
@@ -1004,7 +1090,7 @@ static int job_create(bfmx_job_t** out, bfm_state_t* state, bfm_sim_kind_t kind,
 		if (target >= 4) {
 			bool none;
 
-			job->coarse = bfmi_coarse_for_mesh(state, mesh, job->plan->elems_hash, job->part, (int32_t) target, &none);
+			job->coarse = bfmi_coarse_for_mesh(state, wmesh, job->plan->elems_hash, job->part, (int32_t) target, &none);
 
 			if (job->coarse != NULL && bfmi_coarse_upload(job->coarse) < 0) {
 				BFMI_FAIL(state, "uploading the coarse level failed: %s", bfmg_last_error());
@@ -1502,6 +1588,7 @@ int bfmx_job_destroy(bfmx_job_t* job) {
 	bfmg_free(job->d_stamp);
 	bfmg_free(job->d_cval);
 	bfmg_free(job->d_xg);
+	bfmg_free(job->d_xp);
 	bfmi_coarse_release(job->coarse);
 	bfmi_hier_release(job->hier);
 	bfmg_free(job->d_tabs);
@@ -1521,6 +1608,7 @@ int bfmx_job_destroy(bfmx_job_t* job) {
 
 	bfmi_plan_release(job->plan);
 	bfmi_part_release(job->part);
+	bfmi_renum_release(job->renum);
 	free(job);
 
 	return 0;
@@ -1754,6 +1842,16 @@ int bfmx_job_download(bfmx_job_t* job) {
 		d_src = job->d_xg;
 	}
 
+	/* an internally renumbered job: node a of the caller is node to_new[a] here */
+
+	if (job->renum != NULL) {
+		if (bfmg_gather_blocks(job->d_xp, d_src, job->renum->d_to_new, job->renum->n_nodes) < 0) {
+			return BFMI_FAIL(job->state, "reordering the displacements failed: %s", bfmg_last_error());
+		}
+
+		d_src = job->d_xp;
+	}
+
 	/* effects[node * dim + k] = x[node * dim + k] (sim.c:127-131): same interleaving, one copy */
 
 	if (bytes >= ((size_t) 32 << 20)) {
@@ -1787,6 +1885,18 @@ int bfmx_job_spmv_time(bfmx_job_t* job, int reps, float* ms_per_launch) {
 
 int bfmx_job_read(bfmx_job_t* job, double* b, double* x) {
 	size_t const bytes = (size_t) job->plan->nb * 2 * sizeof(double); /* local rows on a partitioned job */
+
+	if (job->renum != NULL && job->part == NULL) { /* internally renumbered: hand both back in the caller's numbering */
+		if (b != NULL && (!job->assembled || bfmg_gather_blocks(job->d_xp, job->d_b, job->renum->d_to_new, job->renum->n_nodes) < 0 || bfmg_download(b, job->d_xp, bytes) < 0)) {
+			return -1;
+		}
+
+		if (x != NULL && (!job->solved || bfmg_gather_blocks(job->d_xp, job->d_x, job->renum->d_to_new, job->renum->n_nodes) < 0 || bfmg_download(x, job->d_xp, bytes) < 0)) {
+			return -1;
+		}
+
+		return 0;
+	}
 
 	if (b != NULL && (!job->assembled || bfmg_download(b, job->d_b, bytes) < 0)) {
 		return -1;

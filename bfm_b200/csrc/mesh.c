@@ -31,6 +31,7 @@ int bfm_mesh_destroy(bfm_mesh_t* mesh) {
 	bfmi_plan_forget(mesh); /* drop any cached symbolic plan keyed on this mesh */
 	bfmi_part_forget(mesh); /* ... and its row partition */
 	bfmi_coarse_forget(mesh); /* ... and the solver's aggregates */
+	bfmi_renum_forget(mesh); /* ... and its internally renumbered copy */
 
 	bfmg_host_unpin(mesh->coords); /* bfm_sim_run page-locks large coordinate arrays in place */
 

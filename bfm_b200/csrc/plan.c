@@ -484,11 +484,15 @@ static struct {
 static uint64_t cache_clock;
 
 bfmi_plan_t* bfmi_plan_for_mesh(bfm_state_t* state, bfm_mesh_t const* mesh) {
+	return bfmi_plan_for_mesh_hashed(state, mesh, hash_elems(mesh->elems, mesh->n_elems * mesh->kind));
+}
+
+/* hash = bfmi_mesh_hash(mesh), for callers that have it already (1.2 GB to read at 50 M DOF) */
+bfmi_plan_t* bfmi_plan_for_mesh_hashed(bfm_state_t* state, bfm_mesh_t const* mesh, uint64_t hash) {
 	if (mesh->dim != 2 || (mesh->kind != BFM_ELEM_KIND_SIMPLEX && mesh->kind != BFM_ELEM_KIND_QUAD)) {
 		return NULL; /* reference system.c:436-442 */
 	}
 
-	uint64_t const hash = hash_elems(mesh->elems, mesh->n_elems * mesh->kind);
 	int victim = 0;
 
 	for (int i = 0; i < CACHE_SLOTS; i++) {

@@ -484,6 +484,16 @@ __global__ void __launch_bounds__(kBlock) k_sym_walk_half_edges(int32_t const* _
 	}
 }
 
+/* ---- back from the internal numbering -------------------------------------------------------------------- */
+
+__global__ void __launch_bounds__(kBlock) k_gather_blocks(double2* __restrict__ dst, double2 const* __restrict__ src, int32_t const* __restrict__ index, int64_t n) {
+	pdl_sync();
+
+	for (int64_t i = (int64_t) blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t) gridDim.x * kBlock) {
+		dst[i] = src[index[i]];
+	}
+}
+
 int grid_for(int64_t items) {
 	return bfmg_grid((items + kBlock - 1) / kBlock, 8);
 }
@@ -675,4 +685,12 @@ done:
 	bfmg_free(keys);
 
 	return rv;
+}
+
+extern "C" int bfmg_gather_blocks(double* d_dst, double const* d_src, int32_t const* d_index, size_t n) {
+	if (!bfmg_ready()) {
+		return -1;
+	}
+
+	return n == 0 ? 0 : BFMG_LAUNCH(k_gather_blocks, grid_for((int64_t) n), kBlock, 0, (double2*) d_dst, (double2 const*) d_src, d_index, (int64_t) n);
 }

@@ -99,6 +99,7 @@ PROTOTYPES = {
 	"bfmx_job_batch_status": (_int, [C.c_void_p, C.c_size_t, _P(BatchStatus)]),
 	"bfmx_sim_run_batch": (_int, [_P(_P(abi.Sim)), C.c_size_t]),
 	"bfmx_mesh_compute_edges": (_int, [_P(abi.Mesh)]),
+	"bfmx_mesh_internal_numbering": (_int, [_P(abi.Mesh), _P(C.c_int32)]),
 	"bfmx_mesh_plate": (_int, [_P(abi.Mesh), _P(abi.State), C.c_size_t, C.c_size_t, C.c_double, C.c_double, _int, C.c_bool]),
 	"bfmx_mesh_pattern_sizes": (_int, [_P(abi.Mesh), _P(C.c_size_t), _P(C.c_size_t), _P(C.c_size_t), _P(C.c_size_t)]),
 	"bfmx_mesh_pattern_copy": (_int, [_P(abi.Mesh), c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_uint32_p]),
@@ -218,6 +219,16 @@ def plate(nx: int, ny: int, lx: float = 4.0, ly: float = 1.0, kind: int = 3, wit
 	mesh.dim = 2
 	mesh.kind = kind
 	return mesh
+
+
+def internal_numbering(mesh):
+	"""to_new (numpy int32) when bfm_sim_run would work on an internally renumbered copy of this mesh, else None"""
+
+	to_new = np.zeros(mesh.c_mesh.n_nodes, np.int32)
+	rv = mesh.binding.lib.bfmx_mesh_internal_numbering(C.byref(mesh.c_mesh), to_new.ctypes.data_as(c_int32_p))
+	assert rv >= 0
+
+	return to_new if rv == 1 else None
 
 
 def pattern(mesh) -> dict:

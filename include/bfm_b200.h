@@ -124,6 +124,12 @@ int bfmx_sim_run_batch(bfm_sim_t** sims, size_t n_sims);
 /* (re)derive mesh->edges from the connectivity exactly as the Wavefront reader does (reference mesh.c:52-102) */
 int bfmx_mesh_compute_edges(bfm_mesh_t* mesh);
 
+/* Does bfm_sim_run work on an internally renumbered copy of this mesh (bfm_b200/csrc/renumber.c: a numbering with no
+ * locality - mean node-number span of an element above 2^20 - or BFM_RENUMBER=1)?  1: yes, and to_new[a] (if not NULL,
+ * n_nodes entries) is the internal number of the caller's node a along a Morton curve through the coordinates;
+ * 0: the caller's numbering is used as it is; -1: error.  Results always come back in the caller's numbering. */
+int bfmx_mesh_internal_numbering(bfm_mesh_t* mesh, int32_t* to_new);
+
 /* structured plate [0,lx]x[0,ly] with nx*ny cells: 2 triangles (a,b,d),(a,d,c) per cell, or 1 quad */
 int bfmx_mesh_plate(bfm_mesh_t* mesh, bfm_state_t* state, size_t nx, size_t ny, double lx, double ly, bfm_elem_kind_t kind, bool with_edges);
 

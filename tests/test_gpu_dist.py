@@ -23,7 +23,7 @@ def _gpu_count() -> int:
 		return 0
 
 
-@pytest.mark.parametrize("world,exchange", [(2, "peer"), (2, "nccl"), (4, "peer"), (8, "peer")])
+@pytest.mark.parametrize("world,exchange", [(2, "peer"), (2, "nccl"), (2, "peer-renumbered"), (4, "peer"), (8, "peer")])
 def test_partitioned_run_matches_reference(world, exchange, tmp_path):
 	"""exchange: the per-iteration halo / dot-product / coarse exchanges over NVLink peer memory (CUDA IPC
 	mailboxes, posted from inside the kernels - the default) or over NCCL (BFM_P2P=0)"""
@@ -39,6 +39,10 @@ def test_partitioned_run_matches_reference(world, exchange, tmp_path):
 	]
 
 	env = dict(os.environ, BFM_P2P="0" if exchange == "nccl" else "1")
+
+	if exchange == "peer-renumbered": # every mesh partitioned on its internal Morton numbering (bfm_b200/csrc/renumber.c)
+		env["BFM_RENUMBER"] = "1"
+
 	proc = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
 	assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-6000:]
 
@@ -51,4 +55,4 @@ def test_partitioned_run_matches_reference(world, exchange, tmp_path):
 			assert r["converged"] == 1 and r["rel_residual"] <= 1e-12, (rank, name, r)
 			assert r["err"] <= 1e-9, (rank, name, r)
 			assert r["same_on_all_ranks"] and r["b_bitwise"] and r["staged_equals_run"], (rank, name, r)
-			assert r["n_ranks"] == world and r["peer_memory"] == (1 if exchange == "peer" else 0)
+			assert r["n_ranks"] == world and r["peer_memory"] == (0 if exchange == "nccl" else 1)

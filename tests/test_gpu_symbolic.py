@@ -158,3 +158,74 @@ def test_large_plate_runs_on_the_device_built_plan(lib):
 		out.append(np.array(case.instance.effects))
 
 	assert np.array_equal(out[0], out[1])
+
+
+# ---- internal numbering (bfm_b200/csrc/renumber.c) ---------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name", ["lepl8_all_kinds", "plate_neumann_16x4", "plate_funky_20x5", "plate_q4_24x6", "lepl8_axisym", "bridge", "gear60", "plate_160x40"])
+@pytest.mark.parametrize("one_cta", ["1", "0"])
+def test_renumbered_run_matches_reference(name, one_cta, lib, golden):
+	"""bfm_sim_run on the internally renumbered copy of the mesh (forced: these meshes are small and well numbered):
+	all condition kinds, non-zero Dirichlet values, Neumann loads in edge order, FUNKY forces, quads, axisymmetry -
+	displacements come back in the caller's numbering, within 1e-9 of the reference's direct solve"""
+
+	with _env(BFM_RENUMBER="1", BFM_ONE_CTA=one_cta):
+		case = cases.build(name, lib)
+		assert ext.internal_numbering(case.mesh) is not None
+		case.sim.run()
+
+	stats = ext.last_stats(lib)
+	want = golden[f"{name}/effects"]
+
+	assert stats["cg_converged"] == 1
+	assert float(np.linalg.norm(np.asarray(case.instance.effects) - want) / np.linalg.norm(want)) <= 1e-9
+
+
+def test_randomly_numbered_plate_on_its_internal_numbering(lib):
+	"""the plate with nodes numbered at random and elements in random order: solved on the Morton numbering it gives
+	the displacements of the naturally numbered plate (compared node by node through the permutation)"""
+
+	from bfm_b200 import workloads
+
+	nx, ny = 600, 150
+	coords, elems = cases.plate_arrays(nx, ny)
+	new_coords, new_elems = shuffled(coords, elems, seed=5)
+
+	# recover the permutation the helper drew: new_coords[perm] = coords
+	perm = np.random.RandomState(5).permutation(len(coords))
+
+	def solve(c, e, renumber):
+		with _env(BFM_RENUMBER=renumber):
+			mesh = api.Mesh.from_arrays(c, e, binding=lib)
+			left = c[:, 0] == 0.0
+			E, nu, rho = workloads.STEEL
+			material = api.Material("steel", rho, E, nu, binding=lib)
+			rule = api.Rule_gauss_legendre(2, mesh.kind, binding=lib)
+			obj = api.Obj(mesh, material, rule)
+			instance = api.Instance(obj)
+			keep = [mesh, material, rule, obj]
+
+			for kind in (api.Condition.DIRICHLET_X, api.Condition.DIRICHLET_Y):
+				cond = api.Condition(mesh, kind, 0.0)
+				cond.set_nodes(left)
+				instance.add_condition(cond)
+				keep.append(cond)
+
+			sim = api.Sim(api.CSim.PLANAR_STRESS, binding=lib)
+			sim.add_instance(instance)
+			force = api.Force_linear(workloads.GRAVITY, binding=lib)
+			sim.add_force(force)
+			sim.run()
+
+			assert ext.last_stats(lib)["cg_converged"] == 1
+			return workloads.effects_view(instance).reshape(-1, 2).copy()
+
+	natural = solve(coords, elems, "0")
+	kept = solve(new_coords, new_elems, "0")
+	morton = solve(new_coords, new_elems, "1")
+
+	norm = np.linalg.norm(natural)
+
+	assert np.linalg.norm(kept[perm] - natural) / norm <= 1e-9
+	assert np.linalg.norm(morton[perm] - natural) / norm <= 1e-9

@@ -573,3 +573,35 @@ def test_edge_derivation_parallel_path_matches_live_reference(lib, ref, tmp_path
 	assert len(want) > (1 << 17)
 	assert np.array_equal(got_reader, want)
 	assert np.array_equal(got_generator, want)
+
+
+def test_internal_numbering_is_a_local_permutation(lib, monkeypatch):
+	"""renumber.c: a mesh numbered at random gets a Morton numbering (a permutation; elements keep their node sets;
+	the mean node-number span of an element collapses); small or well numbered meshes are left alone"""
+
+	nx, ny = 240, 60
+	coords, elems = cases.plate_arrays(nx, ny)
+	rng = np.random.RandomState(3)
+	perm = rng.permutation(len(coords))
+	shuffled_coords = np.empty_like(coords)
+	shuffled_coords[perm] = coords
+	shuffled_elems = perm[elems.astype(np.int64)].astype(np.uint64)
+
+	def span(e):
+		e = np.asarray(e, np.int64)
+		return float((e.max(axis=1) - e.min(axis=1)).mean())
+
+	monkeypatch.delenv("BFM_RENUMBER", raising=False)
+	assert ext.internal_numbering(api.Mesh.from_arrays(shuffled_coords, shuffled_elems, binding=lib)) is None  # 14 701 nodes: fits any cache
+
+	monkeypatch.setenv("BFM_RENUMBER", "0")
+	assert ext.internal_numbering(api.Mesh.from_arrays(shuffled_coords, shuffled_elems, binding=lib)) is None
+
+	monkeypatch.setenv("BFM_RENUMBER", "1")
+	mesh = api.Mesh.from_arrays(shuffled_coords, shuffled_elems, binding=lib)
+	to_new = ext.internal_numbering(mesh)
+
+	assert to_new is not None and np.array_equal(np.sort(to_new), np.arange(len(coords)))
+	assert span(shuffled_elems) > len(coords) / 4            # random: an element spans a third of the numbering
+	assert span(to_new[shuffled_elems.astype(np.int64)]) < 4 * (nx + 2)  # Morton: comparable with the row-by-row numbering's nx + 2
+	assert np.array_equal(ext.internal_numbering(mesh), to_new)          # cached, deterministic

@@ -1,6 +1,7 @@
 """How much does node numbering cost?  The structured plate with its nodes renumbered at random (seeded) - the worst case
 for every gather of the solver: q = A p reads p at scattered rows, the aggregates' members are scattered - against the
-same plate in natural order.  Prints one JSON line per variant (profiles/r2_summary.md quotes it).
+same plate in natural order.  Prints one JSON line per variant (profiles/r2_summary.md quotes it), and the same randomly numbered plate run on the
+internal Morton numbering of bfm_b200/csrc/renumber.c.
 
     python tools/irregular_probe.py [NXxNY]           # default 1600x400 = 1.28 M nodes, 2.6 M DOF
 """
@@ -22,7 +23,12 @@ binding = api.default_binding()
 assert ext.device_available(binding), binding.lib.bfmx_device_error()
 
 
-def run(label, coords, elems):
+def run(label, coords, elems, renumber=None):
+	if renumber is None:
+		os.environ.pop("BFM_RENUMBER", None)
+	else:
+		os.environ["BFM_RENUMBER"] = renumber
+
 	mesh = api.Mesh.from_arrays(coords, elems, binding=binding)
 	left = coords[:, 0] == 0.0
 	E, nu, rho = workloads.STEEL
@@ -54,12 +60,12 @@ def run(label, coords, elems):
 	job.download()
 
 	print(json.dumps({
-		"numbering": label, "cells": cells, "n_dofs": s["n_dofs"], "cg_iterations": s["cg_iterations"], "mg_levels": s["mg_levels"],
+		"numbering": label, "internally_renumbered": ext.internal_numbering(mesh) is not None, "cells": cells, "n_dofs": s["n_dofs"], "cg_iterations": s["cg_iterations"], "mg_levels": s["mg_levels"],
 		"solve_ms": s["ms_solve"], "us_per_iteration": (s["ms_solve"] - s["ms_solve_setup"]) * 1e3 / max(s["cg_iterations"], 1),
 		"spmv_us": spmv_ms * 1e3, "spmv_stored_format_gbs": stored / (spmv_ms * 1e-3) / 1e9, "assemble_ms": s["ms_assemble"],
 	}), flush=True)
 
-	return np.array(instance.effects)
+	return workloads.effects_view(instance).reshape(-1, 2).copy()
 
 
 coords, elems = workloads.plate_arrays(nx, ny)
@@ -70,7 +76,12 @@ perm = rng.permutation(len(coords))          # new id of old node a = perm[a]
 inverse = np.empty_like(perm)
 inverse[perm] = np.arange(len(perm))
 
-shuffled = run("random", coords[inverse], perm[elems.astype(np.int64)].astype(np.uint64))
+random_coords, random_elems = coords[inverse], perm[elems.astype(np.int64)].astype(np.uint64)
 
-err = np.linalg.norm(shuffled[perm] - natural) / np.linalg.norm(natural)
-print(json.dumps({"same_displacements_rel_l2": float(err)}), flush=True)
+kept = run("random, kept (BFM_RENUMBER=0)", random_coords, random_elems, renumber="0")
+auto = run("random, library's choice", random_coords, random_elems)
+forced = run("random, Morton (BFM_RENUMBER=1)", random_coords, random_elems, renumber="1")
+
+for label, got in (("kept", kept), ("auto", auto), ("forced", forced)):
+	err = np.linalg.norm(got[perm] - natural) / np.linalg.norm(natural)
+	print(json.dumps({"variant": label, "same_displacements_rel_l2": float(err)}), flush=True)
