@@ -269,6 +269,7 @@ int bfmx_mesh_compute_edges(bfm_mesh_t* mesh) {
 typedef struct {
 	char* buf;
 	char const* at;
+	char const* end; /* the terminating NUL */
 } scan_t;
 
 static int scan_open(scan_t* sc, char const* path) {
@@ -294,6 +295,7 @@ static int scan_open(scan_t* sc, char const* path) {
 
 	sc->buf[size] = '\0';
 	sc->at = sc->buf;
+	sc->end = sc->buf + size;
 
 	return 0;
 }
@@ -394,6 +396,148 @@ static void scan_skip_line(scan_t* sc) {
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * big files: the long sections, one record per line, parsed by all threads
+ *
+ * A 25 M-node mesh is gigabytes of text, and a single thread converting it with strtod takes the better part of a
+ * minute.  The sections that matter ("i : x y" nodes and "i : a b c [d]" elements of a LEPL1110 file, "v" and "f"
+ * lines of an OBJ) are written one record per line by every tool around, so: find the line starts in parallel
+ * (newlines counted per 1 MB chunk, prefix sum), let every thread parse its share of the lines with the SAME token
+ * scanners as the serial reader, and check that each line held exactly one record and nothing else.  scanf does not
+ * care about line breaks, so a file may legally split or join records differently; the first line that is not
+ * exactly one record makes the whole section fall back to the serial scanner (whose behaviour is the reference's
+ * fscanf's), so the fast path can only ever produce what the serial one would.  BFM_READER=serial switches it off.
+ * ------------------------------------------------------------------------------------------- */
+
+#define PAR_CHUNK ((size_t) 1 << 20)
+#define PAR_MIN_BYTES ((size_t) 1 << 20) /* smaller inputs are not worth the threads */
+
+static bool reader_parallel(size_t bytes) {
+	char const* const env = getenv("BFM_READER");
+	return bytes >= PAR_MIN_BYTES && (env == NULL || strcmp(env, "serial") != 0);
+}
+
+/* line starts from `from` on: starts[0] = from, starts[i] = one past the i-th newline; at most `want` lines.
+ * Returns the lines found (each line i is [starts[i], starts[i + 1])), or 0 without memory; *out is malloc'd */
+static size_t index_lines(char const* from, char const* end, size_t want, char const*** out) {
+	size_t const bytes = (size_t) (end - from);
+	size_t const n_chunks = (bytes + PAR_CHUNK - 1) / PAR_CHUNK;
+	size_t* const count = calloc(n_chunks + 2, sizeof *count);
+
+	*out = NULL;
+
+	if (count == NULL || bytes == 0 || want == 0) {
+		free(count);
+		return 0;
+	}
+
+#pragma omp parallel for schedule(static)
+	for (size_t c = 0; c < n_chunks; c++) {
+		char const* at = from + c * PAR_CHUNK;
+		char const* const stop = c + 1 < n_chunks ? at + PAR_CHUNK : end;
+		size_t n = 0;
+
+		while ((at = memchr(at, '\n', (size_t) (stop - at))) != NULL) {
+			n++, at++;
+		}
+
+		count[c + 1] = n;
+	}
+
+	for (size_t c = 0; c < n_chunks; c++) {
+		count[c + 1] += count[c];
+	}
+
+	size_t const newlines = count[n_chunks];
+	size_t lines = newlines + (end[-1] != '\n'); /* a last line without its newline still counts */
+
+	lines = lines < want ? lines : want;
+
+	char const** const starts = malloc((lines + 2) * sizeof *starts);
+
+	if (starts == NULL) {
+		free(count);
+		return 0;
+	}
+
+	starts[0] = from;
+	starts[lines] = end; /* overwritten below when the file goes on after the last wanted line */
+
+#pragma omp parallel for schedule(static)
+	for (size_t c = 0; c < n_chunks; c++) {
+		char const* at = from + c * PAR_CHUNK;
+		char const* const stop = c + 1 < n_chunks ? at + PAR_CHUNK : end;
+		size_t idx = count[c];
+
+		while (idx < lines && (at = memchr(at, '\n', (size_t) (stop - at))) != NULL) {
+			starts[++idx] = ++at;
+		}
+	}
+
+	free(count);
+
+	*out = starts;
+	return lines;
+}
+
+/* only blanks between at and stop? (and the scanner did not run past the line) */
+static bool line_done(char const* at, char const* stop) {
+	if (at > stop) {
+		return false;
+	}
+
+	for (; at < stop; at++) {
+		if (!isspace((unsigned char) *at)) {
+			return false;
+		}
+	}
+
+	return true;
+}
+
+/* `n` records "index : v v .." of `width` values each (doubles into dvals, else sizes into svals), one per line, from
+ * the scanner's position on.  true: all parsed, scanner moved behind them.  false: not in that shape (or too small to
+ * bother): nothing consumed, the caller scans them one by one */
+static bool scan_records_parallel(scan_t* sc, size_t n, size_t width, double* dvals, size_t* svals) {
+	if (n < 4096 || !reader_parallel((size_t) (sc->end - sc->at))) {
+		return false;
+	}
+
+	scan_t first = *sc;
+
+	scan_ws(&first); /* the rest of the header line */
+
+	char const** starts;
+	size_t const lines = index_lines(first.at, sc->end, n, &starts);
+
+	if (lines != n) {
+		free(starts);
+		return false;
+	}
+
+	bool ok = true;
+
+#pragma omp parallel for schedule(static) reduction(&& : ok)
+	for (size_t i = 0; i < n; i++) {
+		scan_t line = {.buf = NULL, .at = starts[i], .end = sc->end};
+		size_t index;
+		bool good = scan_size(&line, &index) && scan_lit(&line, " :");
+
+		for (size_t k = 0; good && k < width; k++) {
+			good = dvals != NULL ? scan_double(&line, &dvals[i * width + k]) : scan_size(&line, &svals[i * width + k]);
+		}
+
+		ok = ok && good && line_done(line.at, starts[i + 1]);
+	}
+
+	if (ok) {
+		sc->at = starts[n];
+	}
+
+	free(starts);
+	return ok;
+}
+
+/* ---------------------------------------------------------------------------------------------
  * LEPL1110 text meshes (reference mesh.c:104-201)
  *
  *   Number of nodes N          then N lines  "i : x y"
@@ -432,7 +576,7 @@ int bfm_mesh_read_lepl1110(bfm_mesh_t* mesh, bfm_state_t* state, char const* nam
 		goto done;
 	}
 
-	for (size_t i = 0; i < mesh->n_nodes; i++) {
+	for (size_t i = scan_records_parallel(&sc, mesh->n_nodes, 2, mesh->coords, NULL) ? mesh->n_nodes : 0; i < mesh->n_nodes; i++) {
 		if (!scan_size(&sc, &index) || !scan_lit(&sc, " :") || !scan_double(&sc, &mesh->coords[2 * i]) || !scan_double(&sc, &mesh->coords[2 * i + 1])) {
 			goto done;
 		}
@@ -488,7 +632,7 @@ int bfm_mesh_read_lepl1110(bfm_mesh_t* mesh, bfm_state_t* state, char const* nam
 		goto done;
 	}
 
-	for (size_t i = 0; i < mesh->n_elems; i++) {
+	for (size_t i = scan_records_parallel(&sc, mesh->n_elems, mesh->kind, NULL, mesh->elems) ? mesh->n_elems : 0; i < mesh->n_elems; i++) {
 		if (!scan_size(&sc, &index) || !scan_lit(&sc, " :")) {
 			goto done;
 		}
@@ -563,6 +707,176 @@ done:
  * line is skipped.  z is kept only when `full`.
  * ------------------------------------------------------------------------------------------- */
 
+/* what one line of an OBJ file is to the reader */
+enum { OBJ_SKIP, OBJ_VERTEX, OBJ_FACE, OBJ_ODD };
+
+/* classifies the line [at, stop) and, when out pointers are given, parses it.  OBJ_ODD: a line the serial scanner
+ * would not treat as one self-contained record (a record running over the line end, or something after it that could
+ * itself be a record) */
+static int obj_line(char const* at, char const* stop, char const* end, size_t dim, double* xyz_out, size_t* tri_out) {
+	scan_t line = {.buf = NULL, .at = at, .end = end};
+	char header[16];
+
+	scan_ws(&line);
+
+	if (line.at >= stop) {
+		return OBJ_SKIP; /* blank */
+	}
+
+	scan_word(&line, header, sizeof header);
+
+	if (strcmp(header, "v") == 0) {
+		double xyz[3];
+
+		for (size_t k = 0; k < 3; k++) {
+			if (!scan_double(&line, &xyz[k]) || line.at > stop) {
+				return OBJ_ODD;
+			}
+		}
+
+		if (!line_done(line.at, stop)) {
+			return OBJ_ODD;
+		}
+
+		if (xyz_out != NULL) {
+			memcpy(xyz_out, xyz, dim * sizeof *xyz);
+		}
+
+		return OBJ_VERTEX;
+	}
+
+	if (strcmp(header, "f") == 0) {
+		size_t tri[3];
+
+		for (size_t k = 0; k < 3; k++) {
+			if (!scan_size(&line, &tri[k]) || line.at > stop) {
+				return OBJ_ODD;
+			}
+
+			tri[k]--;
+
+			while (*line.at != '\0' && !isspace((unsigned char) *line.at)) { /* "a/at/an" */
+				line.at++;
+			}
+		}
+
+		if (!line_done(line.at, stop)) {
+			return OBJ_ODD;
+		}
+
+		if (tri_out != NULL) {
+			memcpy(tri_out, tri, sizeof tri);
+		}
+
+		return OBJ_FACE;
+	}
+
+	if (strcmp(header, "o") == 0) {
+		char word[256];
+
+		/* "o name": the serial scanner takes the next word as the name, and whatever follows on the line as new
+		 * header words */
+		if (!scan_word(&line, word, sizeof word) || line.at > stop) {
+			return OBJ_ODD;
+		}
+
+		return line_done(line.at, stop) ? OBJ_SKIP : OBJ_ODD;
+	}
+
+	/* anything else: the serial scanner skips the rest of the line; a header of 15+ characters is cut by %15s and its
+	 * tail would be read as the next header - leave that to it */
+	return strlen(header) < sizeof header - 1 ? OBJ_SKIP : OBJ_ODD;
+}
+
+/* the whole file by lines, in parallel (see "big files" above).  1: mesh->coords / elems filled, 0: not in that shape,
+ * -1: out of memory */
+static int read_wavefront_parallel(bfm_mesh_t* mesh, scan_t* sc) {
+	bfm_state_t* const state = mesh->state;
+	size_t const bytes = (size_t) (sc->end - sc->buf);
+
+	if (!reader_parallel(bytes)) {
+		return 0;
+	}
+
+	char const** starts;
+	size_t const lines = index_lines(sc->buf, sc->end, SIZE_MAX / 16, &starts);
+
+	if (lines == 0) {
+		return 0;
+	}
+
+	size_t const block = 4096; /* lines per counting block */
+	size_t const n_blocks = (lines + block - 1) / block;
+	size_t* const first_v = calloc(n_blocks + 1, sizeof *first_v);
+	size_t* const first_f = calloc(n_blocks + 1, sizeof *first_f);
+	bool ok = first_v != NULL && first_f != NULL;
+	int rv = 0;
+
+	if (!ok) {
+		rv = -1;
+		goto out;
+	}
+
+#pragma omp parallel for schedule(static) reduction(&& : ok)
+	for (size_t b = 0; b < n_blocks; b++) {
+		size_t const stop = (b + 1) * block < lines ? (b + 1) * block : lines;
+
+		for (size_t i = b * block; i < stop; i++) {
+			int const what = obj_line(starts[i], starts[i + 1], sc->end, mesh->dim, NULL, NULL);
+
+			first_v[b + 1] += what == OBJ_VERTEX;
+			first_f[b + 1] += what == OBJ_FACE;
+			ok = ok && what != OBJ_ODD;
+		}
+	}
+
+	if (!ok) {
+		goto out;
+	}
+
+	for (size_t b = 0; b < n_blocks; b++) {
+		first_v[b + 1] += first_v[b];
+		first_f[b + 1] += first_f[b];
+	}
+
+	mesh->n_nodes = first_v[n_blocks];
+	mesh->n_elems = first_f[n_blocks];
+	mesh->coords = mesh->n_nodes > 0 ? state->alloc(mesh->n_nodes * mesh->dim * sizeof *mesh->coords) : NULL;
+	mesh->elems = mesh->n_elems > 0 ? state->alloc(mesh->n_elems * 3 * sizeof *mesh->elems) : NULL;
+
+	if ((mesh->n_nodes > 0 && mesh->coords == NULL) || (mesh->n_elems > 0 && mesh->elems == NULL)) {
+		state->free(mesh->coords);
+		state->free(mesh->elems);
+		mesh->coords = NULL, mesh->elems = NULL;
+		mesh->n_nodes = mesh->n_elems = 0;
+		rv = -1;
+		goto out;
+	}
+
+#pragma omp parallel for schedule(static)
+	for (size_t b = 0; b < n_blocks; b++) {
+		size_t const stop = (b + 1) * block < lines ? (b + 1) * block : lines;
+		size_t v = first_v[b], f = first_f[b];
+
+		for (size_t i = b * block; i < stop; i++) {
+			int const what = obj_line(starts[i], starts[i + 1], sc->end, mesh->dim, mesh->coords != NULL ? &mesh->coords[v * mesh->dim] : NULL, mesh->elems != NULL ? &mesh->elems[f * 3] : NULL);
+
+			v += what == OBJ_VERTEX;
+			f += what == OBJ_FACE;
+		}
+	}
+
+	rv = 1;
+
+out:
+
+	free(first_v);
+	free(first_f);
+	free(starts);
+
+	return rv;
+}
+
 int bfm_mesh_read_wavefront(bfm_mesh_t* mesh, bfm_state_t* state, char const* name, bool full) {
 	memset(mesh, 0, sizeof *mesh);
 
@@ -581,7 +895,13 @@ int bfm_mesh_read_wavefront(bfm_mesh_t* mesh, bfm_state_t* state, char const* na
 	char header[16];
 	int rv = -1;
 
-	while (scan_word(&sc, header, sizeof header)) {
+	int const fast = read_wavefront_parallel(mesh, &sc);
+
+	if (fast < 0) {
+		goto done;
+	}
+
+	while (fast == 0 && scan_word(&sc, header, sizeof header)) {
 		if (strcmp(header, "o") == 0) {
 			char obj_name[256];
 			scan_word(&sc, obj_name, sizeof obj_name);

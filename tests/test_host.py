@@ -605,3 +605,103 @@ def test_internal_numbering_is_a_local_permutation(lib, monkeypatch):
 	assert span(shuffled_elems) > len(coords) / 4            # random: an element spans a third of the numbering
 	assert span(to_new[shuffled_elems.astype(np.int64)]) < 4 * (nx + 2)  # Morton: comparable with the row-by-row numbering's nx + 2
 	assert np.array_equal(ext.internal_numbering(mesh), to_new)          # cached, deterministic
+
+
+def _write_obj(path, coords, elems, odd=False, triplets=False):
+	with open(path, "w") as f:
+		f.write("# a comment that mentions v 1 2 3\no plate\n\n")
+		np.savetxt(f, np.c_[coords, np.zeros(len(coords))], fmt="v %.17g %.17g %g")
+		f.write("vn 0 0 1\nvt 0.5 0.5\ns off\n")
+		half = len(elems) // 2
+		np.savetxt(f, elems[:half].astype(np.int64) + 1, fmt="f %d %d %d")
+
+		if triplets:  # "a/at/an": more than the reference's "%zu %zu %zu" reads, tolerated by both of our scanners
+			np.savetxt(f, np.repeat(elems[half:].astype(np.int64) + 1, 3, axis=1), fmt="f %d/%d/%d %d/%d/%d %d/%d/%d")
+		else:
+			np.savetxt(f, elems[half:].astype(np.int64) + 1, fmt="f %d %d %d")
+
+		if odd:  # a record broken over two lines: legal for fscanf, not "one record per line"
+			f.write("v 9.5 8.5\n7.5\nf 1 2\n3\n")
+
+
+@pytest.mark.parametrize("odd", [False, True])
+def test_parallel_wavefront_reader_matches_reference(odd, lib, ref, tmp_path, monkeypatch):
+	"""files above 1 MB are parsed by all threads, one line per record, with a fallback to the serial scanner when a
+	line is not exactly one record: nodes, elements and edges must be the reference reader's either way"""
+
+	coords, elems = cases.plate_arrays(400, 160)
+	path = tmp_path / "plate.obj"
+	_write_obj(path, coords, elems, odd=odd)
+
+	assert path.stat().st_size > (1 << 20)
+
+	want = api.Mesh_wavefront(str(path), binding=ref)
+
+	monkeypatch.delenv("BFM_READER", raising=False)
+	fast = api.Mesh_wavefront(str(path), binding=lib)
+
+	monkeypatch.setenv("BFM_READER", "serial")
+	slow = api.Mesh_wavefront(str(path), binding=lib)
+
+	assert want.n_nodes == len(coords) + odd and want.elems_array.shape[0] == len(elems) + odd
+
+	for got in (fast, slow):
+		assert np.array_equal(got.coords_array, want.coords_array)
+		assert np.array_equal(got.elems_array, want.elems_array)
+		assert np.array_equal(got.edges_array, want.edges_array)
+
+	# vertex/texture/normal triplets: beyond the reference's reader; the two scanners of ours must agree
+	_write_obj(path, coords, elems, odd=odd, triplets=True)
+
+	slow = api.Mesh_wavefront(str(path), binding=lib)
+	monkeypatch.delenv("BFM_READER", raising=False)
+	fast = api.Mesh_wavefront(str(path), binding=lib)
+
+	assert np.array_equal(fast.elems_array, want.elems_array) and np.array_equal(slow.elems_array, want.elems_array)
+	assert np.array_equal(fast.edges_array, want.edges_array)
+
+
+@pytest.mark.parametrize("kind,odd", [(3, False), (4, False), (3, True)])
+def test_parallel_lepl1110_reader_matches_reference(kind, odd, lib, ref, tmp_path, monkeypatch):
+	nx, ny = 300, 150
+	coords, elems = cases.plate_arrays(nx, ny, kind=kind)
+	boundary = np.arange(nx)  # a made-up boundary edge list: (element, node, node)
+	path = tmp_path / "plate.lepl1110"
+
+	with open(path, "w") as f:
+		f.write(f"Number of nodes {len(coords)} \n")
+
+		for i, (x, y) in enumerate(coords):
+			sep = "\n   " if odd and i == 1000 else " "  # one record broken over two lines
+			f.write(f"{i:6d} : {x:14.7e}{sep}{y:14.7e} \n")
+
+		f.write(f"Number of edges {len(boundary)} \n")
+
+		for i in boundary:
+			f.write(f"{i:6d} : {i:6d} {i + 1:6d} \n")
+
+		f.write(f"Number of {'triangles' if kind == 3 else 'quads'} {len(elems)} \n")
+
+		for i, e in enumerate(elems):
+			f.write(f"{i:6d} : " + " ".join(f"{int(v):6d}" for v in e) + " \n")
+
+		f.write("Number of domains 2 \n")
+		f.write("  Domain :      0 \n  Name : Left side \n  Number of elements :      3\n     0      1      2 \n")
+		f.write("  Domain :      1 \n  Name : Entity 1 \n  Number of elements :      2\n     5      6 \n")
+
+	assert path.stat().st_size > (1 << 20)
+
+	want = api.Mesh_lepl1110(str(path), binding=ref)
+
+	monkeypatch.delenv("BFM_READER", raising=False)
+	fast = api.Mesh_lepl1110(str(path), binding=lib)
+
+	monkeypatch.setenv("BFM_READER", "serial")
+	slow = api.Mesh_lepl1110(str(path), binding=lib)
+
+	for got in (fast, slow):
+		assert got.kind == kind and got.n_nodes == len(coords)
+		assert np.array_equal(got.coords_array, want.coords_array)
+		assert np.array_equal(got.elems_array, want.elems_array)
+		assert np.array_equal(got.edges_array, want.edges_array)
+		assert got.c_mesh.n_domains == 2
