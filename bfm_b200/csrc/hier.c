@@ -114,28 +114,43 @@ void bfmi_hier_free(bfmi_hier_t* h) {
  * agg[a] = aggregate of node a, compacted to 0 .. n_agg - 1 in order of each aggregate's smallest node, or -1 for
  * nodes left out of the coarse space (isolated nodes: nothing to interpolate from).  Returns n_agg (0: give up). */
 
+/* root of v without touching the forest: safe while other threads read it too */
+static inline int32_t find_root(int32_t const* parent, int32_t v) {
+	while (parent[v] != v) {
+		v = parent[v];
+	}
+
+	return v;
+}
+
 static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32_t min_nodes, int32_t* agg) {
 	int32_t const n = L->n;
 	double const* const pos = L->pos;
 
 	int32_t const lo = L->row_lo, hi = L->row_hi; /* the nodes this rank aggregates: all of them on one GPU */
+	bool const big = hi - lo > 100000;            /* worth the host threads */
 
+	double x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
+	bool bad = false;
+
+#pragma omp parallel for schedule(static) if (n > 100000)
 	for (int32_t a = 0; a < n; a++) {
 		agg[a] = -1;
 	}
 
-	double x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
-
+#pragma omp parallel for schedule(static) reduction(min : x0, y0) reduction(max : x1, y1) reduction(|| : bad) if (big)
 	for (int32_t a = lo; a < hi; a++) {
 		double const x = pos[2 * (size_t) a + 0];
 		double const y = pos[2 * (size_t) a + 1];
 
-		if (!(x == x) || !(y == y) || isinf(x) || isinf(y)) {
-			return 0;
-		}
+		bad = bad || !(x == x) || !(y == y) || isinf(x) || isinf(y);
 
 		x0 = x < x0 ? x : x0, x1 = x > x1 ? x : x1;
 		y0 = y < y0 ? y : y0, y1 = y > y1 ? y : y1;
+	}
+
+	if (bad) {
+		return 0;
 	}
 
 	double wx = x1 - x0;
@@ -175,12 +190,13 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 		return 0;
 	}
 
+#pragma omp parallel for schedule(static) if (n > 100000)
 	for (int32_t a = 0; a < n; a++) {
 		bin[a] = -1;
 		parent[a] = a;
 	}
 
-#pragma omp parallel for schedule(static) if (hi - lo > 100000)
+#pragma omp parallel for schedule(static) if (big)
 	for (int32_t a = lo; a < hi; a++) {
 		int64_t bx = (int64_t) ((pos[2 * (size_t) a + 0] - x0) / wx * (double) nbx);
 		int64_t by = (int64_t) ((pos[2 * (size_t) a + 1] - y0) / wy * (double) nby);
@@ -189,7 +205,6 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 		by = by >= nby ? nby - 1 : (by < 0 ? 0 : by);
 
 		bin[a] = (int32_t) (by * nbx + bx);
-		parent[a] = a;
 	}
 
 #define FIND(v, out)                               \
@@ -205,8 +220,9 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 	/* connected pieces of every bin: nodes of one bin joined through couplings of the operator.  The smaller
 	 * root wins, so the result does not depend on traversal order; on a solid mesh a bin is one piece, on
 	 * truss-like geometry a bin can cut through members that do not touch and each becomes its own aggregate.
-	 * Unions never leave a bin, so the bins are independent: nodes are bucketed by bin (counting sort, ascending
-	 * inside a bin) and the buckets shared out over the host threads. */
+	 * Unions never leave a bin, so the bins are independent: nodes are bucketed by bin (counted and dropped with
+	 * integer atomics, then every bucket put in ascending order by the thread that owns it - the same buckets a
+	 * serial counting sort fills) and the buckets shared out over the host threads. */
 
 	{
 		int64_t const n_bins = nbx * nby;
@@ -222,20 +238,33 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 			return 0;
 		}
 
+#pragma omp parallel for schedule(static) if (big)
 		for (int32_t a = lo; a < hi; a++) {
-			start[bin[a] + 2]++;
+			__atomic_fetch_add(&start[bin[a] + 2], 1, __ATOMIC_RELAXED);
 		}
 
 		for (int64_t b = 0; b < n_bins; b++) {
 			start[b + 2] += start[b + 1];
 		}
 
+#pragma omp parallel for schedule(static) if (big)
 		for (int32_t a = lo; a < hi; a++) {
-			order[start[bin[a] + 1]++] = a;
+			order[__atomic_fetch_add(&start[bin[a] + 1], 1, __ATOMIC_RELAXED)] = a;
 		}
 
-#pragma omp parallel for schedule(dynamic, 64) if (hi - lo > 100000)
+#pragma omp parallel for schedule(dynamic, 64) if (big)
 		for (int64_t b = 0; b < n_bins; b++) {
+			for (int64_t i = start[b] + 1; i < start[b + 1]; i++) { /* ascending nodes inside the bin */
+				int32_t const cur = order[i];
+				int64_t j = i;
+
+				for (; j > start[b] && order[j - 1] > cur; j--) {
+					order[j] = order[j - 1];
+				}
+
+				order[j] = cur;
+			}
+
 			for (int64_t i = start[b]; i < start[b + 1]; i++) {
 				int32_t const a = order[i];
 
@@ -267,20 +296,53 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 	}
 
 	/* pieces below min_nodes join a piece they are coupled to (a few passes: a chain of tiny pieces needs more
-	 * than one) */
+	 * than one).  The joining itself goes node by node in ascending order - its outcome depends on that order - but
+	 * only nodes of pieces that are too small when a pass starts can take part (pieces only grow), and on a solid mesh
+	 * there are none: they are found in parallel first */
+
+	int32_t* small = NULL;
 
 	for (int pass = 0; pass < 4 && min_nodes > 1; pass++) {
 		memset(size, 0, ((size_t) n + 1) * sizeof *size);
 
+#pragma omp parallel for schedule(static) if (big)
 		for (int32_t a = lo; a < hi; a++) {
-			int32_t r;
-			FIND(a, r);
-			size[r]++;
+			__atomic_fetch_add(&size[find_root(parent, a)], 1, __ATOMIC_RELAXED);
+		}
+
+		int64_t n_small = 0;
+
+#pragma omp parallel for schedule(static) reduction(+ : n_small) if (big)
+		for (int32_t a = lo; a < hi; a++) {
+			n_small += size[find_root(parent, a)] < min_nodes;
+		}
+
+		if (n_small == 0) {
+			break;
+		}
+
+		free(small);
+		small = malloc(((size_t) n_small + 1) * sizeof *small);
+
+		if (small == NULL) {
+			free(bin);
+			free(parent);
+			free(size);
+			return 0;
+		}
+
+		n_small = 0;
+
+		for (int32_t a = lo; a < hi; a++) {
+			if (size[find_root(parent, a)] < min_nodes) {
+				small[n_small++] = a;
+			}
 		}
 
 		bool changed = false;
 
-		for (int32_t a = lo; a < hi; a++) {
+		for (int64_t i = 0; i < n_small; i++) {
+			int32_t const a = small[i];
 			int32_t ra;
 			FIND(a, ra);
 
@@ -316,31 +378,71 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 		}
 	}
 
+	free(small);
+
 	memset(size, 0, ((size_t) n + 1) * sizeof *size);
 
+#pragma omp parallel for schedule(static) if (big)
 	for (int32_t a = lo; a < hi; a++) {
-		int32_t r;
-		FIND(a, r);
-		size[r]++;
-	}
-
-	/* compact: ids in order of each piece's smallest node (its root); pieces still too small are left out */
-
-	int32_t n_agg = 0;
-
-	for (int32_t a = lo; a < hi; a++) {
-		if (parent[a] == a) {
-			bin[a] = size[a] >= min_nodes ? n_agg++ : -1; /* bin[] is free now: reuse as root -> id */
-		}
-	}
-
-	for (int32_t a = lo; a < hi; a++) {
-		int32_t r;
-		FIND(a, r);
-		agg[a] = bin[r];
+		__atomic_fetch_add(&size[find_root(parent, a)], 1, __ATOMIC_RELAXED);
 	}
 
 #undef FIND
+
+	/* compact: ids in order of each piece's smallest node (its root); pieces still too small are left out.
+	 * bin[] is free now: reused as root -> id (a chunked prefix sum over the roots that are kept) */
+
+	int32_t n_agg = 0;
+
+	{
+		int64_t const chunk = 1 << 16;
+		int64_t const n_chunks = ((int64_t) (hi - lo) + chunk - 1) / chunk;
+		int32_t* const first_id = calloc((size_t) n_chunks + 1, sizeof *first_id);
+
+		if (first_id == NULL) {
+			free(bin);
+			free(parent);
+			free(size);
+			return 0;
+		}
+
+#pragma omp parallel for schedule(static) if (big)
+		for (int64_t c = 0; c < n_chunks; c++) {
+			int32_t const end = lo + (c + 1) * chunk < hi ? (int32_t) (lo + (c + 1) * chunk) : hi;
+			int32_t kept = 0;
+
+			for (int32_t a = (int32_t) (lo + c * chunk); a < end; a++) {
+				kept += parent[a] == a && size[a] >= min_nodes;
+			}
+
+			first_id[c + 1] = kept;
+		}
+
+		for (int64_t c = 0; c < n_chunks; c++) {
+			first_id[c + 1] += first_id[c];
+		}
+
+		n_agg = first_id[n_chunks];
+
+#pragma omp parallel for schedule(static) if (big)
+		for (int64_t c = 0; c < n_chunks; c++) {
+			int32_t const end = lo + (c + 1) * chunk < hi ? (int32_t) (lo + (c + 1) * chunk) : hi;
+			int32_t id = first_id[c];
+
+			for (int32_t a = (int32_t) (lo + c * chunk); a < end; a++) {
+				if (parent[a] == a) {
+					bin[a] = size[a] >= min_nodes ? id++ : -1;
+				}
+			}
+		}
+
+		free(first_id);
+	}
+
+#pragma omp parallel for schedule(static) if (big)
+	for (int32_t a = lo; a < hi; a++) {
+		agg[a] = bin[find_root(parent, a)];
+	}
 
 	free(bin);
 	free(parent);
@@ -356,6 +458,7 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 static int build_transfer(bfmi_hier_level_t* L) {
 	int32_t const n = L->n;
 	int32_t const nc = L->n_coarse;
+	bool const big = n > 100000;
 
 	L->p_ptr = malloc(((size_t) n + 1) * sizeof *L->p_ptr);
 	L->r_ptr = calloc((size_t) nc + 2, sizeof *L->r_ptr);
@@ -364,12 +467,46 @@ static int build_transfer(bfmi_hier_level_t* L) {
 		return -1;
 	}
 
-	int32_t n_p = 0;
+	/* p_ptr: prefix sum of "has an aggregate", by chunks */
 
-	for (int32_t a = 0; a < n; a++) {
-		L->p_ptr[a] = n_p;
-		n_p += L->agg[a] >= 0;
+	int64_t const chunk = 1 << 16;
+	int64_t const n_chunks = ((int64_t) n + chunk - 1) / chunk;
+	int32_t* const first = calloc((size_t) n_chunks + 1, sizeof *first);
+
+	if (first == NULL) {
+		return -1;
 	}
+
+#pragma omp parallel for schedule(static) if (big)
+	for (int64_t c = 0; c < n_chunks; c++) {
+		int32_t const end = (c + 1) * chunk < n ? (int32_t) ((c + 1) * chunk) : n;
+		int32_t cnt = 0;
+
+		for (int32_t a = (int32_t) (c * chunk); a < end; a++) {
+			cnt += L->agg[a] >= 0;
+		}
+
+		first[c + 1] = cnt;
+	}
+
+	for (int64_t c = 0; c < n_chunks; c++) {
+		first[c + 1] += first[c];
+	}
+
+	int32_t const n_p = first[n_chunks];
+
+#pragma omp parallel for schedule(static) if (big)
+	for (int64_t c = 0; c < n_chunks; c++) {
+		int32_t const end = (c + 1) * chunk < n ? (int32_t) ((c + 1) * chunk) : n;
+		int32_t at = first[c];
+
+		for (int32_t a = (int32_t) (c * chunk); a < end; a++) {
+			L->p_ptr[a] = at;
+			at += L->agg[a] >= 0;
+		}
+	}
+
+	free(first);
 
 	L->p_ptr[n] = n_p;
 	L->n_p = n_p;
@@ -382,12 +519,13 @@ static int build_transfer(bfmi_hier_level_t* L) {
 		return -1;
 	}
 
+#pragma omp parallel for schedule(static) if (big)
 	for (int32_t a = 0; a < n; a++) {
 		if (L->agg[a] >= 0) {
 			L->p_col[L->p_ptr[a]] = L->agg[a];
 
 			if (a >= L->row_lo && a < L->row_hi) {
-				L->r_ptr[L->agg[a] + 2]++;
+				__atomic_fetch_add(&L->r_ptr[L->agg[a] + 2], 1, __ATOMIC_RELAXED);
 			}
 		}
 	}
@@ -396,12 +534,33 @@ static int build_transfer(bfmi_hier_level_t* L) {
 		L->r_ptr[g + 2] += L->r_ptr[g + 1];
 	}
 
-	for (int32_t a = L->row_lo; a < L->row_hi; a++) { /* ascending nodes inside every coarse node's list */
-		for (int32_t e = L->p_ptr[a]; e < L->p_ptr[a + 1]; e++) {
-			int32_t const at = L->r_ptr[L->p_col[e] + 1]++;
+	/* every coarse node's list of owned fine nodes, ascending: dropped in with an atomic cursor, then each list put
+	 * in order by one thread (a node has one entry, p_ptr[a], so the entries follow the nodes) */
 
-			L->r_ent[at] = e;
-			L->r_node[at] = a;
+#pragma omp parallel for schedule(static) if (big)
+	for (int32_t a = L->row_lo; a < L->row_hi; a++) {
+		if (L->agg[a] >= 0) {
+			L->r_node[__atomic_fetch_add(&L->r_ptr[L->agg[a] + 1], 1, __ATOMIC_RELAXED)] = a;
+		}
+	}
+
+#pragma omp parallel for schedule(dynamic, 1024) if (big)
+	for (int32_t g = 0; g < nc; g++) {
+		int32_t const beg = L->r_ptr[g], end = L->r_ptr[g + 1];
+
+		for (int32_t i = beg + 1; i < end; i++) {
+			int32_t const cur = L->r_node[i];
+			int32_t j = i;
+
+			for (; j > beg && L->r_node[j - 1] > cur; j--) {
+				L->r_node[j] = L->r_node[j - 1];
+			}
+
+			L->r_node[j] = cur;
+		}
+
+		for (int32_t i = beg; i < end; i++) {
+			L->r_ent[i] = L->p_ptr[L->r_node[i]];
 		}
 	}
 
@@ -716,13 +875,34 @@ static int centroids(bfmi_hier_level_t* L, int32_t n_agg, int32_t id_shift, doub
 		return -1;
 	}
 
-	for (int32_t a = L->row_lo; a < L->row_hi; a++) { /* fixed order: identical wherever it is computed */
-		int32_t const g = L->agg[a] - id_shift;
+	if (L->r_ptr != NULL && id_shift == 0) {
+		/* the transfer lists exist (build_transfer): every aggregate's owned nodes in ascending order - the order the
+		 * loop below adds them in, so the sums are the same to the last bit, one aggregate per thread */
 
-		if (L->agg[a] >= 0) {
-			cen[2 * (size_t) g + 0] += L->pos[2 * (size_t) a + 0];
-			cen[2 * (size_t) g + 1] += L->pos[2 * (size_t) a + 1];
-			count[g]++;
+#pragma omp parallel for schedule(static) if (n_agg > 20000)
+		for (int32_t g = 0; g < n_agg; g++) {
+			double sx = 0, sy = 0;
+
+			for (int32_t at = L->r_ptr[g]; at < L->r_ptr[g + 1]; at++) {
+				sx += L->pos[2 * (size_t) L->r_node[at] + 0];
+				sy += L->pos[2 * (size_t) L->r_node[at] + 1];
+			}
+
+			cen[2 * (size_t) g + 0] = sx;
+			cen[2 * (size_t) g + 1] = sy;
+			count[g] = L->r_ptr[g + 1] - L->r_ptr[g];
+		}
+	}
+
+	else {
+		for (int32_t a = L->row_lo; a < L->row_hi; a++) { /* fixed order: identical wherever it is computed */
+			int32_t const g = L->agg[a] - id_shift;
+
+			if (L->agg[a] >= 0) {
+				cen[2 * (size_t) g + 0] += L->pos[2 * (size_t) a + 0];
+				cen[2 * (size_t) g + 1] += L->pos[2 * (size_t) a + 1];
+				count[g]++;
+			}
 		}
 	}
 
@@ -733,6 +913,7 @@ static int centroids(bfmi_hier_level_t* L, int32_t n_agg, int32_t id_shift, doub
 
 	free(count);
 
+#pragma omp parallel for schedule(static) if (L->row_hi - L->row_lo > 100000)
 	for (int32_t a = L->row_lo; a < L->row_hi; a++) {
 		int32_t const g = L->agg[a] - id_shift;
 
@@ -891,8 +1072,8 @@ bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, bfmi
 
 			int rv = N->pos != NULL && rows != NULL && lens != NULL ? 0 : -1;
 
-			rv = rv < 0 ? rv : centroids(L, n_agg, 0, N->pos);
 			rv = rv < 0 ? rv : build_transfer(L);
+			rv = rv < 0 ? rv : centroids(L, n_agg, 0, N->pos); /* after the transfer lists: summed aggregate by aggregate */
 			rv = rv < 0 ? rv : coarse_rows(L, 0, n_agg, rows, lens);
 			rv = rv < 0 ? rv : layout_level(N, n_agg, rows, lens);
 

@@ -17,8 +17,10 @@
  */
 #include "internal.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #define SLICE 32
 
@@ -214,6 +216,12 @@ int64_t bfmi_plan_find(bfmi_plan_t const* plan, int32_t a, int32_t b) {
 
 /* ---- plan from a mesh ------------------------------------------------------------------------- */
 
+static double plan_now_ms(void) {
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 /* the same plan built by symbolic.cu.  The contributor map (ctr_ptr, ctr) stays on the device - only the assembly
  * kernel reads it; bfmx_mesh_pattern_copy fetches it on demand */
 static bfmi_plan_t* build_on_device(bfm_mesh_t const* mesh, uint64_t hash) {
@@ -239,6 +247,11 @@ static bfmi_plan_t* build_on_device(bfm_mesh_t const* mesh, uint64_t hash) {
 	plan->elems_hash = hash;
 	plan->nb = (int32_t) nn;
 
+	bool const verbose = getenv("BFM_JOB_VERBOSE") != NULL;
+	double t_mark = plan_now_ms();
+
+#define MARK(what) do { if (verbose) { double const now_ = plan_now_ms(); fprintf(stderr, "[plan] %-28s %8.2f ms\n", (what), now_ - t_mark); t_mark = now_; } } while (0)
+
 	int32_t* const elems32 = malloc((ne * kind + 1) * sizeof *elems32);
 	int32_t* d_elems = NULL;
 	bool bad = elems32 == NULL;
@@ -260,11 +273,15 @@ static bfmi_plan_t* build_on_device(bfm_mesh_t const* mesh, uint64_t hash) {
 
 	free(elems32);
 
+	MARK("connectivity to the device");
+
 	if (bfmg_plan_build(plan->nb, (int64_t) ne, (int32_t) kind, d_elems, &plan->dev, &plan->n_ctr) < 0) {
 		bfmg_free(d_elems);
 		free(plan);
 		return NULL;
 	}
+
+	MARK("kernels (symbolic.cu)");
 
 	plan->dev.elems = d_elems;
 	plan->on_device = true; /* from here on plan_free releases the device arrays */
@@ -287,6 +304,9 @@ static bfmi_plan_t* build_on_device(bfm_mesh_t const* mesh, uint64_t hash) {
 		plan_free(plan);
 		return NULL;
 	}
+
+	MARK("pattern to the host");
+#undef MARK
 
 	int64_t blocks = 0;
 

@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-echo "== symbolic + renumbering tests"
-timeout 900 python -m pytest tests/test_gpu_symbolic.py -x -q 2>&1 | tail -15
-echo "== irregular probe 6000x1500"
-timeout 600 python tools/irregular_probe.py 6000x1500 2>> gpurun_out/err.log | tee gpurun_out/r2_irregular_probe_18m_renumbered.jsonl
-tail -3 gpurun_out/err.log
+export BFM_QUIET=1
+BFM_JOB_VERBOSE=1 python tools/profile_symbolic.py 10000x2500 2>&1 | grep -v "^\[job\]"
+echo "== cold start + bench"
+BFM_JOB_VERBOSE=1 BFM_MG_VERBOSE=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity-check 2> gpurun_out/r2_cold_verbose.log | python tools/show_bench.py /dev/stdin
+grep "\[plan\]\|\[job\]\|\[hier\] level 0" gpurun_out/r2_cold_verbose.log | sed -n 1,20p
