@@ -26,6 +26,7 @@ int bfmg_alloc(void** d_ptr, size_t bytes);
 void bfmg_free(void* d_ptr);
 int bfmg_upload(void* d_dst, void const* src, size_t bytes);
 int bfmg_download(void* dst, void const* d_src, size_t bytes); /* synchronises */
+int bfmg_upload_narrow(int32_t* d_dst, size_t const* src, size_t count, size_t limit, int* out_of_range); /* size_t -> int32 on the way; flags values >= limit */
 int bfmg_copy(void* d_dst, void const* d_src, size_t bytes);
 int bfmg_host_pin(void const* ptr, size_t bytes);  /* page-lock a long-lived caller buffer in place (idempotent; -1: not pinned, copies still work) */
 void bfmg_host_unpin(void const* ptr);             /* before the buffer is freed; harmless for buffers never pinned */

@@ -133,31 +133,26 @@ static int edges_on_device(bfm_mesh_t* mesh) {
 		return 0;
 	}
 
-	int32_t* const elems32 = malloc(n_half * sizeof *elems32);
-	bool bad = elems32 == NULL;
-
-	if (!bad) {
-#pragma omp parallel for schedule(static) reduction(|| : bad) if (n_half > ((size_t) 1 << 18))
-		for (size_t i = 0; i < n_half; i++) {
-			bad = bad || mesh->elems[i] >= nn;
-			elems32[i] = (int32_t) mesh->elems[i];
-		}
-	}
-
-	if (bad) { /* connectivity outside the node table: the host sort does not mind, the per-node segments would */
-		free(elems32);
-		return 0;
-	}
-
 	int32_t* d_elems = NULL;
 	int64_t* d_edges = NULL;
 	int64_t n_out = 0;
+	int bad = 0;
 	int rv = -1;
 
-	if (
-		bfmg_alloc((void**) &d_elems, n_half * sizeof *d_elems) == 0 && bfmg_upload(d_elems, elems32, n_half * sizeof *d_elems) == 0 &&
-		bfmg_edges_build((int32_t) nn, (int64_t) mesh->n_elems, (int32_t) sides, d_elems, &d_edges, &n_out) == 0
-	) {
+	/* connectivity narrowed to 32 bits on its way to the device; node numbers outside the table: the host sort does
+	 * not mind them, the per-node segments would - the caller takes the host path */
+	if (bfmg_alloc((void**) &d_elems, n_half * sizeof *d_elems) < 0 || bfmg_upload_narrow(d_elems, mesh->elems, n_half, nn, &bad) < 0) {
+		BFMI_FAIL(state, "edge derivation on the device failed: %s", bfmg_last_error());
+		bfmg_free(d_elems);
+		return -1;
+	}
+
+	if (bad) {
+		bfmg_free(d_elems);
+		return 0;
+	}
+
+	if (bfmg_edges_build((int32_t) nn, (int64_t) mesh->n_elems, (int32_t) sides, d_elems, &d_edges, &n_out) == 0) {
 		_Static_assert(sizeof(bfm_edge_t) == 4 * sizeof(int64_t), "an edge record is nodes[2], elems[2], 8 bytes each");
 
 		mesh->edges = n_out > 0 ? state->alloc((size_t) n_out * sizeof *mesh->edges) : NULL;
@@ -179,7 +174,6 @@ static int edges_on_device(bfm_mesh_t* mesh) {
 
 	bfmg_free(d_elems);
 	bfmg_free(d_edges);
-	free(elems32);
 
 	return rv;
 }

@@ -252,26 +252,15 @@ static bfmi_plan_t* build_on_device(bfm_mesh_t const* mesh, uint64_t hash) {
 
 #define MARK(what) do { if (verbose) { double const now_ = plan_now_ms(); fprintf(stderr, "[plan] %-28s %8.2f ms\n", (what), now_ - t_mark); t_mark = now_; } } while (0)
 
-	int32_t* const elems32 = malloc((ne * kind + 1) * sizeof *elems32);
 	int32_t* d_elems = NULL;
-	bool bad = elems32 == NULL;
+	int bad = 0;
 
-	if (!bad) {
-#pragma omp parallel for schedule(static) reduction(|| : bad) if (ne * kind > ((size_t) 1 << 18))
-		for (size_t i = 0; i < ne * kind; i++) {
-			bad = bad || mesh->elems[i] >= nn; /* connectivity points outside the node table */
-			elems32[i] = (int32_t) mesh->elems[i];
-		}
-	}
-
-	if (bad || bfmg_alloc((void**) &d_elems, (ne * kind + 1) * sizeof *d_elems) < 0 || bfmg_upload(d_elems, elems32, ne * kind * sizeof *d_elems) < 0) {
-		free(elems32);
+	/* connectivity: narrowed to 32 bits on its way into the staging buffers; a node number outside the table fails */
+	if (bfmg_alloc((void**) &d_elems, (ne * kind + 1) * sizeof *d_elems) < 0 || bfmg_upload_narrow(d_elems, mesh->elems, ne * kind, nn, &bad) < 0 || bad) {
 		bfmg_free(d_elems);
 		free(plan);
 		return NULL;
 	}
-
-	free(elems32);
 
 	MARK("connectivity to the device");
 
