@@ -204,7 +204,8 @@ def workload_config(nx: int, ny: int, gpus: int, stats: dict | None = None) -> d
 	solver = "FP64 PCG to a relative residual of 1e-12, Jacobi scaling"
 
 	if stats and stats.get("mg_levels", 0):
-		solver += f" + aggregation multigrid W-cycle preconditioner ({stats['mg_levels']} levels, rigid-body modes per aggregate, damped-Jacobi smoothing fused into the SpMVs, dense last level of dimension {stats.get('coarse_dim', 0)})"
+		smoothed = os.environ.get("BFM_MG_SMOOTH", "1") != "0"
+		solver += f" + {'smoothed-aggregation multigrid V-cycle' if smoothed else 'aggregation multigrid W-cycle'} preconditioner ({stats['mg_levels']} levels, rigid-body modes per aggregate, damped-Jacobi smoothing fused into the SpMVs, dense last level of dimension {stats.get('coarse_dim', 0)})"
 	elif stats and stats.get("coarse_dim", 0):
 		solver += f" + one additive coarse level of rigid-body modes ({stats['coarse_dim'] // 3} aggregates, dense inverse)"
 
@@ -223,47 +224,51 @@ def workload_config(nx: int, ny: int, gpus: int, stats: dict | None = None) -> d
 # ---- algorithmic bytes of one multigrid-preconditioned PCG iteration (mg.cuh header) ----
 
 
-def mg_gammas(n_levels: int) -> list[int]:
-	"""visits of the next level per cycle on the sparse levels 1 .. n_levels - 2 (mg.cuh: BFM_MG_GAMMA, default 2)"""
+def mg_gammas(n_levels: int, smoothed: bool = True) -> list[int]:
+	"""visits of the next level per cycle on the sparse levels 1 .. n_levels - 2 (mg.cuh: BFM_MG_GAMMA; default 1 -
+	a V-cycle - with smoothed aggregation, 2 with the tentative prolongator)"""
 
 	env = os.environ.get("BFM_MG_GAMMA", "")
+	default = 1 if smoothed else 2
 	out = []
 
 	for l in range(1, n_levels - 1):
-		g = 2
+		g = default
 
 		if env:
 			parts = env.split(",")
-			g = int(parts[min(l - 1, len(parts) - 1)] or 2)
+			g = int(parts[min(l - 1, len(parts) - 1)] or default)
 
-		out.append(g if 1 <= g <= 4 else 2)
+		out.append(g if 1 <= g <= 4 else default)
 
 	return out
 
 
-def mg_iteration_bytes(levels: list[dict], coarse_dim: int) -> dict:
-	"""levels: [{n, n_slots}] from bfmx_hier_info.  Stored-format bytes every kernel of one iteration must move:
-	level 0 (2x2 blocks, 36 B per slot): k_spmv<kDot> 36 S + 32 n, k_update_xr 96 n, k_spmv_mg<kPre> 36 S + 32 n,
-	k_mg_restrict 48 n (t 16 + P 24 in FP32 + 2 indices), k_mg_prolong 64 n, k_spmv_mg<kPost> 36 S + 48 n, k_update_p
-	48 n; level l >= 1 (3x3 blocks, 76 B per slot, gamma visits of the next level): (gamma + 1) fused SpMVs of
-	76 S + 72 n, gamma restrictions of 104 n and prolongations of 128 n (+ 24 n when adding); the dense last level
-	8 nc^2 per visit."""
+def mg_iteration_bytes(levels: list[dict], coarse_dim: int, smoothed: bool = True) -> dict:
+	"""levels: [{n, n_slots, n_entries}] from bfmx_hier_info (E = entries of the level's prolongator: n with the
+	tentative one, ~2.7 n with smoothed aggregation).  Stored-format bytes every kernel of one iteration must move:
+	level 0 (2x2 blocks; S slots): k_spmv<kDot> 36 S + 32 n (FP64 operator), k_update_xr 96 n, k_spmv_mg<kPre>
+	20 S + 32 n and k_spmv_mg<kPost> 20 S + 48 n (FP32 copy of the operator), k_mg_restrict 16 n + 32 E (t, P in FP32
+	24 B + two indices), k_mg_prolong 32 n + 28 E (r, z, P 24 B + column), k_update_p 48 n;
+	level l >= 1 (3x3 blocks, FP32 copy: 40 B per slot; gamma visits of the next level): (gamma + 1) fused SpMVs of
+	40 S + 72 n, gamma restrictions of 24 n + 80 E and prolongations of 48 n + 76 E (+ 24 n when adding) and the next
+	level's vector (24 B per node) twice; the dense last level 8 nc^2 per visit."""
 
-	n0, s0 = levels[0]["n"], levels[0]["n_slots"]
-	per_level = [3 * (36 * s0) + (32 + 96 + 32 + 48 + 64 + 48 + 48) * n0]
-	gammas = mg_gammas(len(levels))
+	n0, s0, e0 = levels[0]["n"], levels[0]["n_slots"], levels[0]["n_entries"]
+	n1 = levels[1]["n"] if len(levels) > 1 else 0
+	per_level = [(36 + 20 + 20) * s0 + (32 + 96 + 32 + 48 + 16 + 32 + 48) * n0 + (32 + 28) * e0 + 2 * 24 * n1]
+	gammas = mg_gammas(len(levels), smoothed)
 	visits = 1
 
 	for l in range(1, len(levels) - 1):
-		n, sl, g = levels[l]["n"], levels[l]["n_slots"], gammas[l - 1]
-		per_level.append(visits * ((g + 1) * (76 * sl + 72 * n) + g * (104 + 128) * n + (g - 1) * 24 * n + g * 24 * levels[l + 1]["n"]))
+		n, sl, e, g = levels[l]["n"], levels[l]["n_slots"], levels[l]["n_entries"], gammas[l - 1]
+		per_level.append(visits * ((g + 1) * (40 * sl + 72 * n) + g * ((24 + 48) * n + (80 + 76) * e) + (g - 1) * 24 * n + g * 2 * 24 * levels[l + 1]["n"]))
 		visits *= g
 
 	nc = (coarse_dim + 31) // 32 * 32
 	per_level.append(visits * 8 * nc * nc)
 
-	return {"total": sum(per_level), "per_level": per_level, "gammas": gammas, "dense_visits": visits}
-
+	return {"total": sum(per_level), "per_level": per_level, "gammas": gammas, "dense_visits": visits, "smoothed_aggregation": smoothed}
 
 
 # ---- parity where the driver can see it ---------------------------------------------------------------------
@@ -548,8 +553,8 @@ def main():
 
 		info = ext.HierInfo()
 		assert not lib.bfmx_hier_info(case.mesh.c_mesh, ctypes.byref(info))
-		levels = [{"n": info.n_nodes[l], "n_slots": info.n_slots[l]} for l in range(info.n_levels)]
-		mg_model = mg_iteration_bytes(levels, s["coarse_dim"])
+		levels = [{"n": info.n_nodes[l], "n_slots": info.n_slots[l], "n_entries": info.n_entries[l]} for l in range(info.n_levels)]
+		mg_model = mg_iteration_bytes(levels, s["coarse_dim"], bool(info.smoothed))
 		mg_model["levels"] = levels
 		iter_bytes = mg_model["total"]
 

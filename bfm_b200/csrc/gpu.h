@@ -194,6 +194,8 @@ typedef struct {
 	/* towards the next level (unused on the last) */
 	int32_t n_coarse;
 	int32_t n_p;
+	int32_t smoothed;    /* smoothed aggregation: rows that are all this rank's get (I - w A^) P~ (k_mg_smooth) */
+	int32_t pad_;
 	int32_t* agg;        /* [n] aggregate, -1: none */
 	float* geom;         /* [n] float2 */
 	int32_t* p_ptr;      /* prolongator entries by fine node */

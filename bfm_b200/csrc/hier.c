@@ -455,6 +455,70 @@ static int32_t aggregate_level(bfmi_hier_level_t const* L, int64_t target, int32
 
 /* CSR of the prolongator (one entry per node that has an aggregate - ghosts included, the Galerkin product needs
  * their rows) and its transpose over the nodes this rank owns (restriction sums over owned nodes only) */
+/* Smoothed aggregation (L->smoothed): the prolongator is (I - w A^) P~ instead of the tentative P~, so the row of a node
+ * reaches the aggregates of all its neighbours.  Only nodes whose whole row is this rank's - owned, no ghost among
+ * the columns - are smoothed: their entries name this rank's aggregates only, so restriction, prolongation and the
+ * Galerkin rows of this rank's aggregates stay local, exactly as with the tentative prolongator (a rank sees the plain,
+ * one-entry rows of its ghosts, which is what their owner gives them too: interface nodes are never smoothed).  On one
+ * GPU and on replicated levels every node is smoothed.  mg.cuh (k_mg_smooth) applies the same rule. */
+static inline bool smoothable(bfmi_hier_level_t const* L, int32_t a) {
+	if (!L->smoothed || a < L->row_lo || a >= L->row_hi || L->agg[a] < 0) {
+		return false;
+	}
+
+	for (int32_t t = 0; t < L->row_len[a]; t++) {
+		int32_t const b = L->scol[slot_of(L->slice_off, a, t)];
+
+		if (b < L->row_lo || b >= L->row_hi) {
+			return false;
+		}
+	}
+
+	return true;
+}
+
+/* the coarse nodes of the entries of node a, ascending, into out (room for row_len + 1); returns their number */
+static inline int32_t entries_of(bfmi_hier_level_t const* L, int32_t a, int32_t* out) {
+	if (L->agg[a] < 0) {
+		return 0;
+	}
+
+	int32_t cnt = 0;
+
+	out[cnt++] = L->agg[a];
+
+	if (smoothable(L, a)) {
+		for (int32_t t = 0; t < L->row_len[a]; t++) {
+			int32_t const g = L->agg[L->scol[slot_of(L->slice_off, a, t)]];
+			int32_t i = 0;
+
+			if (g < 0) {
+				continue;
+			}
+
+			for (; i < cnt && out[i] != g; i++) {
+			}
+
+			if (i == cnt) {
+				out[cnt++] = g;
+			}
+		}
+
+		for (int32_t i = 1; i < cnt; i++) {
+			int32_t const cur = out[i];
+			int32_t j = i;
+
+			for (; j > 0 && out[j - 1] > cur; j--) {
+				out[j] = out[j - 1];
+			}
+
+			out[j] = cur;
+		}
+	}
+
+	return cnt;
+}
+
 static int build_transfer(bfmi_hier_level_t* L) {
 	int32_t const n = L->n;
 	int32_t const nc = L->n_coarse;
@@ -467,23 +531,46 @@ static int build_transfer(bfmi_hier_level_t* L) {
 		return -1;
 	}
 
-	/* p_ptr: prefix sum of "has an aggregate", by chunks */
+	int32_t longest = 1;
+
+	if (L->smoothed) {
+		for (int32_t a = L->row_lo; a < L->row_hi; a++) {
+			longest = L->row_len[a] > longest ? L->row_len[a] : longest;
+		}
+	}
+
+	/* entries per node (p_ptr[a + 1] for now), then p_ptr: their prefix sum, by chunks */
+
+#pragma omp parallel if (big)
+	{
+		int32_t* const scratch = malloc(((size_t) longest + 2) * sizeof *scratch);
+
+#pragma omp for schedule(static)
+		for (int32_t a = 0; a < n; a++) {
+			L->p_ptr[a + 1] = scratch != NULL ? entries_of(L, a, scratch) : -1;
+		}
+
+		free(scratch);
+	}
 
 	int64_t const chunk = 1 << 16;
 	int64_t const n_chunks = ((int64_t) n + chunk - 1) / chunk;
-	int32_t* const first = calloc((size_t) n_chunks + 1, sizeof *first);
+	int64_t* const first = calloc((size_t) n_chunks + 1, sizeof *first);
 
 	if (first == NULL) {
 		return -1;
 	}
 
-#pragma omp parallel for schedule(static) if (big)
+	bool failed = false;
+
+#pragma omp parallel for schedule(static) reduction(|| : failed) if (big)
 	for (int64_t c = 0; c < n_chunks; c++) {
 		int32_t const end = (c + 1) * chunk < n ? (int32_t) ((c + 1) * chunk) : n;
-		int32_t cnt = 0;
+		int64_t cnt = 0;
 
 		for (int32_t a = (int32_t) (c * chunk); a < end; a++) {
-			cnt += L->agg[a] >= 0;
+			failed = failed || L->p_ptr[a + 1] < 0;
+			cnt += L->p_ptr[a + 1];
 		}
 
 		first[c + 1] = cnt;
@@ -493,22 +580,28 @@ static int build_transfer(bfmi_hier_level_t* L) {
 		first[c + 1] += first[c];
 	}
 
-	int32_t const n_p = first[n_chunks];
+	if (failed || first[n_chunks] > INT32_MAX / 9) { /* nine value planes are indexed with 32-bit entries */
+		free(first);
+		return -1;
+	}
+
+	int32_t const n_p = (int32_t) first[n_chunks];
+
+	L->p_ptr[0] = 0;
 
 #pragma omp parallel for schedule(static) if (big)
 	for (int64_t c = 0; c < n_chunks; c++) {
 		int32_t const end = (c + 1) * chunk < n ? (int32_t) ((c + 1) * chunk) : n;
-		int32_t at = first[c];
+		int32_t at = (int32_t) first[c];
 
 		for (int32_t a = (int32_t) (c * chunk); a < end; a++) {
-			L->p_ptr[a] = at;
-			at += L->agg[a] >= 0;
+			at += L->p_ptr[a + 1];
+			L->p_ptr[a + 1] = at; /* chunk c only writes p_ptr[c * chunk + 1 .. end]: no overlap with its neighbours */
 		}
 	}
 
 	free(first);
 
-	L->p_ptr[n] = n_p;
 	L->n_p = n_p;
 
 	L->p_col = malloc(((size_t) n_p + 1) * sizeof *L->p_col);
@@ -519,28 +612,45 @@ static int build_transfer(bfmi_hier_level_t* L) {
 		return -1;
 	}
 
-#pragma omp parallel for schedule(static) if (big)
-	for (int32_t a = 0; a < n; a++) {
-		if (L->agg[a] >= 0) {
-			L->p_col[L->p_ptr[a]] = L->agg[a];
+#pragma omp parallel if (big)
+	{
+		int32_t* const scratch = malloc(((size_t) longest + 2) * sizeof *scratch);
+
+#pragma omp for schedule(static)
+		for (int32_t a = 0; a < n; a++) {
+			int32_t const cnt = L->p_ptr[a + 1] - L->p_ptr[a];
+
+			if (cnt == 0 || scratch == NULL) {
+				continue;
+			}
+
+			entries_of(L, a, scratch);
+			memcpy(&L->p_col[L->p_ptr[a]], scratch, (size_t) cnt * sizeof *scratch);
 
 			if (a >= L->row_lo && a < L->row_hi) {
-				__atomic_fetch_add(&L->r_ptr[L->agg[a] + 2], 1, __ATOMIC_RELAXED);
+				for (int32_t i = 0; i < cnt; i++) {
+					__atomic_fetch_add(&L->r_ptr[scratch[i] + 2], 1, __ATOMIC_RELAXED);
+				}
 			}
 		}
+
+		free(scratch);
 	}
 
 	for (int32_t g = 0; g < nc; g++) {
 		L->r_ptr[g + 2] += L->r_ptr[g + 1];
 	}
 
-	/* every coarse node's list of owned fine nodes, ascending: dropped in with an atomic cursor, then each list put
-	 * in order by one thread (a node has one entry, p_ptr[a], so the entries follow the nodes) */
+	/* every coarse node's list of (owned fine node, entry), ascending by node: dropped in with an atomic cursor, then
+	 * each list put in order by one thread (a node has at most one entry per coarse node) */
 
 #pragma omp parallel for schedule(static) if (big)
 	for (int32_t a = L->row_lo; a < L->row_hi; a++) {
-		if (L->agg[a] >= 0) {
-			L->r_node[__atomic_fetch_add(&L->r_ptr[L->agg[a] + 1], 1, __ATOMIC_RELAXED)] = a;
+		for (int32_t e = L->p_ptr[a]; e < L->p_ptr[a + 1]; e++) {
+			int32_t const at = __atomic_fetch_add(&L->r_ptr[L->p_col[e] + 1], 1, __ATOMIC_RELAXED);
+
+			L->r_node[at] = a;
+			L->r_ent[at] = e;
 		}
 	}
 
@@ -550,17 +660,16 @@ static int build_transfer(bfmi_hier_level_t* L) {
 
 		for (int32_t i = beg + 1; i < end; i++) {
 			int32_t const cur = L->r_node[i];
+			int32_t const cur_ent = L->r_ent[i];
 			int32_t j = i;
 
 			for (; j > beg && L->r_node[j - 1] > cur; j--) {
 				L->r_node[j] = L->r_node[j - 1];
+				L->r_ent[j] = L->r_ent[j - 1];
 			}
 
 			L->r_node[j] = cur;
-		}
-
-		for (int32_t i = beg; i < end; i++) {
-			L->r_ent[i] = L->p_ptr[L->r_node[i]];
+			L->r_ent[j] = cur_ent;
 		}
 	}
 
@@ -883,14 +992,19 @@ static int centroids(bfmi_hier_level_t* L, int32_t n_agg, int32_t id_shift, doub
 		for (int32_t g = 0; g < n_agg; g++) {
 			double sx = 0, sy = 0;
 
+			int32_t members = 0;
+
 			for (int32_t at = L->r_ptr[g]; at < L->r_ptr[g + 1]; at++) {
-				sx += L->pos[2 * (size_t) L->r_node[at] + 0];
-				sy += L->pos[2 * (size_t) L->r_node[at] + 1];
+				if (L->agg[L->r_node[at]] == g) { /* a smoothed prolongator lists the neighbours of the aggregate too */
+					sx += L->pos[2 * (size_t) L->r_node[at] + 0];
+					sy += L->pos[2 * (size_t) L->r_node[at] + 1];
+					members++;
+				}
 			}
 
 			cen[2 * (size_t) g + 0] = sx;
 			cen[2 * (size_t) g + 1] = sy;
-			count[g] = L->r_ptr[g + 1] - L->r_ptr[g];
+			count[g] = members;
 		}
 	}
 
@@ -941,10 +1055,11 @@ bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, bfmi
 	/* aggregate sizes: nodes per aggregate on the mesh level and on the levels above; the last level is solved by
 	 * a dense inverse and may hold this many nodes (three unknowns each) */
 	int64_t const ratio0 = env_i64("BFM_MG_RATIO0", 16);
-	int64_t const ratio = env_i64("BFM_MG_RATIO", 6);
+	int64_t const ratio = env_i64("BFM_MG_RATIO", env_i64("BFM_MG_SMOOTH", BFMI_MG_SMOOTH_DEFAULT) != 0 ? 8 : 6);
 	int64_t const dense_nodes = env_i64("BFM_MG_DENSE_NODES", 1024);
 	int64_t const dense_limit = 2 * dense_nodes; /* pieces of bins can exceed the target */
 	int64_t replicated_nodes = env_i64("BFM_MG_REPLICATED_NODES", 65536);
+	bool const smooth = env_i64("BFM_MG_SMOOTH", BFMI_MG_SMOOTH_DEFAULT) != 0; /* smoothed aggregation (build_transfer) */
 
 	int const world = part != NULL ? part->world : 1;
 	int const rank = part != NULL ? part->rank : 0;
@@ -1033,6 +1148,7 @@ bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, bfmi
 		}
 
 		L->agg = malloc(((size_t) L->n + 1) * sizeof *L->agg);
+		L->smoothed = smooth;
 
 		if (L->agg == NULL) {
 			goto fail;
@@ -1547,6 +1663,7 @@ int bfmi_hier_upload(bfmi_hier_t* h, bfmg_pattern_t const* pat0, size_t* h2d_byt
 		if (l + 1 < h->n_levels) {
 			d->n_coarse = L->n_coarse;
 			d->n_p = L->n_p;
+			d->smoothed = L->smoothed ? 1 : 0;
 
 			if (
 				mirror((void**) &d->agg, L->agg, (size_t) L->n * sizeof(int32_t), &bytes) < 0 ||
@@ -1616,7 +1733,7 @@ static uint64_t hash_coords(double const* coords, size_t count) {
 }
 
 static uint64_t settings_hash(void) {
-	return (uint64_t) env_i64("BFM_MG_RATIO0", 16) * 1000003u + (uint64_t) env_i64("BFM_MG_RATIO", 6) * 10007u + (uint64_t) env_i64("BFM_MG_DENSE_NODES", 1024) + (uint64_t) env_i64("BFM_MG_REPLICATED_NODES", 65536) * 7919u;
+	return (uint64_t) env_i64("BFM_MG_RATIO0", 16) * 1000003u + (uint64_t) env_i64("BFM_MG_RATIO", env_i64("BFM_MG_SMOOTH", BFMI_MG_SMOOTH_DEFAULT) != 0 ? 8 : 6) * 10007u + (uint64_t) env_i64("BFM_MG_DENSE_NODES", 1024) + (uint64_t) env_i64("BFM_MG_REPLICATED_NODES", 65536) * 7919u + (uint64_t) env_i64("BFM_MG_SMOOTH", BFMI_MG_SMOOTH_DEFAULT) * 104729u;
 }
 
 static bool same_key(bfmi_hier_t const* h, bfmi_plan_t const* plan, uint64_t coords_hash, int rank, int world) {
@@ -1709,7 +1826,10 @@ int bfmx_hier_info(bfm_mesh_t* mesh, bfmx_hier_info_t* info) {
 		for (int l = 0; l < h->n_levels; l++) {
 			info->n_nodes[l] = h->level[l].n;
 			info->n_slots[l] = h->level[l].n_slots;
+			info->n_entries[l] = l + 1 < h->n_levels ? h->level[l].n_p : 0;
 		}
+
+		info->smoothed = h->level[0].smoothed ? 1 : 0;
 	}
 
 	bfmi_hier_release(h);

@@ -185,6 +185,8 @@ BFMI_HIDDEN void bfmi_coarse_forget(bfm_mesh_t const* gmesh);
  * aggregation hierarchy of the multilevel preconditioner (hier.c), kernels in mg.cuh
  * ------------------------------------------------------------------------------------------- */
 
+#define BFMI_MG_SMOOTH_DEFAULT 1 /* BFM_MG_SMOOTH: 1 = smoothed aggregation on every level (V-cycle), 0 = plain aggregation (W-cycle) */
+
 typedef struct bfmi_hier_level {
 	int32_t n;            /* nodes of this level (level 0: the nodes the plan covers) */
 	int32_t dofs;         /* unknowns per node: 2 on level 0, 3 above */
@@ -223,6 +225,7 @@ typedef struct bfmi_hier_level {
 	int32_t* r_ptr;       /* [n_coarse + 1] its transpose by coarse node */
 	int32_t* r_ent;       /* [n_p] entry index */
 	int32_t* r_node;      /* [n_p] fine node of that entry, ascending per coarse node */
+	bool smoothed;        /* smoothed aggregation: nodes whose row is all this rank's reach their neighbours' aggregates (hier.c: build_transfer) */
 
 	bfmg_mg_level_t dev;
 } bfmi_hier_level_t;

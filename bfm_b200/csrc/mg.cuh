@@ -316,6 +316,144 @@ __global__ void k_mg_pscale(bfmg_mg_level_t L, double const* __restrict__ dsc_co
 	}
 }
 
+/* Smoothed aggregation: P <- (I - w A^) P~ with w = factor / (row-sum bound of A^), on the rows hier.c laid out for it
+ * (build_transfer: nodes whose whole row is this rank's; everybody else keeps the tentative row).  One thread per
+ * node; for each of its entries (coarse node J) the row of A^ is walked once and the columns b of aggregate J
+ * contribute -w A^_ab P~_b, P~_b rebuilt from b's geometry and scaling - nothing is read from pval, so the update is in
+ * place.  Fixed order: deterministic.  FINE as in k_mg_rap (level 0: the scaled operator's two planes of double2). */
+template <int NB, typename PT>
+__global__ void __launch_bounds__(kBlock) k_mg_smooth(bfmg_mg_level_t L, double const* __restrict__ fine, double const* __restrict__ dsc, PT* __restrict__ pval, unsigned long long const* __restrict__ gersh, double factor) {
+	pdl_sync();
+
+	int const a = L.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (a >= L.row_hi) {
+		return;
+	}
+
+	int const ga = L.agg[a];
+	int const abase = L.slice_off[a / kWarp] + a % kWarp;
+	int const alen = L.row_len[a];
+
+	if (ga < 0) {
+		return;
+	}
+
+	for (int u = 0; u < alen; u++) { /* hier.c's rule: a ghost among the columns keeps the row tentative */
+		int const b = L.scol[abase + u * kWarp];
+
+		if (b < L.row_lo || b >= L.row_hi) {
+			return;
+		}
+	}
+
+	double const w = factor / __longlong_as_double((long long) *gersh);
+	size_t const np = (size_t) L.n_p;
+	size_t const ns = (size_t) L.n_slots;
+
+	for (int e = L.p_ptr[a]; e < L.p_ptr[a + 1]; e++) {
+		int const J = L.p_col[e];
+		double acc[NB][3];
+
+#pragma unroll
+		for (int k = 0; k < NB; k++) {
+#pragma unroll
+			for (int m = 0; m < 3; m++) {
+				acc[k][m] = 0;
+			}
+		}
+
+		if (J == ga) {
+			float2 const d = ((float2 const*) L.geom)[a];
+			double const s0 = 1.0 / dsc[(size_t) NB * a + 0];
+			double const s1 = 1.0 / dsc[(size_t) NB * a + 1];
+
+			acc[0][0] = s0, acc[0][2] = -(double) d.y * s0;
+			acc[1][1] = s1, acc[1][2] = (double) d.x * s1;
+
+			if (NB == 3) {
+				acc[NB - 1][2] = 1.0 / dsc[(size_t) NB * a + (NB - 1)];
+			}
+		}
+
+		for (int u = 0; u < alen; u++) {
+			int const slot = abase + u * kWarp;
+			int const b = L.scol[slot];
+
+			if (L.agg[b] != J) {
+				continue;
+			}
+
+			double A[NB][NB];
+
+			if (NB == 2) {
+				double2 const top = ((double2 const*) fine)[slot];
+				double2 const bot = ((double2 const*) fine)[ns + slot];
+
+				A[0][0] = top.x, A[0][1] = top.y;
+				A[1][0] = bot.x, A[1][1] = bot.y;
+			}
+
+			else {
+#pragma unroll
+				for (int k = 0; k < NB; k++) {
+#pragma unroll
+					for (int j = 0; j < NB; j++) {
+						A[k][j] = fine[(size_t) (3 * k + j) * ns + slot];
+					}
+				}
+			}
+
+			/* P~_b: rows of [1 0 -dy; 0 1 dx; 0 0 1] scaled by D_b^1/2 (k_mg_tentative) */
+			float2 const d = ((float2 const*) L.geom)[b];
+			double pb[NB][3];
+
+#pragma unroll
+			for (int j = 0; j < NB; j++) {
+#pragma unroll
+				for (int m = 0; m < 3; m++) {
+					pb[j][m] = 0;
+				}
+			}
+
+			{
+				double const s0 = 1.0 / dsc[(size_t) NB * b + 0];
+				double const s1 = 1.0 / dsc[(size_t) NB * b + 1];
+
+				pb[0][0] = s0, pb[0][2] = -(double) d.y * s0;
+				pb[1][1] = s1, pb[1][2] = (double) d.x * s1;
+
+				if (NB == 3) {
+					pb[NB - 1][2] = 1.0 / dsc[(size_t) NB * b + (NB - 1)];
+				}
+			}
+
+#pragma unroll
+			for (int k = 0; k < NB; k++) {
+#pragma unroll
+				for (int m = 0; m < 3; m++) {
+					double t = 0;
+
+#pragma unroll
+					for (int j = 0; j < NB; j++) {
+						t = fma(A[k][j], pb[j][m], t);
+					}
+
+					acc[k][m] = fma(-w, t, acc[k][m]);
+				}
+			}
+		}
+
+#pragma unroll
+		for (int k = 0; k < NB; k++) {
+#pragma unroll
+			for (int m = 0; m < 3; m++) {
+				pval[(size_t) (k * 3 + m) * np + e] = (PT) acc[k][m];
+			}
+		}
+	}
+}
+
 /* out = P^T v: kMgGroup lanes per coarse node walk its entry list (ascending fine nodes), then a fixed
  * shuffle tree - deterministic.  n_out >= 3 * n_coarse: the padding up to it is zeroed (dense level). */
 template <int NB, typename PT, bool CG>
@@ -466,10 +604,14 @@ __global__ void __launch_bounds__(kBlock) k_mg_rap(bfmg_mg_level_t L, bfmg_mg_le
 				for (int u = 0; u < alen; u++) {
 					int const slot = abase + u * kWarp;
 					int const b = L.scol[slot];
-					int const eb = L.p_ptr[b];
+					int eb = L.p_ptr[b];
+					int const eb_end = L.p_ptr[b + 1];
 
-					if (eb == L.p_ptr[b + 1] || L.p_col[eb] != my_col) {
-						continue; /* b is outside the coarse space, or belongs to another lane's column */
+					for (; eb < eb_end && L.p_col[eb] != my_col; eb++) { /* one entry per node, or a few with a smoothed prolongator */
+					}
+
+					if (eb == eb_end) {
+						continue; /* b is outside the coarse space, or has nothing for this lane's column */
 					}
 
 					double A[NB][NB];
@@ -512,6 +654,189 @@ __global__ void __launch_bounds__(kBlock) k_mg_rap(bfmg_mg_level_t L, bfmg_mg_le
 							for (int k = 0; k < NB; k++) {
 								c[i][m] = fma(pa[k][i], t[k], c[i][m]);
 							}
+						}
+					}
+				}
+			}
+
+			if (my_slot >= 0) {
+#pragma unroll
+				for (int i = 0; i < 3; i++) {
+#pragma unroll
+					for (int m = 0; m < 3; m++) {
+						if (DENSE) {
+							val[(size_t) (3 * I + i) * n_dense + 3 * my_col + m] = c[i][m];
+						}
+
+						else {
+							val[(size_t) (3 * i + m) * N.n_slots + my_slot] = c[i][m];
+						}
+					}
+				}
+			}
+		}
+	}
+}
+
+/* The same product in two steps, for prolongators with several entries per node (smoothed aggregation).  Above, the
+ * lane of column J visits every (a, b) pair of the row's support and looks b's entries up - with one entry per node a
+ * third of the visits hit, with a smoothed prolongator (36 nodes in a support instead of 16, 2.7 entries per node, the
+ * same 9 columns) one in seven: 92 ms instead of 33 on the mesh level at 50 M DOF.  So first
+ *
+ *   k_mg_ap    Q = A P by fine node: one thread per row a (SELL-32: lane = row, coalesced) accumulates
+ *              Q(a, J) = sum_b A_ab P(b, J) over its slots in order, the J kept in a short list in local memory
+ *              (first come, first listed; rap_width columns at most, else *overflow and the one-step kernel runs);
+ *   k_mg_ptq   A_c(I, J) = sum_a P(a, I)^T Q(a, J): one warp per coarse node, lane = slot of row I as above, over the
+ *              support's nodes in ascending order - 36 visits with a short search instead of 252.
+ *
+ * Every entry is still summed by one lane in a fixed order.  Q is n_own x rap_width blocks of NB x 3 doubles (+ the
+ * column list): transient set-up memory, 15.6 GB for 25 M mesh nodes. */
+
+template <int NB>
+__host__ __device__ constexpr int rap_width() { return NB == 2 ? 12 : 24; } /* coarse columns a row of Q can hold: mesh level (aggregates of >= 3 nodes, 16 as a rule) / the levels above (6 nodes) */
+
+template <int NB, typename PT>
+__global__ void __launch_bounds__(kBlock) k_mg_ap(bfmg_mg_level_t L, double const* __restrict__ fine, PT const* __restrict__ pval, int32_t* __restrict__ qcol, double* __restrict__ qval, int32_t* __restrict__ overflow) {
+	pdl_sync();
+
+	int const a = blockIdx.x * blockDim.x + threadIdx.x; /* from row 0: lane = row inside the slice */
+
+	if (a < L.row_lo || a >= L.row_hi) {
+		return;
+	}
+
+	constexpr int kRapWidth = rap_width<NB>();
+
+	int const abase = L.slice_off[a / kWarp] + a % kWarp;
+	int const alen = L.row_len[a];
+	size_t const np = (size_t) L.n_p;
+	size_t const ns = (size_t) L.n_slots;
+
+	int32_t col[kRapWidth];
+	double q[kRapWidth][NB * 3];
+	int cnt = 0;
+
+	for (int u = 0; u < alen; u++) {
+		int const slot = abase + u * kWarp;
+		int const b = L.scol[slot];
+		int const eb_end = L.p_ptr[b + 1];
+
+		double A[NB][NB];
+
+		if (NB == 2) {
+			double2 const top = ((double2 const*) fine)[slot];
+			double2 const bot = ((double2 const*) fine)[ns + slot];
+
+			A[0][0] = top.x, A[0][1] = top.y;
+			A[1][0] = bot.x, A[1][1] = bot.y;
+		}
+
+		else {
+#pragma unroll
+			for (int k = 0; k < NB; k++) {
+#pragma unroll
+				for (int j = 0; j < NB; j++) {
+					A[k][j] = fine[(size_t) (3 * k + j) * ns + slot];
+				}
+			}
+		}
+
+		for (int eb = L.p_ptr[b]; eb < eb_end; eb++) {
+			int const J = L.p_col[eb];
+			int t = 0;
+
+			for (; t < cnt && col[t] != J; t++) {
+			}
+
+			if (t == cnt) {
+				if (cnt == kRapWidth) {
+					*overflow = 1;
+					continue;
+				}
+
+				col[cnt++] = J;
+
+#pragma unroll
+				for (int i = 0; i < NB * 3; i++) {
+					q[t][i] = 0;
+				}
+			}
+
+#pragma unroll
+			for (int m = 0; m < 3; m++) {
+#pragma unroll
+				for (int k = 0; k < NB; k++) {
+					double acc = q[t][k * 3 + m];
+
+#pragma unroll
+					for (int j = 0; j < NB; j++) {
+						acc = fma(A[k][j], (double) pval[(size_t) (j * 3 + m) * np + eb], acc);
+					}
+
+					q[t][k * 3 + m] = acc;
+				}
+			}
+		}
+	}
+
+	size_t const row = (size_t) (a - L.row_lo) * kRapWidth;
+
+	for (int t = 0; t < kRapWidth; t++) {
+		qcol[row + t] = t < cnt ? col[t] : -1;
+
+		if (t < cnt) {
+#pragma unroll
+			for (int i = 0; i < NB * 3; i++) {
+				qval[(row + t) * (NB * 3) + i] = q[t][i];
+			}
+		}
+	}
+}
+
+template <int NB, typename PT, bool DENSE>
+__global__ void __launch_bounds__(kBlock) k_mg_ptq(bfmg_mg_level_t L, bfmg_mg_level_t N, PT const* __restrict__ pval, int32_t const* __restrict__ qcol, double const* __restrict__ qval, double* __restrict__ val, int n_dense) {
+	pdl_sync();
+
+	constexpr int kRapWidth = rap_width<NB>();
+
+	int const lane = threadIdx.x & (kWarp - 1);
+	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+	int const n_warps = gridDim.x * blockDim.x / kWarp;
+	size_t const np = (size_t) L.n_p;
+
+	for (int I = warp; I < N.row_hi; I += n_warps) {
+		int const base = N.slice_off[I / kWarp] + I % kWarp;
+		int const len = N.row_len[I];
+
+		for (int t0 = 0; t0 < len; t0 += kWarp) {
+			int const my_slot = t0 + lane < len ? base + (t0 + lane) * kWarp : -1;
+			int const my_col = my_slot >= 0 ? N.scol[my_slot] : -2; /* -2: matches neither a column nor the padding of a list */
+
+			double c[3][3] = {};
+
+			for (int at = L.r_ptr[I]; at < L.r_ptr[I + 1]; at++) {
+				size_t const row = (size_t) (L.r_node[at] - L.row_lo) * kRapWidth;
+				int const ea = L.r_ent[at];
+				int t = 0;
+
+				for (; t < kRapWidth && qcol[row + t] != my_col; t++) {
+				}
+
+				if (t == kRapWidth) {
+					continue;
+				}
+
+				double const* const q = qval + (row + t) * (NB * 3);
+
+#pragma unroll
+				for (int i = 0; i < 3; i++) {
+#pragma unroll
+					for (int k = 0; k < NB; k++) {
+						double const pa = (double) pval[(size_t) (k * 3 + i) * np + ea];
+
+#pragma unroll
+						for (int m = 0; m < 3; m++) {
+							c[i][m] = fma(pa, q[k * 3 + m], c[i][m]);
 						}
 					}
 				}
@@ -784,6 +1109,9 @@ struct MgRun {
 	int32_t* bad = nullptr;
 
 	double omega_factor = 1.8;
+	bool rap_two_step = true;         /* BFM_MG_RAP=direct: the one-step Galerkin kernel for smoothed prolongators too */
+	double smooth_factor = 1.8;       /* prolongator smoothing: w = smooth_factor / (row-sum bound), BFM_MG_SMOOTH_OMEGA.  The bound is
+	                                   * Gershgorin's, ~1.4x the largest eigenvalue on these operators: 1.8 / bound ~ the classic 4 / (3 lambda_max) */
 	double lambda0 = 4;     /* Gershgorin bound of the scaled level-0 operator (after setup) */
 	float2* ftop = nullptr; /* FP32 copy of the scaled level-0 operator for the smoothing products: plane of (a00,a01) */
 	float2* fbot = nullptr; /* ... and of (a10,a11) */
@@ -919,7 +1247,7 @@ struct MgRun {
 		char const* env = getenv("BFM_MG_GAMMA");
 
 		for (int l = 1; l < n_levels - 1; l++) { /* "2" or a list per level from level 1 on, "2,2,1": the last entry repeats */
-			int g = 2;
+			int g = mg->level[l].smoothed ? 1 : 2; /* a smoothed prolongator interpolates well enough for the V-cycle */
 
 			if (env != nullptr && env[0] != 0) {
 				char const* at_env = env;
@@ -944,6 +1272,15 @@ struct MgRun {
 
 		if (env != nullptr && atof(env) > 0 && atof(env) < 2) {
 			omega_factor = atof(env);
+		}
+
+		env = getenv("BFM_MG_RAP");
+		rap_two_step = env == nullptr || strcmp(env, "direct") != 0;
+
+		env = getenv("BFM_MG_SMOOTH_OMEGA");
+
+		if (env != nullptr && atof(env) > 0 && atof(env) < 2) {
+			smooth_factor = atof(env);
 		}
 
 		return 0;
@@ -1066,13 +1403,76 @@ struct MgRun {
 				? BFMG_LAUNCH((k_mg_tentative<2, float>), node_blocks, kBlock, 0, w.L, (double const*) dscale, (float*) w.pval)
 				: BFMG_LAUNCH((k_mg_tentative<3, double>), node_blocks, kBlock, 0, w.L, (double const*) w.dsc, (double*) w.pval);
 
+			if (rc == 0 && w.L.smoothed) { /* smoothed aggregation: (I - w A^) P~ with the scaled operator of this level */
+				int const own_blocks = (w.L.row_hi - w.L.row_lo + kBlock - 1) / kBlock;
+
+				rc = l == 0
+					? BFMG_LAUNCH((k_mg_smooth<2, float>), own_blocks, kBlock, 0, w.L, (double const*) stop, (double const*) dscale, (float*) w.pval, (unsigned long long const*) &D->gersh[0], smooth_factor)
+					: BFMG_LAUNCH((k_mg_smooth<3, double>), own_blocks, kBlock, 0, w.L, (double const*) w.val, (double const*) w.dsc, (double*) w.pval, (unsigned long long const*) &D->gersh[l], smooth_factor);
+			}
+
 			if (rc < 0 || BFMG_CHECK(cudaMemsetAsync(target, 0, target_bytes, bfmg_stream())) < 0) {
 				return -1;
 			}
 
 			int const rap_grid = bfmg_grid(((int64_t) nx.L.row_hi + kWarpsPerBlock - 1) / kWarpsPerBlock, 8);
 
-			if (dense) {
+			/* a prolongator with several entries per node: Q = A P by fine node, then P^T Q (see k_mg_ap); the one-step
+			 * kernel when a node's Q row does not fit kRapWidth columns, or without the memory for Q */
+
+			bool two_step = w.L.smoothed != 0 && rap_two_step;
+
+			if (two_step) {
+				size_t const n_own = (size_t) (w.L.row_hi - w.L.row_lo);
+				int const nb = l == 0 ? 2 : 3;
+				size_t const width = (size_t) (l == 0 ? rap_width<2>() : rap_width<3>());
+				int32_t* qcol = nullptr;
+				double* qval = nullptr;
+				int32_t overflow = 0;
+
+				if (bfmg_alloc((void**) &qcol, n_own * width * sizeof *qcol) < 0 || bfmg_alloc((void**) &qval, n_own * width * nb * 3 * sizeof *qval) < 0) {
+					two_step = false;
+				}
+
+				else {
+					int const ap_grid = (w.L.row_hi + kBlock - 1) / kBlock;
+
+					rc = BFMG_CHECK(cudaMemsetAsync(bad + 8, 0, sizeof(int32_t), bfmg_stream()));
+
+					rc = rc < 0 ? rc : (l == 0
+						? BFMG_LAUNCH((k_mg_ap<2, float>), ap_grid, kBlock, 0, w.L, (double const*) stop, (float const*) w.pval, qcol, qval, bad + 8)
+						: BFMG_LAUNCH((k_mg_ap<3, double>), ap_grid, kBlock, 0, w.L, (double const*) w.val, (double const*) w.pval, qcol, qval, bad + 8));
+
+					if (rc == 0) {
+						rc = dense
+							? (l == 0
+								? BFMG_LAUNCH((k_mg_ptq<2, float, true>), rap_grid, kBlock, 0, w.L, nx.L, (float const*) w.pval, (int32_t const*) qcol, (double const*) qval, target, nc)
+								: BFMG_LAUNCH((k_mg_ptq<3, double, true>), rap_grid, kBlock, 0, w.L, nx.L, (double const*) w.pval, (int32_t const*) qcol, (double const*) qval, target, nc))
+							: (l == 0
+								? BFMG_LAUNCH((k_mg_ptq<2, float, false>), rap_grid, kBlock, 0, w.L, nx.L, (float const*) w.pval, (int32_t const*) qcol, (double const*) qval, target, nc)
+								: BFMG_LAUNCH((k_mg_ptq<3, double, false>), rap_grid, kBlock, 0, w.L, nx.L, (double const*) w.pval, (int32_t const*) qcol, (double const*) qval, target, nc));
+					}
+
+					if (rc == 0 && (BFMG_CHECK(cudaMemcpyAsync(&overflow, bad + 8, sizeof overflow, cudaMemcpyDeviceToHost, bfmg_stream())) < 0 || BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0)) {
+						rc = -1;
+					}
+
+					two_step = overflow == 0;
+				}
+
+				bfmg_free(qcol);
+				bfmg_free(qval);
+
+				if (rc < 0) {
+					return -1;
+				}
+			}
+
+			if (two_step) {
+				/* done above */
+			}
+
+			else if (dense) {
 				rc = l == 0
 					? BFMG_LAUNCH((k_mg_rap<2, float, true>), rap_grid, kBlock, 0, w.L, nx.L, (double const*) stop, (float const*) w.pval, target, nc)
 					: BFMG_LAUNCH((k_mg_rap<3, double, true>), rap_grid, kBlock, 0, w.L, nx.L, (double const*) w.val, (double const*) w.pval, target, nc);

@@ -48,7 +48,7 @@ class Stats(C.Structure):  # bfmx_stats_t
 
 
 class HierInfo(C.Structure):  # bfmx_hier_info_t
-	_fields_ = [("n_levels", C.c_int32), ("n_nodes", C.c_int32 * 12), ("n_slots", C.c_int64 * 12)]
+	_fields_ = [("n_levels", C.c_int32), ("n_nodes", C.c_int32 * 12), ("n_slots", C.c_int64 * 12), ("n_entries", C.c_int64 * 12), ("smoothed", C.c_int32), ("pad_", C.c_int32)]
 
 
 class PartitionInfo(C.Structure):  # bfmx_partition_info_t

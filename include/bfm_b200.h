@@ -185,6 +185,9 @@ typedef struct {
 	int32_t n_levels;
 	int32_t n_nodes[BFMX_HIER_MAX_LEVELS];
 	int64_t n_slots[BFMX_HIER_MAX_LEVELS];   /* padded SELL-32 slots of the level's operator */
+	int64_t n_entries[BFMX_HIER_MAX_LEVELS]; /* entries of the prolongator towards the next level (0 on the last): one per node with the tentative prolongator, one per (node, neighbouring aggregate) with smoothed aggregation */
+	int32_t smoothed;                        /* 1: smoothed aggregation (BFM_MG_SMOOTH, the default), V-cycle; 0: plain aggregation, W-cycle */
+	int32_t pad_;
 } bfmx_hier_info_t;
 
 int bfmx_hier_info(bfm_mesh_t* mesh, bfmx_hier_info_t* info);

@@ -63,8 +63,12 @@ def tentative(level, dofs, sq):
 
 
 class Emulation:
-	def __init__(self, A, levels, gamma=2, omega=1.8, single_precision_p=True):
-		"""A: the assembled matrix (scipy, DOFs interleaved per node); levels: hierarchy()"""
+	def __init__(self, A, levels, gamma=None, omega=1.8, single_precision_p=True, smooth=False, smooth_omega=1.8):
+		"""A: the assembled matrix (scipy, DOFs interleaved per node); levels: hierarchy().  smooth: smoothed aggregation
+		as k_mg_smooth does it on one GPU - P = (I - w A^) P~ on every level, w = smooth_omega / (largest absolute row
+		sum) - with a V-cycle unless gamma says otherwise (the tentative prolongator needs the W-cycle)"""
+
+		gamma = gamma if gamma is not None else (1 if smooth else 2)
 
 		d = np.abs(A.diagonal())
 		self.dscale = np.where(d > 0, 1.0 / np.sqrt(np.where(d > 0, d, 1.0)), 1.0)
@@ -77,6 +81,10 @@ class Emulation:
 
 		for l in range(len(levels) - 1):
 			P = tentative(levels[l], 2 if l == 0 else 3, 1.0 / dsc)
+
+			if smooth:
+				bound = float(abs(self.ops[l]).sum(axis=1).max())
+				P = (P - (smooth_omega / bound) * (self.ops[l] @ P)).tocsr()
 
 			if l == 0 and single_precision_p:
 				P.data = P.data.astype(np.float32).astype(np.float64)

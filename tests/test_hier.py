@@ -15,8 +15,11 @@ def _pattern(level):
 	return sp.csr_matrix((np.ones(len(level["col"]), np.int8), level["col"].astype(np.int64), level["rowptr"].astype(np.int64)), shape=(n, n))
 
 
+@pytest.mark.parametrize("smooth", ["0", "1"])
 @pytest.mark.parametrize("name", ["gear60", "plate_160x40", "plate_300x75", "plate_jitter_40x10", "bridge_dam"])
-def test_hierarchy_invariants(name, lib, monkeypatch):
+def test_hierarchy_invariants(name, smooth, lib, monkeypatch):
+	monkeypatch.setenv("BFM_MG_SMOOTH", smooth)
+
 	if name == "bridge_dam":
 		monkeypatch.setenv("BFM_MG_RATIO0", "6")      # a small truss mesh: small aggregates so that it still gets levels
 		monkeypatch.setenv("BFM_MG_DENSE_NODES", "64")
@@ -38,10 +41,17 @@ def test_hierarchy_invariants(name, lib, monkeypatch):
 		degree = np.diff(fine["rowptr"])
 		assert np.all(degree[agg < 0] <= 1)
 
-		# pattern of the next level == pattern of P^T A P, P the aggregate indicator
+		# pattern of the next level == pattern of P^T A P, P the aggregate indicator - or, with smoothed aggregation,
+		# the pattern of (I + A) times it: every node reaches the aggregates of its neighbours
 		keep = np.flatnonzero(agg >= 0)
-		P = sp.csr_matrix((np.ones(len(keep), np.int8), (keep, agg[keep].astype(np.int64))), shape=(fine["n"], coarse["n"]))
-		want = (P.T @ _pattern(fine) @ P).tocsr()
+		P = sp.csr_matrix((np.ones(len(keep), np.int32), (keep, agg[keep].astype(np.int64))), shape=(fine["n"], coarse["n"]))
+
+		if smooth == "1":
+			mask = sp.diags((agg >= 0).astype(np.float64))
+			P = (mask @ (_pattern(fine).astype(np.int32) @ P + P)).tocsr()
+			P.data[:] = 1
+
+		want = (P.T @ _pattern(fine).astype(np.int32) @ P).tocsr()
 		want.sort_indices()
 		got = _pattern(coarse)
 
@@ -64,6 +74,25 @@ def test_no_hierarchy_for_tiny_meshes(lib):
 
 	assert mg_emulation.hierarchy(lib, ext.plate(4, 2, kind=3, binding=lib)) == []   # 15 nodes: nothing to coarsen
 	assert len(mg_emulation.hierarchy(lib, cases.build("lepl8", lib).mesh)) == 2     # 335 nodes: mesh level + dense level
+
+
+@pytest.mark.parametrize("name,most", [("gear60", 200), ("plate_160x40", 60), ("plate_300x75", 70)])
+def test_emulated_smoothed_aggregation_converges_to_the_reference(name, most, lib, golden, monkeypatch):
+	"""the same with smoothed aggregation (BFM_MG_SMOOTH=1: k_mg_smooth, V-cycle), on the hierarchy hier.c lays out for it"""
+
+	monkeypatch.setenv("BFM_MG_SMOOTH", "1")
+
+	case = cases.build(name, lib)
+	levels = mg_emulation.hierarchy(lib, case.mesh)
+	system = cases.oracle_problem(case).system()
+
+	emu = mg_emulation.Emulation(system.scipy().tocsr(), levels, smooth=True)
+	x, iterations = emu.solve(system.b.copy())
+
+	assert iterations <= most, iterations
+
+	want = golden[f"{name}/effects"].reshape(-1)
+	assert np.linalg.norm(x - want) / np.linalg.norm(want) <= 1e-9
 
 
 @pytest.mark.parametrize("name,most", [("gear60", 320), ("plate_160x40", 80), ("plate_jitter_40x10", 60)])
