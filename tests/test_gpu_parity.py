@@ -396,13 +396,16 @@ def test_coarse_level_changes_speed_not_answers(name, lib, golden, monkeypatch):
 	assert runs["24"]["cg_iterations"] * 1.6 < runs["0"]["cg_iterations"], (runs["0"]["cg_iterations"], runs["24"]["cg_iterations"])
 
 
+@pytest.mark.parametrize("smooth", ["1", "0"])
 @pytest.mark.parametrize("name", ["gear60", "plate_160x40", "plate_300x75", "bridge_dam", "plate_q4_jitter_24x6", "lepl8_all_kinds"])
-def test_multilevel_preconditioner_changes_speed_not_answers(name, lib, golden, monkeypatch):
-	"""general path with the aggregation multigrid cycle (hier.c, mg.cuh) against the diagonal preconditioner
+def test_multilevel_preconditioner_changes_speed_not_answers(name, smooth, lib, golden, monkeypatch):
+	"""general path with the aggregation multigrid cycle (hier.c, mg.cuh) - smoothed aggregation with a V-cycle (the
+	default) and the tentative prolongator with a W-cycle (BFM_MG_SMOOTH=0) - against the diagonal preconditioner
 	alone: the same displacements to the north star's tolerance, several times fewer iterations"""
 
 	monkeypatch.setenv("BFM_ONE_CTA", "0")
 	monkeypatch.setenv("BFM_COARSE_AGGREGATES", "0")
+	monkeypatch.setenv("BFM_MG_SMOOTH", smooth)
 
 	if case_is_small := name in ("bridge_dam", "plate_q4_jitter_24x6", "lepl8_all_kinds"):
 		monkeypatch.setenv("BFM_MG_RATIO0", "6")       # small meshes: small aggregates so that they still get levels
@@ -424,6 +427,31 @@ def test_multilevel_preconditioner_changes_speed_not_answers(name, lib, golden, 
 
 	assert runs["0"]["mg_levels"] == 0 and runs["1"]["mg_levels"] >= 2 and runs["1"]["coarse_dim"] > 0
 	assert runs["1"]["cg_iterations"] * (2 if case_is_small else 4) < runs["0"]["cg_iterations"], (runs["0"]["cg_iterations"], runs["1"]["cg_iterations"])
+
+
+def test_galerkin_product_in_one_and_two_steps(lib, golden, monkeypatch):
+	"""smoothed aggregation: the coarse operators from k_mg_ap + k_mg_ptq (Q = A P by fine node, then P^T Q) and from the
+	one-step kernel (BFM_MG_RAP=direct) are the same product in another association: same iteration count, displacements
+	equal far below the tolerance"""
+
+	monkeypatch.setenv("BFM_ONE_CTA", "0")
+	monkeypatch.setenv("BFM_MG_DENSE_NODES", "100")  # 22 876 -> 1 430 -> ~180 nodes: two Galerkin products, the second one dense
+
+	case = cases.build("plate_300x75", lib)
+	outs, its = [], []
+
+	for how in ("two-step", "direct"):
+		monkeypatch.setenv("BFM_MG_RAP", how)
+		case.sim.run()
+		stats = ext.last_stats(lib)
+
+		assert stats["cg_converged"] == 1 and stats["mg_levels"] >= 3
+		outs.append(case.instance.effects.copy())
+		its.append(stats["cg_iterations"])
+
+	assert abs(its[0] - its[1]) <= 1
+	assert rel_l2(outs[0], outs[1]) <= 1e-11
+	assert rel_l2(outs[0], golden["plate_300x75/effects"]) <= REL_L2
 
 
 def test_multilevel_preconditioner_is_deterministic(lib, monkeypatch):
