@@ -14,12 +14,15 @@
  * Aggregates are the connected pieces of the cells of a uniform grid of bins over the level's bounding box
  * (pieces too small to carry three independent modes join a neighbour).  Between two levels sits the
  * prolongator P, stored by its sparsity structure (CSR by fine node + its transpose by coarse node); its
- * values are computed on the device for every solve because they carry the matrix's diagonal scaling.  The
- * next level's operator P^T A P is computed on the device too (k_mg_rap); its sparsity pattern is computed
- * here, symbolically, as the same product.
+ * values are computed on the device for every solve because they carry the matrix's diagonal scaling.  With
+ * smoothed aggregation (BFM_MG_SMOOTH, the default) P = (I - w A^) P~: the row of a node has an entry for the
+ * aggregate of every neighbour (build_transfer below), with the tentative prolongator P~ one entry, its own
+ * aggregate's.  The next level's operator P^T A P is computed on the device too (k_mg_ap + k_mg_ptq, or
+ * k_mg_rap); its sparsity pattern is computed here, symbolically, as the same product.
  *
  * Several GPUs (one rank per GPU, partition.c): every rank builds the hierarchy of ITS rows.  Aggregates are formed
- * from owned nodes only, so they never straddle two ranks: restriction and prolongation stay local and only the
+ * from owned nodes only, so they never straddle two ranks - and only nodes with no ghost among their columns are
+ * smoothed, so no prolongator row does either: restriction and prolongation stay local and only the
  * products with a level's operator need a halo exchange, exactly as on the mesh level.  A level is DISTRIBUTED
  * (local numbering: owned nodes first, then the ghosts of each neighbour, ascending by the owner's numbering)
  * while it is large; from the first level of at most BFM_MG_REPLICATED_NODES nodes on it is REPLICATED: every

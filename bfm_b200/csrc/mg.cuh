@@ -12,9 +12,11 @@
  *             scaled to a unit diagonal, SELL-32 with nine value planes
  *   last      dense, inverted once per solve by coarse.cuh's blocked Gauss-Jordan
  *
- * P holds, per node of an aggregate, the aggregate's rigid-body modes seen from that node, in the scaled
- * variables of both levels: P_a = D_a^1/2 [1 0 -dy; 0 1 dx; (0 0 1)] D_I^-1/2.  One cycle on level l for a
- * right-hand side g (damped Jacobi, the diagonal being the identity):
+ * The tentative prolongator P~ holds, per node of an aggregate, the aggregate's rigid-body modes seen from that node,
+ * in the scaled variables of both levels: P~_a = D_a^1/2 [1 0 -dy; 0 1 dx; (0 0 1)] D_I^-1/2.  With smoothed
+ * aggregation (the default; hier.c lays the entries out, k_mg_smooth fills them) P = (I - w_s A^) P~ and the cycle is
+ * a V-cycle; with P = P~ (BFM_MG_SMOOTH=0) it has to be a W-cycle.  One cycle on level l for a right-hand side g
+ * (damped Jacobi, the diagonal being the identity):
  *
  *   z = w g                       pre-smoothing from a zero guess needs no product
  *   t = g - A z                   one fused SpMV (k_spmv_mg<kPre> / k_blk_spmv<kPre>)
@@ -25,14 +27,15 @@
  * always holds and the smoother - hence the whole cycle - is symmetric positive definite.  The preconditioner
  * changes how fast CG converges, not what it converges to: the stopping test stays on the true CG residual.
  *
- * Set-up, once per solve: P from the diagonal scaling; A_{l+1} = P^T A_l P by k_mg_rap (one warp per coarse
+ * Set-up, once per solve: P from the diagonal scaling (and the level's scaled operator); A_{l+1} = P^T A_l P by
+ * k_mg_ap + k_mg_ptq (Q = A P by fine node, P^T Q by coarse node) or, for one-entry rows, k_mg_rap (one warp per coarse
  * node, one pass over A_l); its diagonal, scaling and row-sum bound; at the end the dense inverse.  Everything is deterministic: fixed-order sums, no floating-point atomics (the row-sum bound
  * is a maximum, taken with an integer atomicMax on the bit pattern of non-negative doubles).
  *
  * All kernels are HBM-bound streaming work.  Algorithmic bytes per mesh node and PCG iteration on the
- * structured P1 plate (7 blocks per row), level 0:  k_spmv<kDot> 284 + k_update_xr 96 + k_spmv_mg<kPre> 284 +
- * k_mg_restrict 48 + k_mg_prolong 64 + k_spmv_mg<kPost> 300 + k_update_p 48 = 1124 B; the coarser levels add
- * about a quarter of that.
+ * structured P1 plate (7 blocks per row, 2.65 prolongator entries per node), level 0:  k_spmv<kDot> 284 +
+ * k_update_xr 96 + k_spmv_mg<kPre> 172 + k_mg_restrict 101 + k_mg_prolong 106 + k_spmv_mg<kPost> 188 + k_update_p 48
+ * = 995 B; the coarser levels add about a tenth of that.
  */
 #pragma once
 

@@ -112,3 +112,29 @@ def test_emulated_cycle_converges_to_the_reference(name, most, lib, golden):
 
 	want = golden[f"{name}/effects"].reshape(-1)
 	assert np.linalg.norm(x - want) / np.linalg.norm(want) <= 1e-9
+
+
+def test_hierarchy_info_counts_prolongator_entries(lib, monkeypatch):
+	"""bfmx_hier_info: one entry per node with the tentative prolongator, one per (node, aggregate of a neighbour) with
+	smoothed aggregation - the count bench.py's byte model uses"""
+
+	import ctypes as C
+
+	from bfm_b200 import ext
+
+	case = cases.build("plate_160x40", lib)
+	counts = {}
+
+	for smooth in ("0", "1"):
+		monkeypatch.setenv("BFM_MG_SMOOTH", smooth)
+		info = ext.HierInfo()
+		assert not lib.lib.bfmx_hier_info(case.mesh.c_mesh, C.byref(info))
+		assert info.smoothed == int(smooth) and info.n_levels >= 2 and info.n_entries[info.n_levels - 1] == 0
+		counts[smooth] = (info.n_nodes[0], info.n_entries[0])
+
+	levels = mg_emulation.hierarchy(lib, case.mesh)  # smoothed layout
+	agg, rowptr, col = levels[0]["agg"], levels[0]["rowptr"], levels[0]["col"]
+	want = sum(len(np.unique(agg[col[rowptr[a]:rowptr[a + 1]]])) for a in range(levels[0]["n"]))
+
+	assert counts["0"] == (case.mesh.n_nodes, case.mesh.n_nodes)
+	assert counts["1"] == (case.mesh.n_nodes, want) and want > 2 * case.mesh.n_nodes
