@@ -796,22 +796,24 @@ __global__ void __launch_bounds__(kBlock) k_mg_ap(bfmg_mg_level_t L, double cons
 	}
 }
 
-template <int NB, typename PT, bool DENSE>
+/* G lanes per coarse row: 32, or 16 where the rows are short (the level above the mesh has 9 columns per row on a
+ * plate: two rows per warp keep 18 lanes busy instead of 9).  No shuffles: the two halves of a warp are independent. */
+template <int NB, typename PT, bool DENSE, int G>
 __global__ void __launch_bounds__(kBlock) k_mg_ptq(bfmg_mg_level_t L, bfmg_mg_level_t N, PT const* __restrict__ pval, int32_t const* __restrict__ qcol, double const* __restrict__ qval, double* __restrict__ val, int n_dense) {
 	pdl_sync();
 
 	constexpr int kRapWidth = rap_width<NB>();
 
-	int const lane = threadIdx.x & (kWarp - 1);
-	int const warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
-	int const n_warps = gridDim.x * blockDim.x / kWarp;
+	int const lane = threadIdx.x & (G - 1);
+	int const group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+	int const n_groups = gridDim.x * blockDim.x / G;
 	size_t const np = (size_t) L.n_p;
 
-	for (int I = warp; I < N.row_hi; I += n_warps) {
+	for (int I = group; I < N.row_hi; I += n_groups) {
 		int const base = N.slice_off[I / kWarp] + I % kWarp;
 		int const len = N.row_len[I];
 
-		for (int t0 = 0; t0 < len; t0 += kWarp) {
+		for (int t0 = 0; t0 < len; t0 += G) {
 			int const my_slot = t0 + lane < len ? base + (t0 + lane) * kWarp : -1;
 			int const my_col = my_slot >= 0 ? N.scol[my_slot] : -2; /* -2: matches neither a column nor the padding of a list */
 
@@ -1447,13 +1449,15 @@ struct MgRun {
 						: BFMG_LAUNCH((k_mg_ap<3, double>), ap_grid, kBlock, 0, w.L, (double const*) w.val, (double const*) w.pval, qcol, qval, bad + 8));
 
 					if (rc == 0) {
+						int const half_grid = bfmg_grid(((int64_t) nx.L.row_hi + 2 * kWarpsPerBlock - 1) / (2 * kWarpsPerBlock), 8); /* two rows per warp */
+
 						rc = dense
 							? (l == 0
-								? BFMG_LAUNCH((k_mg_ptq<2, float, true>), rap_grid, kBlock, 0, w.L, nx.L, (float const*) w.pval, (int32_t const*) qcol, (double const*) qval, target, nc)
-								: BFMG_LAUNCH((k_mg_ptq<3, double, true>), rap_grid, kBlock, 0, w.L, nx.L, (double const*) w.pval, (int32_t const*) qcol, (double const*) qval, target, nc))
+								? BFMG_LAUNCH((k_mg_ptq<2, float, true, 32>), rap_grid, kBlock, 0, w.L, nx.L, (float const*) w.pval, (int32_t const*) qcol, (double const*) qval, target, nc)
+								: BFMG_LAUNCH((k_mg_ptq<3, double, true, 32>), rap_grid, kBlock, 0, w.L, nx.L, (double const*) w.pval, (int32_t const*) qcol, (double const*) qval, target, nc))
 							: (l == 0
-								? BFMG_LAUNCH((k_mg_ptq<2, float, false>), rap_grid, kBlock, 0, w.L, nx.L, (float const*) w.pval, (int32_t const*) qcol, (double const*) qval, target, nc)
-								: BFMG_LAUNCH((k_mg_ptq<3, double, false>), rap_grid, kBlock, 0, w.L, nx.L, (double const*) w.pval, (int32_t const*) qcol, (double const*) qval, target, nc));
+								? BFMG_LAUNCH((k_mg_ptq<2, float, false, 16>), half_grid, kBlock, 0, w.L, nx.L, (float const*) w.pval, (int32_t const*) qcol, (double const*) qval, target, nc)
+								: BFMG_LAUNCH((k_mg_ptq<3, double, false, 32>), rap_grid, kBlock, 0, w.L, nx.L, (double const*) w.pval, (int32_t const*) qcol, (double const*) qval, target, nc));
 					}
 
 					if (rc == 0 && (BFMG_CHECK(cudaMemcpyAsync(&overflow, bad + 8, sizeof overflow, cudaMemcpyDeviceToHost, bfmg_stream())) < 0 || BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0)) {
