@@ -59,6 +59,7 @@ struct Scalars {
 	double rr;      /* r.r of the current residual (the convergence measure; equals rho without a coarse level) */
 	double xx;      /* ||x^||^2 of the solution accumulated since the last refinement (one GPU) */
 	double floor2;  /* > 0: refinement armed - done = 4 once r.r <= floor2 * xx (the residual has reached FP64's floor) */
+	double floor2_late; /* the at-the-floor threshold a refinement re-arms with (floor2 may start out as the early one of the replacement) */
 	double part;                       /* this rank's share of the reduction in flight */
 	double gath[BFMG_DIST_MAX_RANKS];  /* every rank's share, in rank order */
 
@@ -432,7 +433,7 @@ __global__ void k_share(Scalars* S, int arm_again) {
 		S->rho = total[0];
 		S->rr = total[0];
 		S->xx = 0;
-		S->floor2 = arm_again ? S->floor2 : 0;
+		S->floor2 = (arm_again & 1) ? S->floor2_late : 0;
 		S->done = !(total[0] == total[0]) ? 2 : (total[0] <= S->tol2 * S->bnorm2 ? 1 : (S->iter >= S->max_iter ? 3 : 0));
 	}
 
@@ -922,10 +923,13 @@ __global__ void __launch_bounds__(kBlock) k_residual_dd(
 		}
 
 		else if (REFINE) {
-			S->rho = total;
+			if (!(arm_again & 2)) { /* bit 1: residual replacement - the search direction and its rho = r.z live on */
+				S->rho = total;
+			}
+
 			S->rr = total;
 			S->xx = 0;
-			S->floor2 = arm_again ? S->floor2 : 0;
+			S->floor2 = (arm_again & 1) ? S->floor2_late : 0;
 			S->done = !(total == total) ? 2 : (total <= S->tol2 * S->bnorm2 ? 1 : (S->iter >= S->max_iter ? 3 : 0));
 		}
 
@@ -1341,6 +1345,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		 * chunk late, so launches after convergence are wasted - 64 cheap iterations, or 8 multigrid ones */
 		int const chunk = opts->chunk > 0 ? opts->chunk : (use_mg ? 8 : 64);
 		int refinements = 0;
+		int replacements = 0;
 		bool have_base = false; /* d_x holds the solution accumulated before the last refinement */
 
 		{
@@ -1357,9 +1362,20 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		 * double-double arithmetic (k_residual_dd) and CG restarts on it with a fresh accumulator for the
 		 * correction; the stopping test stays ||r|| <= tol ||b^||.  Costs ~5 % more iterations (the restart loses
 		 * the Krylov space) and brings the displacements within ~1e-13 of the exact solve (tests: SuperLU with
-		 * extended-precision refinement at 0.1 / 0.5 / 2 M DOF).  BFM_CG_REFINE=0 switches it off. */
+		 * extended-precision refinement at 0.1 / 0.5 / 2 M DOF).  BFM_CG_REFINE=0 switches it off.
+		 *
+		 * Residual replacement before that (one GPU): the restart is what costs - ~11 of 73 iterations at 50 M DOF.
+		 * Replacing the residual WITHOUT restarting - same search direction, same rho - is free of that, but only
+		 * while the jump it makes in r (the drift of the recursion so far, ~eps |A^| |x^| sqrt(k)) is small against r
+		 * itself: done at the floor it stalls CG for good (measured in the numpy twin: 400+ iterations at phi = 6 ..
+		 * 300 eps ||x^||, 91 at 1 000, 59-62 = no penalty at 3 000 .. 30 000), and a second one is never safe (folding
+		 * the accumulator into x rounds at eps ||x||, the very floor).  So the first event is a replacement at
+		 * r.r <= (1e4 eps)^2 x^.x^ that keeps p; from there on the accumulator holds only the correction and the
+		 * recursion's floor drops with it; the at-the-floor restart above stays armed behind it for the case that the
+		 * correction reaches its own floor before the tolerance.  BFM_CG_REPLACE=0 switches the replacement off. */
 
 		int max_refinements = 0;
+		bool replace_first = false; /* the next refinement event is the early replacement */
 
 		if (use_mg) {
 			char const* const env = getenv("BFM_CG_REFINE");
@@ -1367,15 +1383,25 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 			max_refinements = env != nullptr ? atoi(env) : 2;
 
 			if (max_refinements > 0) {
+				char const* const env_rep = getenv("BFM_CG_REPLACE");
+
+				replace_first = !shared && (env_rep == nullptr || atoi(env_rep) != 0);
+
 				/* measured on the plates: the recursion drifts from the true residual by ~2.2 eps ||x^|| (2e-6 ||b^|| at
 				 * 50 M DOF, 7e-8 at 2 M); refine when the residual is within 3x of that - later the iterations are
 				 * wasted on noise, earlier the correction is large enough to hit its own floor and need a second restart
 				 * (each restart costs the ~15 iterations it takes to rebuild the Krylov space) */
 				char const* const env_phi = getenv("BFM_CG_REFINE_AT");
 				double const phi = (env_phi != nullptr && atof(env_phi) > 0 ? atof(env_phi) : 6.0) * 2.220446049250313e-16;
-				double const floor2 = phi * phi;
+				char const* const env_early = getenv("BFM_CG_REPLACE_AT");
+				double const phi_early = (env_early != nullptr && atof(env_early) > 0 ? atof(env_early) : 1.0e4) * 2.220446049250313e-16;
+				double const floors[2] = {replace_first ? phi_early * phi_early : phi * phi, phi * phi};
 
-				if (BFMG_CHECK(cudaMemcpyAsync(&S->floor2, &floor2, sizeof floor2, cudaMemcpyHostToDevice, bfmg_stream())) < 0 || BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0) {
+				if (
+					BFMG_CHECK(cudaMemcpyAsync(&S->floor2, &floors[0], sizeof(double), cudaMemcpyHostToDevice, bfmg_stream())) < 0 ||
+					BFMG_CHECK(cudaMemcpyAsync(&S->floor2_late, &floors[1], sizeof(double), cudaMemcpyHostToDevice, bfmg_stream())) < 0 ||
+					BFMG_CHECK(cudaStreamSynchronize(bfmg_stream())) < 0
+				) {
 					goto out;
 				}
 			}
@@ -1481,17 +1507,24 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 				break;
 			}
 
-			/* the recursion has reached FP64's floor: refine on the original system and go on */
+			/* the recursion has reached FP64's floor: refine on the original system and go on - or, the first time on
+			 * one GPU, has come within 1e4 of it: replace the residual and keep the search direction */
 
-			refinements++;
+			bool const keep = replace_first;
+
+			replace_first = false;
+			replacements += keep;
+			refinements += !keep;
+
+			int const arm = (keep ? 2 : 0) | ((keep || refinements < max_refinements) ? 1 : 0);
 
 			bool const ok = (have_base
 				? BFMG_LAUNCH((k_unscale<true, true>), (n_own + kBlock - 1) / kBlock, kBlock, 0, n_own, dscale + lo, xhat + lo, (double2*) d_x + lo)
 				: BFMG_LAUNCH((k_unscale<false, true>), (n_own + kBlock - 1) / kBlock, kBlock, 0, n_own, dscale + lo, xhat + lo, (double2*) d_x + lo)) == 0 &&
 				HALO(d_x, false) &&
-				BFMG_LAUNCH(k_residual_dd<true>, G.spmv, kBlock, 0, *pat, vtop, vbot, (double2 const*) d_b, (double2 const*) d_x, dscale, r, partials, S, refinements < max_refinements ? 1 : 0) == 0 &&
-				(!shared || BFMG_LAUNCH(k_share<kShareRefine>, 1, 1, 0, S, refinements < max_refinements ? 1 : 0) == 0) &&
-				MG_PRECONDITION(true);
+				BFMG_LAUNCH(k_residual_dd<true>, G.spmv, kBlock, 0, *pat, vtop, vbot, (double2 const*) d_b, (double2 const*) d_x, dscale, r, partials, S, arm) == 0 &&
+				(!shared || BFMG_LAUNCH(k_share<kShareRefine>, 1, 1, 0, S, arm) == 0) &&
+				(keep ? MG_PRECONDITION(false) : MG_PRECONDITION(true));
 
 			if (!ok) {
 				goto out;
@@ -1503,7 +1536,7 @@ int bfmg_pcg(bfmg_pattern_t const* pat, double const* d_val, double const* d_b, 
 		res->iterations = last.iter;
 		res->rel_residual = last.bnorm2 > 0 ? sqrt(last.rr / last.bnorm2) : 0;
 		res->converged = last.done == 1 ? 1 : (last.done == 3 ? 0 : -1);
-		res->restarts = refinements;
+		res->restarts = refinements + replacements;
 
 		/* the solution in the reference's variables: x = D^-1/2 x^ (+ what was accumulated before a refinement) */
 
