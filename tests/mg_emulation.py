@@ -147,3 +147,67 @@ class Emulation:
 			rho = rz
 
 		return self.dscale * x, max_iter
+
+
+def residual_extended(A, b, x):
+	"""b - A x with the products and sums in extended precision (x86 long double: what k_residual_dd's double-double
+	arithmetic buys on the device), rounded to double at the end"""
+
+	prod = A.data.astype(np.longdouble) * x.astype(np.longdouble)[A.indices]
+	sums = np.add.reduceat(prod, A.indptr[:-1])
+	sums[np.diff(A.indptr) == 0] = 0
+
+	return (b.astype(np.longdouble) - sums).astype(np.float64)
+
+
+def solve_refined(emu: Emulation, A, b, mode: str, phi: float, tol=1e-12, max_iter=200, max_events=4):
+	"""PCG on the scaled system as solver.cu runs it, with its two ways of getting below FP64's residual floor:
+
+	mode "none"      plain PCG;
+	mode "restart"   once r.r <= (phi eps)^2 x^.x^: fold the accumulator into x, recompute the residual of the ORIGINAL
+	                 system in extended precision, restart CG on it (solver.cu at phi = 6);
+	mode "replace"   the same, but the search direction and rho survive (solver.cu's early replacement at phi = 1e4).
+
+	Returns (x, iterations, events)."""
+
+	eps = np.finfo(np.float64).eps
+	Ah, ds = emu.ops[0], emu.dscale
+	bh = ds * b
+	bnorm = np.linalg.norm(bh)
+	base = np.zeros_like(b)
+	xh = np.zeros_like(bh)
+	r = bh.copy()
+	z = emu.cycle(0, r)
+	p = z.copy()
+	rho = r @ z
+	events = 0
+	it = 0
+
+	for it in range(1, max_iter + 1):
+		q = Ah @ p
+		alpha = rho / (p @ q)
+		xh += alpha * p
+		r -= alpha * q
+		rr = r @ r
+
+		if np.sqrt(rr) <= tol * bnorm:
+			break
+
+		if mode != "none" and events < max_events and rr <= (phi * eps) ** 2 * (xh @ xh):
+			events += 1
+			base = base + ds * xh
+			xh[:] = 0
+			r = ds * residual_extended(A, b, base)
+
+			if mode == "restart":
+				z = emu.cycle(0, r)
+				p = z.copy()
+				rho = r @ z
+				continue
+
+		z = emu.cycle(0, r)
+		rz = r @ z
+		p = z + (rz / rho) * p
+		rho = rz
+
+	return base + ds * xh, it, events

@@ -138,3 +138,41 @@ def test_hierarchy_info_counts_prolongator_entries(lib, monkeypatch):
 
 	assert counts["0"] == (case.mesh.n_nodes, case.mesh.n_nodes)
 	assert counts["1"] == (case.mesh.n_nodes, want) and want > 2 * case.mesh.n_nodes
+
+
+def test_emulated_refinement_window(lib, monkeypatch):
+	"""solver.cu's two ways below FP64's residual floor, in the numpy twin on a 0.18 M-DOF plate (at 0.5 M DOF the same
+	experiment gives 2.7e-9 / 5.9e-15 / 1.3e-14 in 59 / 67 / 59 iterations): plain PCG stops 1e-10 short of the exact
+	solution however small its recursive residual; the restart at the floor (phi = 6) gets to 1e-15 and pays iterations for
+	the lost Krylov space; replacing the residual while KEEPING the search direction is free at phi = 1e4 - and stalls CG
+	when done at the floor, which is why the device does it early and only once"""
+
+	import scipy.sparse.linalg as spla
+
+	monkeypatch.setenv("BFM_MG_SMOOTH", "1")
+
+	case = cases.build("plate_600x150", lib)
+	levels = mg_emulation.hierarchy(lib, case.mesh)
+	system = cases.oracle_problem(case).system()
+	A, b = system.scipy().tocsr(), system.b.copy()
+
+	lu = spla.splu(A.tocsc())
+	exact = lu.solve(b)
+
+	for _ in range(3):
+		exact = exact + lu.solve(mg_emulation.residual_extended(A, b, exact))
+
+	emu = mg_emulation.Emulation(A, levels, smooth=True)
+	err = lambda x: float(np.linalg.norm(x - exact) / np.linalg.norm(exact))
+
+	x, plain_its, _ = mg_emulation.solve_refined(emu, A, b, "none", 0)
+	assert 1e-11 < err(x) < 1e-8          # the floor
+
+	x, restart_its, events = mg_emulation.solve_refined(emu, A, b, "restart", 6)
+	assert err(x) < 1e-13 and events == 1 and restart_its >= plain_its + 2
+
+	x, replace_its, events = mg_emulation.solve_refined(emu, A, b, "replace", 1e4, max_events=1)
+	assert err(x) < 1e-13 and events == 1 and replace_its <= plain_its + 1
+
+	x, stalled_its, _ = mg_emulation.solve_refined(emu, A, b, "replace", 6, max_iter=150, max_events=1)
+	assert stalled_its == 150
