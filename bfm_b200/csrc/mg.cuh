@@ -23,7 +23,7 @@
  *   z += P cycle_{l+1}(P^T t)     restriction, recursion (gamma visits: V- or W-cycle), prolongation
  *   z += w (g - A z)              one fused SpMV (kPost); on level 0 it also leaves r.z for CG
  *
- * with w = 1.8 / (largest absolute row sum): a Gershgorin bound of the largest eigenvalue, so w lambda_max < 2
+ * with w = 1.9 / (largest absolute row sum): a Gershgorin bound of the largest eigenvalue, so w lambda_max < 2
  * always holds and the smoother - hence the whole cycle - is symmetric positive definite.  The preconditioner
  * changes how fast CG converges, not what it converges to: the stopping test stays on the true CG residual.
  *
@@ -1113,7 +1113,8 @@ struct MgRun {
 	double* dmu = nullptr;  /* its solution [nc] */
 	int32_t* bad = nullptr;
 
-	double omega_factor = 1.8;
+	double omega_factor = 1.9;        /* Jacobi damping: w = omega_factor / (row-sum bound) < 2 / lambda_max whatever the matrix (BFM_MG_OMEGA);
+	                                   * 1.8 -> 1.9: 72 -> 67 iterations at 50 M DOF */
 	bool rap_two_step = true;         /* BFM_MG_RAP=direct: the one-step Galerkin kernel for smoothed prolongators too */
 	double smooth_factor = 1.8;       /* prolongator smoothing: w = smooth_factor / (row-sum bound), BFM_MG_SMOOTH_OMEGA.  The bound is
 	                                   * Gershgorin's, ~1.4x the largest eigenvalue on these operators: 1.8 / bound ~ the classic 4 / (3 lambda_max) */

@@ -63,7 +63,7 @@ def tentative(level, dofs, sq):
 
 
 class Emulation:
-	def __init__(self, A, levels, gamma=None, omega=1.8, single_precision_p=True, smooth=False, smooth_omega=1.8):
+	def __init__(self, A, levels, gamma=None, omega=1.9, single_precision_p=True, smooth=False, smooth_omega=1.8):
 		"""A: the assembled matrix (scipy, DOFs interleaved per node); levels: hierarchy().  smooth: smoothed aggregation
 		as k_mg_smooth does it on one GPU - P = (I - w A^) P~ on every level, w = smooth_omega / (largest absolute row
 		sum) - with a V-cycle unless gamma says otherwise (the tentative prolongator needs the W-cycle)"""
