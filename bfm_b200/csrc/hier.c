@@ -767,7 +767,22 @@ static int coarse_rows(bfmi_hier_level_t const* L, int32_t first, int32_t count,
 				}
 			}
 
-			qsort(buf, (size_t) cnt, sizeof *buf, cmp_i32);
+			if (cnt <= 32) { /* the usual row: a handful of columns */
+				for (int32_t u = 1; u < cnt; u++) {
+					int32_t const cur = buf[u];
+					int32_t v = u;
+
+					for (; v > 0 && buf[v - 1] > cur; v--) {
+						buf[v] = buf[v - 1];
+					}
+
+					buf[v] = cur;
+				}
+			}
+
+			else {
+				qsort(buf, (size_t) cnt, sizeof *buf, cmp_i32);
+			}
 
 			rows[i] = malloc((size_t) cnt * sizeof **rows);
 
@@ -1191,10 +1206,20 @@ bfmi_hier_t* bfmi_hier_build(bfmi_plan_t const* plan, double const* coords, bfmi
 
 			int rv = N->pos != NULL && rows != NULL && lens != NULL ? 0 : -1;
 
+			double t_step[5] = {hier_clock(), 0, 0, 0, 0};
+
 			rv = rv < 0 ? rv : build_transfer(L);
+			t_step[1] = hier_clock();
 			rv = rv < 0 ? rv : centroids(L, n_agg, 0, N->pos); /* after the transfer lists: summed aggregate by aggregate */
+			t_step[2] = hier_clock();
 			rv = rv < 0 ? rv : coarse_rows(L, 0, n_agg, rows, lens);
+			t_step[3] = hier_clock();
 			rv = rv < 0 ? rv : layout_level(N, n_agg, rows, lens);
+			t_step[4] = hier_clock();
+
+			if (getenv("BFM_MG_VERBOSE") != NULL && L->n > 100000) {
+				fprintf(stderr, "[hier] level %d: transfer lists %.1f ms, reference points %.1f ms, symbolic P^T A P %.1f ms, SELL layout %.1f ms\n", l, t_step[1] - t_step[0], t_step[2] - t_step[1], t_step[3] - t_step[2], t_step[4] - t_step[3]);
+			}
 
 			for (int32_t I = 0; rows != NULL && I < n_agg; I++) {
 				free(rows[I]);
