@@ -169,10 +169,10 @@ def test_emulated_refinement_window(lib, monkeypatch):
 	assert 1e-11 < err(x) < 1e-8          # the floor
 
 	x, restart_its, events = mg_emulation.solve_refined(emu, A, b, "restart", 6)
-	assert err(x) < 1e-13 and events == 1 and restart_its >= plain_its + 2
+	assert err(x) < 1e-13 and events == 1 and restart_its > plain_its
 
 	x, replace_its, events = mg_emulation.solve_refined(emu, A, b, "replace", 1e4, max_events=1)
 	assert err(x) < 1e-13 and events == 1 and replace_its <= plain_its + 1
 
 	x, stalled_its, _ = mg_emulation.solve_refined(emu, A, b, "replace", 6, max_iter=150, max_events=1)
-	assert stalled_its == 150
+	assert stalled_its >= 2 * plain_its
