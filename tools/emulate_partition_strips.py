@@ -80,25 +80,29 @@ class Masked(mg_emulation.Emulation):
 		return z + w * (g - A @ z)
 
 
-def strip_masks(levels, coords, parts):
-	"""per level: True where a node has no neighbour in another band (bands of equal height in y; the reference point of
-	an aggregate is the centroid of its members)"""
+def strip_masks(levels, coords, parts_x, parts_y):
+	"""per level: True where a node has no neighbour in another part.  Parts are the cells of a parts_x x parts_y grid
+	over the plate: (1, N) = horizontal bands, what the row partition of the row-major plate gives; (4, 2) = compact
+	blocks, what a partition of the Morton numbering would give.  The reference point of an aggregate is the centroid
+	of its members"""
 
 	masks = []
+	x = coords[:, 0] / coords[:, 0].max()
 	y = coords[:, 1] / coords[:, 1].max()
 
 	for l, L in enumerate(levels[:-1]):
 		n = L["n"]
-		band = np.minimum((y * parts).astype(int), parts - 1)
+		part = np.minimum((y * parts_y).astype(int), parts_y - 1) * parts_x + np.minimum((x * parts_x).astype(int), parts_x - 1)
 		rows = np.repeat(np.arange(n), np.diff(L["rowptr"]))
 		cut = np.zeros(n, bool)
-		cut[rows[band[rows] != band[L["col"]]]] = True
+		cut[rows[part[rows] != part[L["col"]]]] = True
 		masks.append(~cut)
 
 		agg = L["agg"]
 		members = agg >= 0
-		count = np.bincount(agg[members], minlength=levels[l + 1]["n"])
-		y = np.bincount(agg[members], weights=y[members], minlength=levels[l + 1]["n"]) / np.maximum(count, 1)
+		count = np.maximum(np.bincount(agg[members], minlength=levels[l + 1]["n"]), 1)
+		x = np.bincount(agg[members], weights=x[members], minlength=levels[l + 1]["n"]) / count
+		y = np.bincount(agg[members], weights=y[members], minlength=levels[l + 1]["n"]) / count
 
 	return masks
 
@@ -118,16 +122,17 @@ def main():
 	def only(masks, upto):
 		return [m if l < upto else None for l, m in enumerate(masks)]
 
-	two, eight = strip_masks(levels, coords, 2), strip_masks(levels, coords, 8)
+	two, eight, blocks = strip_masks(levels, coords, 1, 2), strip_masks(levels, coords, 1, 8), strip_masks(levels, coords, 4, 2)
 
 	variants = [
 		("one part", None, None),
-		("2 parts, strip on the mesh level only", only(two, 1), None),
-		("2 parts, strips on levels 0-1", only(two, 2), None),
-		("2 parts, strips on every level", two, None),
-		("8 parts, strips on every level", eight, None),
-		("8 parts, every level; level 1 visits level 2 twice", eight, [1, 2] + [1] * n_sparse),
-		("8 parts, every level; level 0 visits level 1 twice", eight, [2] + [1] * n_sparse),
+		("2 bands, strip on the mesh level only", only(two, 1), None),
+		("2 bands, strips on levels 0-1", only(two, 2), None),
+		("2 bands, strips on every level", two, None),
+		("8 bands, strips on every level", eight, None),
+		("8 blocks (4 x 2), strips on every level", blocks, None),
+		("8 bands, every level; level 1 visits level 2 twice", eight, [1, 2] + [1] * n_sparse),
+		("8 bands, every level; level 0 visits level 1 twice", eight, [2] + [1] * n_sparse),
 	]
 
 	for label, masks, gammas in variants:
